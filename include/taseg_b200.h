@@ -1,0 +1,231 @@
+/*
+ * taseg_b200 — C ABI of the B200-native (sm_100a) sparse-convolution hot path of LittlePey/TASeg.
+ *
+ * Drop-in boundary.  The reference reaches its native code through a pybind11 module
+ * `torchsparse.backend` (TS/torchsparse/backend/pybind_cuda.cpp:18-39, TS = torchsparse/ inside
+ * /root/reference/package/torchsparse.zip) whose functions take at::Tensor by value.  This library
+ * replaces that module with plain C entry points: raw DEVICE pointers, explicit sizes, a dtype enum
+ * and the CUDA stream; every function returns a tsg_status.  No torch type appears here.
+ *
+ * Ownership.  The library never allocates or frees device memory: outputs and workspaces are owned by
+ * the caller (the Python host uses torch's caching allocator).  `*_ws_bytes` functions size workspaces.
+ * All work is enqueued on `stream`; no function synchronises the device or the host.
+ * Data-dependent sizes (number of unique voxels, map pairs) are written to caller-provided device
+ * counters so the host decides when to read them.
+ *
+ * Coordinates are int32 rows [x, y, z, b] (TS/torchsparse/utils/collate.py:28-33).
+ * Exact-coordinate tables require -2^18 <= x,y,z < 2^18 and 0 <= b < 128 (packed 64-bit keys);
+ * a violation raises bit 0 of the caller's `status` word on the device (TSG_ERR_RANGE when read back).
+ */
+#ifndef TASEG_B200_H
+#define TASEG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st *tsg_stream_t;
+
+typedef enum {
+  TSG_OK = 0,
+  TSG_ERR_INVALID = 1,     /* shape/argument mismatch: the reference throws std::invalid_argument
+                              (convolution_cuda.cu:57-59) -> Python ValueError */
+  TSG_ERR_CUDA = 2,        /* a CUDA runtime call failed; tsg_last_error() has the string */
+  TSG_ERR_WORKSPACE = 3,   /* workspace too small */
+  TSG_ERR_RANGE = 4,       /* coordinate outside the packable range */
+  TSG_ERR_UNSUPPORTED = 5  /* shape not supported by this kernel (e.g. channels not padded) */
+} tsg_status;
+
+typedef enum { TSG_F32 = 0, TSG_BF16 = 1, TSG_F16 = 2 } tsg_dtype;
+
+/* epilogue flags for the convolution entry points */
+enum { TSG_EPI_BIAS = 1, TSG_EPI_RELU = 2, TSG_EPI_RESIDUAL = 4, TSG_EPI_ACCUMULATE = 8 };
+
+int tsg_version(void);
+const char *tsg_last_error(void); /* thread-local, valid until the next call on this thread */
+
+/* ---------------------------------------------------------------- hashing
+ * tsg_hash        replaces hash_cuda(idx)                    TS/backend/hash/hash_cuda.h:5,  hash_cuda.cu:10-23,67-73
+ * tsg_kernel_hash replaces kernel_hash_cuda(idx, offsets)    hash_cuda.h:6-7, hash_cuda.cu:27-55,75-84
+ * 64-bit FNV-1a over the four 32-bit words, folded to 60 bits; out is int64 (K x N for the kernel form,
+ * every row keeps its own batch index).  `offsets` is a DEVICE (K,3) int32 array. */
+int tsg_hash(const int32_t *coords, int64_t n, int64_t *out, tsg_stream_t stream);
+int tsg_kernel_hash(const int32_t *coords, int64_t n, const int32_t *offsets, int k, int64_t *out,
+                    tsg_stream_t stream);
+
+/* ---------------------------------------------------------------- key -> index tables (a9)
+ * Open-addressing table of 16-byte slots {uint64 key, int32 value}; `slots` must be a power of two
+ * >= 2n (tsg_table_slots).  Replaces CuckooHashTableCuda_Multi (TS/backend/hashmap/hashmap_cuda.cu:139-212)
+ * and hash_query_cuda(hash_query, hash_target, idx_target) (TS/backend/others/query_cuda.h:5-7,
+ * query_cuda.cu:9-56): value = position of the key in `keys`; on duplicate keys the SMALLEST position wins
+ * (the CPU reference's insert-first behaviour, query_cpu.cpp:22-26).  The table is built once and reused
+ * for every query against the same key set (the reference rebuilds it on every call).
+ * tsg_table_query writes position or -1 (the "-1 = miss" the Python wrapper produces, TS/nn/functional/query.py:32). */
+int64_t tsg_table_slots(int64_t n);
+int tsg_table_build(const int64_t *keys, int64_t n, void *table, int64_t slots, tsg_stream_t stream);
+int tsg_table_query(const void *table, int64_t slots, const int64_t *queries, int64_t nq, int64_t *out,
+                    tsg_stream_t stream);
+
+/* Exact-coordinate table: keys are the packed (b,x,y,z) themselves, not their hash (no collisions). */
+int tsg_coord_table_build(const int32_t *coords, int64_t n, void *table, int64_t slots, int32_t *status,
+                          tsg_stream_t stream);
+
+/* ---------------------------------------------------------------- kernel maps (a15, a17; K2+K4+nonzero+sum fused)
+ * For every output voxel o and kernel offset k, nbr[k*n_out + o] = row of in-voxel at out_coords[o]+offsets[k],
+ * or -1.  `offsets` is a HOST (K,3) int32 array in the reference's weight order
+ * (get_kernel_offsets, TS/nn/utils/kernel.py:11-32), already scaled by tensor stride and dilation; K <= 32.
+ * nbsizes[k] (device int32, K) = number of hits for offset k (TS/nn/functional/conv.py:168).
+ * blockcnt (device int32, K * tsg_kmap_blocks(n_out)) are per-1024-row hit counts, consumed by tsg_kmap_pairs. */
+int64_t tsg_kmap_blocks(int64_t n_out);
+int tsg_kmap_build(const void *table, int64_t slots, const int32_t *out_coords, int64_t n_out,
+                   const int32_t *offsets_host, int k, int32_t *nbr, int32_t *nbsizes, int32_t *blockcnt,
+                   tsg_stream_t stream);
+/* Reference-format map: nbmaps (P,2) int64 rows [in_idx, out_idx], grouped by k, ascending out_idx
+ * (TS/nn/functional/conv.py:169-172).  P = sum(nbsizes) must be known by the caller (it sized nbmaps). */
+int tsg_kmap_pairs(const int32_t *nbr, int k, int64_t n_out, int32_t *blockcnt, int64_t *nbmaps,
+                   tsg_stream_t stream);
+/* Transposed table for dgrad / transposed convolution: nbr_t[k*n_in + i] = o where nbr[k*n_out+o] == i, else -1. */
+int tsg_kmap_transpose(const int32_t *nbr, int k, int64_t n_out, int64_t n_in, int32_t *nbr_t,
+                       tsg_stream_t stream);
+/* Reference-format pairs -> output-stationary table (for callers that hold torchsparse kmaps):
+ * nbmaps (P,2) int32 [in,out], nbsizes HOST (K) int32 (the reference passes nbsizes.cpu(), conv.py:56). */
+int tsg_kmap_from_pairs(const int32_t *nbmaps, const int32_t *nbsizes_host, int k, int transposed,
+                        int64_t n_rows_out, int32_t *nbr, tsg_stream_t stream);
+
+/* ---------------------------------------------------------------- sort / unique (a5, a12, a16)
+ * Stable LSD radix sort of 64-bit keys with a 32-bit payload (payload = 0..n-1 when vals_in is NULL).
+ * Results land in keys_out/vals_out.  ws: tsg_sort_ws_bytes(n). */
+size_t tsg_sort_ws_bytes(int64_t n);
+int tsg_sort_pairs(const uint64_t *keys_in, const uint32_t *vals_in, int64_t n, int begin_bit, int end_bit,
+                   uint64_t *keys_out, uint32_t *vals_out, void *ws, size_t ws_bytes, tsg_stream_t stream);
+
+/* Unique voxels of a coordinate list, ordered lexicographically by (b, x, y, z):
+ *   sparse_quantize + sparse_collate   TS/utils/quantize.py:24-46, TS/utils/collate.py:11-37
+ *   spdownsample (after truncation)    TS/nn/functional/downsample.py:47-52
+ * in_coords (N,4) [x,y,z,b]; if trunc_stride > 0 every x,y,z is first truncated toward zero to a multiple of it
+ * (downsample.py:27-29).  Outputs (any may be NULL): out_coords (<=N,4), first_idx (<=N) = first occurrence in
+ * input order, inverse (N) = voxel row of every input point; *m_dev = number of unique voxels. */
+size_t tsg_unique_ws_bytes(int64_t n);
+int tsg_unique_coords(const int32_t *in_coords, int64_t n, int trunc_stride, int32_t *out_coords,
+                      int32_t *first_idx, int32_t *inverse, int32_t *m_dev, int32_t *status, void *ws,
+                      size_t ws_bytes, tsg_stream_t stream);
+/* Unique by ascending 60-bit FNV hash — the voxel order of initial_voxelize
+ * (R/pcseg/model/segmentor/voxel/minkunet/utils.py:17-18: torch.unique(pc_hash)). */
+int tsg_unique_hash(const int32_t *in_coords, int64_t n, int32_t *out_coords, int32_t *first_idx,
+                    int32_t *inverse, int32_t *m_dev, void *ws, size_t ws_bytes, tsg_stream_t stream);
+
+/* ---------------------------------------------------------------- multi-frame aggregation + quantisation (a1-a4)
+ * tsg_fuse_multi_scan replaces SemantickittiMsDataset.fuse_multi_scan
+ * (R/pcseg/data/dataset/semantickitti/semantickitti_ms.py:403-417): p' = ((P.[p;1])_xyz - t0) . R0 in fp32,
+ * products rounded before left-to-right sums (no FMA) — bit exact with numpy.  pose0/pose: HOST float[16]
+ * row-major 4x4.  pts/out (N,c) fp32, c >= 3, extra columns copied. */
+int tsg_fuse_multi_scan(const float *pts, int64_t n, int c, const float *pose0, const float *pose, float *out,
+                        tsg_stream_t stream);
+/* nuScenes warp (R/pcseg/data/dataset/nuscenes/nuscenes_ms.py:371): xyz = fp32(fp64(xyz) @ R + T); R (3,3), T (3) HOST double. */
+int tsg_transform_point(const float *pts, int64_t n, int c, const double *R, const double *T, float *out,
+                        tsg_stream_t stream);
+
+/* Whole-batch aggregation front end (semantickitti_ms.py:140-149,253-257,263-320 + semantickitti_voxel_ms.py:121-151).
+ * `frames` describes F frames laid out back to back in `pts` (sum n, c_in) fp32:
+ *   sample  batch index b of the frame
+ *   is_cur  1 for the current scan of its sample (listed first within the sample), 0 for history
+ *   pose0/pose  float[16] each (ignored for is_cur)
+ * For every point: warp (history only), append the time flag column (1 current / 0 history) after column 3,
+ * apply the optional keep mask (FSA, `keep` (sum n) uint8 or NULL), clamp history to the current scan's min corner,
+ * quantise round-half-even(xyz / voxel) in fp32, shift by the per-sample min over kept points.
+ * Outputs: feats (sum n, c_in+1), coords (sum n,4) [x,y,z,b], flags (sum n) uint8 = kept.
+ * ws: tsg_aggregate_ws_bytes(n_samples). */
+typedef struct {
+  int64_t offset, count;
+  int32_t sample, is_cur;
+  float pose0[16], pose[16];
+} tsg_frame;
+size_t tsg_aggregate_ws_bytes(int n_samples);
+int tsg_aggregate_quantize(const float *pts, int c_in, const tsg_frame *frames_host, int n_frames, int n_samples,
+                           const uint8_t *keep, float voxel_size, float *feats, int32_t *coords, uint8_t *flags,
+                           void *ws, size_t ws_bytes, tsg_stream_t stream);
+/* Stable stream compaction of rows by a uint8 flag: used after tsg_aggregate_quantize.
+ * rows_a (n, wa) and rows_b (n, wb) are 4-byte-element rows (either may be NULL); *m_dev = rows kept;
+ * pos (n) int32 = destination row or -1.  ws: tsg_compact_ws_bytes(n). */
+size_t tsg_compact_ws_bytes(int64_t n);
+int tsg_compact_rows(const uint8_t *flags, int64_t n, const void *rows_a, int wa, void *out_a, const void *rows_b,
+                     int wb, void *out_b, int32_t *pos, int32_t *m_dev, void *ws, size_t ws_bytes,
+                     tsg_stream_t stream);
+/* out[i, :] = src[idx[i], :] for 4-byte-element rows (feature pick of voxel representatives, logits to points). */
+int tsg_gather_rows(const void *src, int width, const int32_t *idx, int64_t n, void *out, tsg_stream_t stream);
+
+/* ---------------------------------------------------------------- point <-> voxel (a10-a14)
+ * tsg_count replaces count_cuda(idx, s)                                   TS/backend/others/count_cuda.h:5
+ * tsg_voxelize_fwd/bwd replace voxelize_forward_cuda / voxelize_backward_cuda   TS/backend/voxelize/voxelize_cuda.h:5-10
+ * tsg_devoxelize_fwd/bwd replace devoxelize_forward_cuda / _backward_cuda        TS/backend/devoxelize/devoxelize_cuda.h:5-11
+ * feats are (rows, c) of `dtype`; accumulation is fp32. */
+int tsg_count(const int32_t *idx, int64_t n, int32_t *out, int64_t m, tsg_stream_t stream);
+int tsg_voxelize_fwd(const void *feats, int dtype, const int32_t *idx, const int32_t *counts, int64_t n, int c,
+                     int64_t m, void *out, float *acc_ws, tsg_stream_t stream);
+int tsg_voxelize_bwd(const void *top_grad, int dtype, const int32_t *idx, const int32_t *counts, int64_t n, int c,
+                     void *bottom_grad, tsg_stream_t stream);
+int tsg_devoxelize_fwd(const void *feats, int dtype, const int32_t *idx8, const float *w8, int64_t n, int c,
+                       void *out, tsg_stream_t stream);
+int tsg_devoxelize_bwd(const void *top_grad, int dtype, const int32_t *idx8, const float *w8, int64_t n, int c,
+                       int64_t m, void *bottom_grad, float *acc_ws, tsg_stream_t stream);
+/* Fused point->voxel lookups on an exact-coordinate table built over the voxels of tensor stride s:
+ *   tsg_point_query      idx[i] = row of voxel floor(p/s)*s                 (point_to_voxel, minkunet/utils.py:44-51)
+ *   tsg_trilinear_query  idx8/w8 = 8 corner rows + calc_ti_weights          (voxel_to_point, minkunet/utils.py:72-85;
+ *                                                                            TS/nn/functional/devoxelize.py:10-48)
+ * pcoords (N,4) fp32 [x,y,z,b].  Corner order = get_kernel_offsets(2, s): z fastest. */
+int tsg_point_query(const void *table, int64_t slots, const float *pcoords, int64_t n, int stride, int32_t *idx,
+                    tsg_stream_t stream);
+int tsg_trilinear_query(const void *table, int64_t slots, const float *pcoords, int64_t n, int stride, int nearest,
+                        int32_t *idx8, float *w8, tsg_stream_t stream);
+/* initial_voxelize front end (minkunet/utils.py:11-16): fc = (C*init_res)/after_res in fp32 (mul then div),
+ * out_f (N,4) fp32 = [fc, b], out_i (N,4) int32 = floor. */
+int tsg_rescale_coords(const float *pcoords, int64_t n, float init_res, float after_res, float *out_f,
+                       int32_t *out_i, tsg_stream_t stream);
+
+/* ---------------------------------------------------------------- sparse convolution (a17-a19)
+ * tsg_conv_fwd replaces convolution_forward_cuda(in_feat, out_feat, kernel, neighbor_map, neighbor_offset, transpose)
+ * (TS/backend/convolution/convolution_cuda.h:5-7, convolution_cuda.cu:53-165):
+ *     out[o,:] = sum_k in[nbr[k,o],:] @ W[k]            (nbr < 0 contributes nothing)
+ * as ONE output-stationary implicit-GEMM launch: no gather/scatter buffers, no per-offset GEMMs, no host sync.
+ * in (n_in, c_in), weight (K, c_in, c_out), out (n_out, c_out): all `dtype`, fp32 accumulate.
+ * Epilogue (eval-mode fusion): out = relu?( acc*scale[c] + bias[c] + residual[o,c] );
+ * scale/bias fp32 (c_out) or NULL, residual same dtype as out or NULL.
+ * Returns TSG_ERR_INVALID when c_in does not match the kernel ("Input feature size and kernel size mismatch"). */
+int tsg_conv_fwd(const void *in, int dtype, int64_t n_in, int c_in, const void *weight, int k, int c_in_w,
+                 int c_out, const int32_t *nbr, int64_t n_out, void *out, const float *scale, const float *bias,
+                 const void *residual, int relu, tsg_stream_t stream);
+/* Backward (convolution_backward_cuda, convolution_cuda.h:9-13, convolution_cuda.cu:167-278):
+ *   dgrad: grad_in[i,:]  = sum_k grad_out[nbr_t[k,i],:] @ W[k]^T      (same kernel, transposed table + weights)
+ *   wgrad: grad_w[k]     = sum_o in[nbr[k,o],:]^T @ grad_out[o,:]
+ * fp32 only (training master precision). */
+int tsg_conv_dgrad(const float *grad_out, int64_t n_out, int c_out, const float *weight, int k, int c_in,
+                   const int32_t *nbr_t, int64_t n_in, float *grad_in, tsg_stream_t stream);
+int tsg_conv_wgrad(const float *in, int64_t n_in, int c_in, const float *grad_out, int64_t n_out, int c_out,
+                   const int32_t *nbr, int k, float *grad_w, tsg_stream_t stream);
+
+/* tcgen05/TMEM path (bf16 operands, fp32 accumulate in tensor memory).
+ * Weights are packed once per layer into the shared-memory image the MMA consumes (128B-swizzled K-major
+ * [c_out][64] blocks per kernel offset and 64-channel slice): tsg_conv_pack_bytes / tsg_conv_pack_weights.
+ * The A operand may come from two feature tensors (channel concat of a decoder feature and its encoder skip,
+ * TS/operators.py:10-17, without materialising the concat): in0 (n_in, c0) then in1 (n_in, c1); c1 may be 0.
+ * c0, c1, c_out multiples of 16; c_out <= 256.  tile_mask (ceil(n_out/128)) uint32 from tsg_kmap_tile_mask.
+ * out dtype TSG_BF16 or TSG_F32. */
+size_t tsg_conv_pack_bytes(int k, int c0, int c1, int c_out);
+int tsg_conv_pack_weights(const float *weight, int k, int c_in, int c_out, int c0, int c1,
+                          const float *out_scale, void *packed, tsg_stream_t stream);
+int tsg_kmap_tile_mask(const int32_t *nbr, int k, int64_t n_out, uint32_t *tile_mask, tsg_stream_t stream);
+int tsg_conv_fwd_tc(const void *in0, int c0, const void *in1, int c1, int64_t n_in, const void *packed_w, int k,
+                    int c_out, const int32_t *nbr, const uint32_t *tile_mask, int64_t n_out, void *out,
+                    int out_dtype, const float *bias, const void *residual, int relu, int num_sms,
+                    tsg_stream_t stream);
+
+/* fp32 -> bf16 with zero padding of the channel dimension to c_pad (first-layer input, 4/5 -> 16 channels). */
+int tsg_cast_pad_bf16(const float *in, int64_t n, int c, int c_pad, void *out, tsg_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TASEG_B200_H */

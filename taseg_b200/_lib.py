@@ -1,0 +1,99 @@
+"""ctypes binding of libtaseg_b200.so — the C ABI declared in include/taseg_b200.h.
+
+The prototypes are parsed from the header itself, so the Python side cannot drift from the contract.
+There is NO fallback: if the shared library is missing the first call raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import re
+from typing import Dict, List, Tuple
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+HEADER = os.path.join(HERE, "..", "include", "taseg_b200.h")
+LIB_PATH = os.path.join(HERE, "libtaseg_b200.so")
+
+TSG_OK, TSG_ERR_INVALID, TSG_ERR_CUDA, TSG_ERR_WORKSPACE, TSG_ERR_RANGE, TSG_ERR_UNSUPPORTED = range(6)
+TSG_F32, TSG_BF16, TSG_F16 = 0, 1, 2
+DTYPES = {torch.float32: TSG_F32, torch.bfloat16: TSG_BF16, torch.float16: TSG_F16}
+
+_SCALARS = {"int": ctypes.c_int, "int32_t": ctypes.c_int32, "int64_t": ctypes.c_int64, "size_t": ctypes.c_size_t,
+            "float": ctypes.c_float, "uint32_t": ctypes.c_uint32, "tsg_stream_t": ctypes.c_void_p}
+
+
+class Frame(ctypes.Structure):
+    """tsg_frame (include/taseg_b200.h)."""
+    _fields_ = [("offset", ctypes.c_int64), ("count", ctypes.c_int64), ("sample", ctypes.c_int32),
+                ("is_cur", ctypes.c_int32), ("pose0", ctypes.c_float * 16), ("pose", ctypes.c_float * 16)]
+
+
+def parse_header(path: str = HEADER) -> Dict[str, Tuple[object, List[object]]]:
+    """name -> (restype, argtypes) for every function declared in the header."""
+    text = open(path).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"^\s*(const char \*|int64_t|size_t|int)\s*(tsg_\w+)\s*\(([^;{]*?)\)\s*;", text, flags=re.M | re.S):
+        ret, name, args = m.group(1).strip(), m.group(2), m.group(3)
+        restype = {"int": ctypes.c_int, "int64_t": ctypes.c_int64, "size_t": ctypes.c_size_t,
+                   "const char *": ctypes.c_char_p}[ret]
+        argtypes = []
+        for a in [x.strip() for x in args.split(",")]:
+            if a in ("void", ""):
+                continue
+            if "*" in a:
+                argtypes.append(ctypes.c_void_p)
+            else:
+                ty = a.replace("const ", "").split()[0]
+                argtypes.append(_SCALARS[ty])
+        protos[name] = (restype, argtypes)
+    return protos
+
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m taseg_b200.build` (there is no CPU or eager fallback)")
+        _lib = ctypes.CDLL(LIB_PATH)
+        for name, (restype, argtypes) in parse_header().items():
+            fn = getattr(_lib, name)
+            fn.restype, fn.argtypes = restype, argtypes
+    return _lib
+
+
+def ptr(t):
+    if t is None:
+        return None
+    if isinstance(t, torch.Tensor):
+        return ctypes.c_void_p(t.data_ptr())
+    return t
+
+
+def stream() -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def check(status: int, what: str = "") -> None:
+    if status == TSG_OK:
+        return
+    msg = lib().tsg_last_error().decode()
+    if status == TSG_ERR_INVALID:
+        raise ValueError(msg or what)       # the reference throws std::invalid_argument -> ValueError
+    raise RuntimeError(f"{what}: status {status}: {msg}")
+
+
+def call(name: str, *args) -> None:
+    check(getattr(lib(), name)(*args), name)
+
+
+def require_cuda(*tensors) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("taseg_b200 runs on CUDA tensors only (no CPU fallback); got a tensor on " + str(t.device))

@@ -1,0 +1,164 @@
+// Shared device/host helpers for the taseg_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/taseg_b200.h"
+
+namespace tsg {
+
+void set_error(const char *fmt, ...);
+
+inline int check_launch(const char *what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return TSG_ERR_CUDA;
+  }
+  return TSG_OK;
+}
+
+#define TSG_CUDA(call)                                               \
+  do {                                                               \
+    cudaError_t e__ = (call);                                        \
+    if (e__ != cudaSuccess) {                                        \
+      tsg::set_error("%s: %s", #call, cudaGetErrorString(e__));      \
+      return TSG_ERR_CUDA;                                           \
+    }                                                                \
+  } while (0)
+
+inline int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+// grid for a grid-stride elementwise kernel: enough CTAs to fill the chip a few times, never more than needed
+inline int grid_for(int64_t work_items, int threads, int ctas_per_sm = 8) {
+  int64_t need = (work_items + threads - 1) / threads;
+  int64_t cap = (int64_t)num_sms() * ctas_per_sm;
+  if (need < 1) need = 1;
+  return (int)(need < cap ? need : cap);
+}
+
+// ------------------------------------------------------------------ coordinate keys
+constexpr int COORD_BITS = 19;
+constexpr int COORD_BIAS = 1 << 18;
+constexpr unsigned long long EMPTY_KEY = ~0ull;
+
+__host__ __device__ inline bool coord_in_range(int x, int y, int z, int b) {
+  return (unsigned)(x + COORD_BIAS) < (1u << COORD_BITS) && (unsigned)(y + COORD_BIAS) < (1u << COORD_BITS) &&
+         (unsigned)(z + COORD_BIAS) < (1u << COORD_BITS) && (unsigned)b < 128u;
+}
+// (b,x,y,z) -> 64-bit key whose unsigned order is the lexicographic order of (b,x,y,z)
+__host__ __device__ inline unsigned long long pack_coord(int x, int y, int z, int b) {
+  return ((unsigned long long)(unsigned)b << 57) | ((unsigned long long)(unsigned)(x + COORD_BIAS) << 38) |
+         ((unsigned long long)(unsigned)(y + COORD_BIAS) << 19) | (unsigned long long)(unsigned)(z + COORD_BIAS);
+}
+__host__ __device__ inline int4 unpack_coord(unsigned long long k) {
+  int4 c;
+  c.w = (int)(k >> 57);
+  c.x = (int)((k >> 38) & ((1u << COORD_BITS) - 1)) - COORD_BIAS;
+  c.y = (int)((k >> 19) & ((1u << COORD_BITS) - 1)) - COORD_BIAS;
+  c.z = (int)(k & ((1u << COORD_BITS) - 1)) - COORD_BIAS;
+  return c;
+}
+
+// reference hash: TS/backend/hash/hash_cuda.cu:10-23
+__host__ __device__ inline long long fnv60(int x, int y, int z, int b) {
+  unsigned long long h = 14695981039346656037ULL;
+  h ^= (unsigned int)x; h *= 1099511628211ULL;
+  h ^= (unsigned int)y; h *= 1099511628211ULL;
+  h ^= (unsigned int)z; h *= 1099511628211ULL;
+  h ^= (unsigned int)b; h *= 1099511628211ULL;
+  h = (h >> 60) ^ (h & 0xFFFFFFFFFFFFFFFULL);
+  return (long long)h;
+}
+
+// ------------------------------------------------------------------ open-addressing table
+struct __align__(16) Slot {
+  unsigned long long key;
+  int val;
+  int pad;
+};
+
+__device__ inline unsigned long long mix64(unsigned long long k) {
+  k ^= k >> 33; k *= 0xff51afd7ed558ccdULL;
+  k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL;
+  k ^= k >> 33;
+  return k;
+}
+
+__device__ inline void table_insert(Slot *tab, unsigned long long mask, unsigned long long key, int val) {
+  unsigned long long s = mix64(key) & mask;
+  while (true) {
+    unsigned long long prev = atomicCAS(&tab[s].key, EMPTY_KEY, key);
+    if (prev == EMPTY_KEY || prev == key) {
+      atomicMin(&tab[s].val, val);
+      return;
+    }
+    s = (s + 1) & mask;
+  }
+}
+
+__device__ inline int table_find(const Slot *__restrict__ tab, unsigned long long mask, unsigned long long key) {
+  unsigned long long s = mix64(key) & mask;
+  while (true) {
+    const ulonglong2 raw = __ldg(reinterpret_cast<const ulonglong2 *>(tab + s));
+    if (raw.x == key) return (int)(unsigned)(raw.y & 0xffffffffull);
+    if (raw.x == EMPTY_KEY) return -1;
+    s = (s + 1) & mask;
+  }
+}
+
+// ------------------------------------------------------------------ block scan (power-of-two block sizes, <=1024)
+template <int THREADS>
+__device__ inline int block_exclusive_scan(int v, int *total) {
+  __shared__ int warp_sums[32];
+  __shared__ int block_total;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) warp_sums[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    int w = lane < THREADS / 32 ? warp_sums[lane] : 0;
+    int winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += t;
+    }
+    if (lane < THREADS / 32) warp_sums[lane] = winc - w;
+    if (lane == 31) block_total = winc;
+  }
+  __syncthreads();
+  int res = inc - v + warp_sums[warp];
+  if (total) *total = block_total;
+  __syncthreads();
+  return res;
+}
+
+// ------------------------------------------------------------------ dtype helpers
+template <typename T> __device__ inline float to_f32(T v);
+template <> __device__ inline float to_f32<float>(float v) { return v; }
+template <> __device__ inline float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <> __device__ inline float to_f32<__half>(__half v) { return __half2float(v); }
+template <typename T> __device__ inline T from_f32(float v);
+template <> __device__ inline float from_f32<float>(float v) { return v; }
+template <> __device__ inline __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <> __device__ inline __half from_f32<__half>(float v) { return __float2half_rn(v); }
+
+}  // namespace tsg

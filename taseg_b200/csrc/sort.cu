@@ -1,0 +1,330 @@
+// Stable LSD radix sort (64-bit keys, 32-bit payload) and the unique-voxel builders on top of it
+// (SURVEY §8 a5 sparse_quantize, a12 initial_voxelize ordering, a16 spdownsample).
+// Sorting packed (b,x,y,z) keys yields the reference's lexicographic voxel order directly, and stability makes the
+// head of every run the FIRST occurrence in input order (np.unique's return_index contract).
+#include "common.cuh"
+
+namespace tsg {
+
+constexpr int RS_THREADS = 256;
+constexpr int RS_ITEMS = 16;
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;
+
+// per-tile digit histogram -> counts[digit * ntiles + tile]
+__global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const unsigned long long *__restrict__ keys, int64_t n,
+                                                             int bit, int *__restrict__ counts, int64_t ntiles) {
+  __shared__ int hist[256];
+  hist[threadIdx.x] = 0;
+  __syncthreads();
+  const int64_t base = (int64_t)blockIdx.x * RS_TILE;
+  const unsigned lane_lt = (1u << (threadIdx.x & 31)) - 1;
+#pragma unroll 4
+  for (int r = 0; r < RS_ITEMS; ++r) {
+    const int64_t i = base + r * RS_THREADS + threadIdx.x;
+    const bool valid = i < n;
+    const int d = valid ? (int)((keys[i] >> bit) & 255) : (256 + (threadIdx.x & 31));
+    const unsigned peers = __match_any_sync(0xffffffffu, d);
+    if (valid && (peers & lane_lt) == 0) atomicAdd(&hist[d], __popc(peers));
+  }
+  __syncthreads();
+  counts[(int64_t)threadIdx.x * ntiles + blockIdx.x] = hist[threadIdx.x];
+}
+
+// one CTA per digit: exclusive scan of its ntiles counts in place, digit total to totals[digit]
+__global__ void __launch_bounds__(256) rs_scan_kernel(int *__restrict__ counts, int64_t ntiles, int *__restrict__ totals) {
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  int *row = counts + (int64_t)blockIdx.x * ntiles;
+  for (int64_t b = 0; b < ntiles; b += 256) {
+    const int64_t i = b + threadIdx.x;
+    const int v = i < ntiles ? row[i] : 0;
+    int tot;
+    const int ex = block_exclusive_scan<256>(v, &tot);
+    if (i < ntiles) row[i] = ex + carry;
+    __syncthreads();
+    if (threadIdx.x == 0) carry += tot;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) totals[blockIdx.x] = carry;
+}
+
+__global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const unsigned long long *__restrict__ keys_in,
+                                                                const unsigned *__restrict__ vals_in, int64_t n,
+                                                                int bit, const int *__restrict__ counts,
+                                                                const int *__restrict__ totals, int64_t ntiles,
+                                                                unsigned long long *__restrict__ keys_out,
+                                                                unsigned *__restrict__ vals_out) {
+  __shared__ int base[256];                      // next free global slot for each digit (this tile)
+  __shared__ int warp_cnt[RS_THREADS / 32][256];  // per-round, per-warp digit counts
+  {
+    int tot;
+    const int ex = block_exclusive_scan<256>(totals[threadIdx.x], &tot);
+    base[threadIdx.x] = ex + counts[(int64_t)threadIdx.x * ntiles + blockIdx.x];
+#pragma unroll
+    for (int w = 0; w < RS_THREADS / 32; ++w) warp_cnt[w][threadIdx.x] = 0;
+  }
+  __syncthreads();
+  const int64_t tile0 = (int64_t)blockIdx.x * RS_TILE;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned lane_lt = (1u << lane) - 1;
+  for (int r = 0; r < RS_ITEMS; ++r) {
+    const int64_t i = tile0 + r * RS_THREADS + threadIdx.x;
+    const bool valid = i < n;
+    unsigned long long key = 0;
+    if (valid) key = keys_in[i];
+    const int d = valid ? (int)((key >> bit) & 255) : (256 + lane);
+    const unsigned peers = __match_any_sync(0xffffffffu, d);
+    const int rank = __popc(peers & lane_lt);
+    if (valid && rank == 0) warp_cnt[warp][d] = __popc(peers);
+    __syncthreads();
+    if (valid) {
+      int pos = base[d] + rank;
+      for (int w = 0; w < warp; ++w) pos += warp_cnt[w][d];
+      keys_out[pos] = key;
+      vals_out[pos] = vals_in ? vals_in[i] : (unsigned)i;
+    }
+    __syncthreads();
+    {
+      int tot = 0;
+#pragma unroll
+      for (int w = 0; w < RS_THREADS / 32; ++w) {
+        tot += warp_cnt[w][threadIdx.x];
+        warp_cnt[w][threadIdx.x] = 0;
+      }
+      base[threadIdx.x] += tot;
+    }
+    __syncthreads();
+  }
+}
+
+struct SortWs {
+  unsigned long long *keys_tmp;
+  unsigned *vals_tmp;
+  int *counts;
+  int *totals;
+};
+
+static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+static size_t sort_ws_layout(int64_t n, char *base, SortWs *ws) {
+  const int64_t ntiles = (n + RS_TILE - 1) / RS_TILE;
+  size_t off = 0;
+  if (ws) ws->keys_tmp = (unsigned long long *)(base + off);
+  off += align256((size_t)n * 8);
+  if (ws) ws->vals_tmp = (unsigned *)(base + off);
+  off += align256((size_t)n * 4);
+  if (ws) ws->counts = (int *)(base + off);
+  off += align256((size_t)256 * (ntiles > 0 ? ntiles : 1) * 4);
+  if (ws) ws->totals = (int *)(base + off);
+  off += align256(256 * 4);
+  return off;
+}
+
+static int sort_pairs(const unsigned long long *keys_in, const unsigned *vals_in, int64_t n, int begin_bit,
+                      int end_bit, unsigned long long *keys_out, unsigned *vals_out, void *ws_mem, size_t ws_bytes,
+                      cudaStream_t stream) {
+  if (n <= 0) return TSG_OK;
+  if (n >= (1ll << 31)) {
+    set_error("tsg_sort_pairs: n must be < 2^31");
+    return TSG_ERR_INVALID;
+  }
+  SortWs ws;
+  if (sort_ws_layout(n, (char *)ws_mem, &ws) > ws_bytes) {
+    set_error("tsg_sort_pairs: workspace too small");
+    return TSG_ERR_WORKSPACE;
+  }
+  const int passes = (end_bit - begin_bit + 7) / 8;
+  const int64_t ntiles = (n + RS_TILE - 1) / RS_TILE;
+  if (passes <= 0) {
+    set_error("tsg_sort_pairs: empty bit range");
+    return TSG_ERR_INVALID;
+  }
+  const unsigned long long *src_k = keys_in;
+  const unsigned *src_v = vals_in;
+  for (int p = 0; p < passes; ++p) {
+    const bool to_out = ((passes - 1 - p) & 1) == 0;
+    unsigned long long *dst_k = to_out ? keys_out : ws.keys_tmp;
+    unsigned *dst_v = to_out ? vals_out : ws.vals_tmp;
+    const int bit = begin_bit + 8 * p;
+    rs_hist_kernel<<<(unsigned)ntiles, RS_THREADS, 0, stream>>>(src_k, n, bit, ws.counts, ntiles);
+    rs_scan_kernel<<<256, 256, 0, stream>>>(ws.counts, ntiles, ws.totals);
+    rs_scatter_kernel<<<(unsigned)ntiles, RS_THREADS, 0, stream>>>(src_k, src_v, n, bit, ws.counts, ws.totals, ntiles,
+                                                                   dst_k, dst_v);
+    src_k = dst_k;
+    src_v = dst_v;
+  }
+  return check_launch("tsg_sort_pairs");
+}
+
+// ---------------------------------------------------------------- unique voxels
+__global__ void make_coord_keys_kernel(const int4 *__restrict__ coords, int64_t n, int trunc_stride,
+                                       unsigned long long *__restrict__ keys, int *status) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int4 c = __ldg(coords + i);
+    if (trunc_stride > 0) {  // torch.div(...).trunc() * stride: C integer division truncates toward zero as well
+      c.x = (c.x / trunc_stride) * trunc_stride;
+      c.y = (c.y / trunc_stride) * trunc_stride;
+      c.z = (c.z / trunc_stride) * trunc_stride;
+    }
+    if (!coord_in_range(c.x, c.y, c.z, c.w)) {
+      if (status) atomicOr(status, 1);
+      c = make_int4(0, 0, 0, 0);
+    }
+    keys[i] = pack_coord(c.x, c.y, c.z, c.w);
+  }
+}
+
+__global__ void make_hash_keys_kernel(const int4 *__restrict__ coords, int64_t n, unsigned long long *__restrict__ keys) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int4 c = __ldg(coords + i);
+    keys[i] = (unsigned long long)fnv60(c.x, c.y, c.z, c.w);
+  }
+}
+
+constexpr int UQ_ROWS = 1024;
+
+__global__ void __launch_bounds__(256) uq_count_kernel(const unsigned long long *__restrict__ skeys, int64_t n,
+                                                       int *__restrict__ blocksum) {
+  const int64_t base = (int64_t)blockIdx.x * UQ_ROWS + threadIdx.x * 4;
+  int c = 0;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int64_t j = base + r;
+    if (j < n) c += (j == 0 || skeys[j] != skeys[j - 1]) ? 1 : 0;
+  }
+  int tot;
+  block_exclusive_scan<256>(c, &tot);
+  if (threadIdx.x == 0) blocksum[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(1024) uq_scan_kernel(int *data, int64_t n, int *total_out) {
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int64_t b = 0; b < n; b += 1024) {
+    const int64_t i = b + threadIdx.x;
+    const int v = i < n ? data[i] : 0;
+    int tot;
+    const int ex = block_exclusive_scan<1024>(v, &tot);
+    if (i < n) data[i] = ex + carry;
+    __syncthreads();
+    if (threadIdx.x == 0) carry += tot;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && total_out) *total_out = carry;
+}
+
+// hash_mode: coordinates are not recoverable from the key -> copy them from the first member of the run
+__global__ void __launch_bounds__(256) uq_write_kernel(const unsigned long long *__restrict__ skeys,
+                                                       const unsigned *__restrict__ sidx, int64_t n,
+                                                       const int *__restrict__ blockoff, int hash_mode,
+                                                       const int4 *__restrict__ in_coords, int4 *__restrict__ out_coords,
+                                                       int *__restrict__ first_idx, int *__restrict__ inverse) {
+  const int64_t base = (int64_t)blockIdx.x * UQ_ROWS + threadIdx.x * 4;
+  bool head[4];
+  int c = 0;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int64_t j = base + r;
+    head[r] = j < n && (j == 0 || skeys[j] != skeys[j - 1]);
+    c += head[r] ? 1 : 0;
+  }
+  int vid = block_exclusive_scan<256>(c, nullptr) + blockoff[blockIdx.x] - 1;  // id of the run open before base
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int64_t j = base + r;
+    if (j >= n) break;
+    const unsigned src = sidx[j];
+    if (head[r]) {
+      ++vid;
+      if (out_coords) out_coords[vid] = hash_mode ? __ldg(in_coords + src) : unpack_coord(skeys[j]);
+      if (first_idx) first_idx[vid] = (int)src;
+    }
+    if (inverse) inverse[src] = vid;
+  }
+}
+
+struct UniqueWs {
+  unsigned long long *keys, *skeys;
+  unsigned *sidx;
+  int *blocksum;
+  char *sort_ws;
+  size_t sort_bytes;
+};
+
+static size_t unique_ws_layout(int64_t n, char *base, UniqueWs *ws) {
+  size_t off = 0;
+  if (ws) ws->keys = (unsigned long long *)(base + off);
+  off += align256((size_t)n * 8);
+  if (ws) ws->skeys = (unsigned long long *)(base + off);
+  off += align256((size_t)n * 8);
+  if (ws) ws->sidx = (unsigned *)(base + off);
+  off += align256((size_t)n * 4);
+  if (ws) ws->blocksum = (int *)(base + off);
+  off += align256((size_t)((n + UQ_ROWS - 1) / UQ_ROWS + 1) * 4);
+  const size_t sb = sort_ws_layout(n, nullptr, nullptr);
+  if (ws) {
+    ws->sort_ws = base + off;
+    ws->sort_bytes = sb;
+  }
+  off += sb;
+  return off;
+}
+
+static int unique_impl(const int32_t *in_coords, int64_t n, int trunc_stride, bool hash_mode, int32_t *out_coords,
+                       int32_t *first_idx, int32_t *inverse, int32_t *m_dev, int32_t *status, void *ws_mem,
+                       size_t ws_bytes, cudaStream_t stream) {
+  if (n <= 0) {
+    if (m_dev) TSG_CUDA(cudaMemsetAsync(m_dev, 0, sizeof(int), stream));
+    return TSG_OK;
+  }
+  UniqueWs ws;
+  if (unique_ws_layout(n, (char *)ws_mem, &ws) > ws_bytes) {
+    set_error("tsg_unique: workspace too small");
+    return TSG_ERR_WORKSPACE;
+  }
+  if (hash_mode)
+    make_hash_keys_kernel<<<grid_for(n, 256), 256, 0, stream>>>((const int4 *)in_coords, n, ws.keys);
+  else
+    make_coord_keys_kernel<<<grid_for(n, 256), 256, 0, stream>>>((const int4 *)in_coords, n, trunc_stride, ws.keys,
+                                                                status);
+  int rc = sort_pairs(ws.keys, nullptr, n, 0, hash_mode ? 60 : 64, ws.skeys, ws.sidx, ws.sort_ws, ws.sort_bytes, stream);
+  if (rc) return rc;
+  const int64_t nblk = (n + UQ_ROWS - 1) / UQ_ROWS;
+  uq_count_kernel<<<(unsigned)nblk, 256, 0, stream>>>(ws.skeys, n, ws.blocksum);
+  uq_scan_kernel<<<1, 1024, 0, stream>>>(ws.blocksum, nblk, m_dev);
+  uq_write_kernel<<<(unsigned)nblk, 256, 0, stream>>>(ws.skeys, ws.sidx, n, ws.blocksum, hash_mode ? 1 : 0,
+                                                      (const int4 *)in_coords, (int4 *)out_coords, first_idx, inverse);
+  return check_launch("tsg_unique");
+}
+
+}  // namespace tsg
+
+using namespace tsg;
+
+extern "C" {
+
+size_t tsg_sort_ws_bytes(int64_t n) { return sort_ws_layout(n > 0 ? n : 1, nullptr, nullptr); }
+
+int tsg_sort_pairs(const uint64_t *keys_in, const uint32_t *vals_in, int64_t n, int begin_bit, int end_bit,
+                   uint64_t *keys_out, uint32_t *vals_out, void *ws, size_t ws_bytes, tsg_stream_t stream) {
+  return sort_pairs((const unsigned long long *)keys_in, vals_in, n, begin_bit, end_bit, (unsigned long long *)keys_out,
+                    vals_out, ws, ws_bytes, stream);
+}
+
+size_t tsg_unique_ws_bytes(int64_t n) { return unique_ws_layout(n > 0 ? n : 1, nullptr, nullptr); }
+
+int tsg_unique_coords(const int32_t *in_coords, int64_t n, int trunc_stride, int32_t *out_coords, int32_t *first_idx,
+                      int32_t *inverse, int32_t *m_dev, int32_t *status, void *ws, size_t ws_bytes,
+                      tsg_stream_t stream) {
+  return unique_impl(in_coords, n, trunc_stride, false, out_coords, first_idx, inverse, m_dev, status, ws, ws_bytes,
+                     stream);
+}
+
+int tsg_unique_hash(const int32_t *in_coords, int64_t n, int32_t *out_coords, int32_t *first_idx, int32_t *inverse,
+                    int32_t *m_dev, void *ws, size_t ws_bytes, tsg_stream_t stream) {
+  return unique_impl(in_coords, n, 0, true, out_coords, first_idx, inverse, m_dev, nullptr, ws, ws_bytes, stream);
+}
+
+}  // extern "C"

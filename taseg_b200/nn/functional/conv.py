@@ -1,0 +1,113 @@
+"""conv3d (TS/torchsparse/nn/functional/conv.py:122-205) on the output-stationary implicit-GEMM kernels.
+
+Differences from the reference that do not change results:
+  * the kernel map is ONE fused device pass (hash of shifted coordinates, table probe, nonzero, sum) over an
+    exact-coordinate table that is built once per tensor stride and cached next to the kernel maps;
+  * the convolution is ONE launch (no per-offset gather/GEMM/scatter, no nbsizes.cpu() sync);
+  * `kmaps[key]` holds a KernelMap that still unpacks as `[nbmaps, nbsizes, (n_in, n_out)]`.
+"""
+from typing import List, Optional, Tuple, Union
+
+import torch
+from torch.autograd import Function
+
+from ... import ops
+from ...tensor import SparseTensor
+from ...utils import make_ntuple
+from ..utils.kernel import kernel_offsets_np
+from .downsample import spdownsample
+
+__all__ = ['conv3d']
+
+
+def coord_table(x: SparseTensor, coords: torch.Tensor, stride) -> ops.Table:
+    key = ('coord_table', tuple(stride))
+    tab = x.kmaps.get(key)
+    if tab is None or tab.n != coords.shape[0]:
+        tab = ops.Table.from_coords(coords)
+        x.kmaps[key] = tab
+    return tab
+
+
+def as_kernel_map(entry, k: int) -> ops.KernelMap:
+    if isinstance(entry, ops.KernelMap):
+        return entry
+    nbmaps, nbsizes, (n_in, n_out) = entry     # reference-format list supplied by user code
+    nbr = ops.kmap_from_pairs(nbmaps, nbsizes, k, False, n_out)
+    return ops.KernelMap(nbr, nbsizes.to(torch.int32).to(nbr.device), None, n_in, n_out, k)
+
+
+def _tc_ok(feats: torch.Tensor, c_in: int, c_out: int) -> bool:
+    return feats.dtype == torch.bfloat16 and c_in % 16 == 0 and c_out % 16 == 0 and c_out <= 256
+
+
+class ConvolutionFunction(Function):
+
+    @staticmethod
+    def forward(ctx, input: torch.Tensor, weight: torch.Tensor, kmap: ops.KernelMap, transposed: bool = False):
+        input = input.contiguous()
+        weight = weight.contiguous()
+        if input.shape[1] != weight.shape[1]:
+            raise ValueError('Input feature size and kernel size mismatch')
+        nbr = kmap.nbr_t if transposed else kmap.nbr
+        n_out = kmap.n_in if transposed else kmap.n_out
+        k, c_in, c_out = weight.shape
+        if _tc_ok(input, c_in, c_out):
+            packed = ops.pack_weights(weight, c_in)
+            out = ops.conv_forward_tc(input, None, packed, k, c_out, nbr, kmap.tile_mask(transposed), n_out)
+        else:
+            out = ops.conv_forward(input, weight, nbr, n_out)
+        ctx.for_backwards = (input, weight, kmap, transposed)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_output: torch.Tensor):
+        input, weight, kmap, transposed = ctx.for_backwards
+        k = weight.shape[0]
+        # pairs (in i, out o, k): dX[i] += dY[o] W[k]^T ; dW[k] += X[i]^T dY[o]
+        tab_in_of_out = kmap.nbr_t if transposed else kmap.nbr       # rows = outputs of the forward, values = inputs
+        tab_out_of_in = kmap.nbr if transposed else kmap.nbr_t       # rows = inputs of the forward, values = outputs
+        grad_input = ops.conv_dgrad(grad_output, weight, tab_out_of_in, input.shape[0]).to(input.dtype)
+        grad_weight = ops.conv_wgrad(input, grad_output, tab_in_of_out, k).to(weight.dtype)
+        return grad_input, grad_weight, None, None
+
+
+def conv3d(input: SparseTensor, weight: torch.Tensor, kernel_size: Union[int, List[int], Tuple[int, ...]],
+           bias: Optional[torch.Tensor] = None, stride: Union[int, List[int], Tuple[int, ...]] = 1,
+           dilation: Union[int, Tuple[int, ...]] = 1, transposed: bool = False) -> SparseTensor:
+    kernel_size, stride, dilation = make_ntuple(kernel_size, 3), make_ntuple(stride, 3), make_ntuple(dilation, 3)
+    feats = input.feats
+    if torch.is_autocast_enabled():        # reference: custom_fwd(cast_inputs=torch.half) (conv.py:19)
+        dt = torch.get_autocast_gpu_dtype()
+        feats, weight = feats.to(dt), weight.to(dt)
+
+    if kernel_size == (1, 1, 1) and stride == (1, 1, 1) and dilation == (1, 1, 1):
+        out_stride, out_coords = input.stride, input.coords
+        out_feats = feats.matmul(weight)
+    elif not transposed:
+        out_stride = tuple(input.stride[k] * stride[k] for k in range(3))
+        if out_stride in input.cmaps:
+            out_coords = input.cmaps[out_stride]
+        elif all(s == 1 for s in stride):
+            out_coords = input.coords
+        else:
+            out_coords = spdownsample(input.coords, stride, kernel_size, input.stride)
+        key = (input.stride, kernel_size, stride, dilation)
+        if key not in input.kmaps:
+            offsets = kernel_offsets_np(kernel_size, stride=input.stride, dilation=dilation)
+            table = coord_table(input, input.coords, input.stride)
+            input.kmaps[key] = ops.build_kmap(table, input.coords.shape[0], out_coords, offsets)
+        kmap = as_kernel_map(input.kmaps[key], weight.shape[0])
+        out_feats = ConvolutionFunction.apply(feats, weight, kmap, False)
+    else:
+        out_stride = tuple(input.stride[k] // stride[k] for k in range(3))
+        out_coords = input.cmaps[out_stride]                                   # KeyError like the reference (conv.py:186)
+        kmap = as_kernel_map(input.kmaps[(out_stride, kernel_size, stride, dilation)], weight.shape[0])
+        out_feats = ConvolutionFunction.apply(feats, weight, kmap, True)
+
+    if bias is not None:
+        out_feats = out_feats + bias.to(out_feats.dtype)
+
+    output = input.derive(out_feats, out_coords, out_stride)
+    output.cmaps.setdefault(out_stride, out_coords)
+    return output

@@ -1,0 +1,451 @@
+"""Tensor-level host wrappers over the C ABI (allocation with torch's caching allocator + one call each).
+
+Everything here launches on torch's current CUDA stream and never synchronises, except where a
+data-dependent size must become a tensor shape (`.item()` on a device counter), which is marked `# sync`.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from ._lib import call, ptr, stream
+
+
+def _i32(t: torch.Tensor) -> torch.Tensor:
+    return t if t.dtype == torch.int32 else t.to(torch.int32)
+
+
+def _empty(shape, dtype, like: torch.Tensor) -> torch.Tensor:
+    return torch.empty(shape, dtype=dtype, device=like.device)
+
+
+def _status(dev) -> torch.Tensor:
+    return torch.zeros(1, dtype=torch.int32, device=dev)
+
+
+def _check_status(status: torch.Tensor, what: str) -> None:
+    if int(status.item()) & 1:
+        raise RuntimeError(f"{what}: coordinate outside the packable range (|x|,|y|,|z| < 2^18, 0 <= b < 128)")
+
+
+# ------------------------------------------------------------------------------- hashing / tables
+def sphash(coords: torch.Tensor, offsets: Optional[torch.Tensor] = None) -> torch.Tensor:
+    L.require_cuda(coords, offsets)
+    coords = coords.contiguous()
+    n = coords.shape[0]
+    if offsets is None:
+        out = _empty((n,), torch.int64, coords)
+        call("tsg_hash", ptr(coords), n, ptr(out), stream())
+        return out
+    offsets = offsets.contiguous()
+    k = offsets.shape[0]
+    out = _empty((k, n), torch.int64, coords)
+    call("tsg_kernel_hash", ptr(coords), n, ptr(offsets), k, ptr(out), stream())
+    return out
+
+
+class Table:
+    """Open-addressing key -> row table living in one torch buffer (16 B per slot)."""
+
+    def __init__(self, n: int, device):
+        self.n = int(n)
+        self.slots = int(L.lib().tsg_table_slots(self.n))
+        self.buf = torch.empty(self.slots * 2, dtype=torch.int64, device=device)
+
+    @classmethod
+    def from_keys(cls, keys: torch.Tensor) -> "Table":
+        keys = keys.contiguous()
+        t = cls(keys.numel(), keys.device)
+        call("tsg_table_build", ptr(keys), t.n, ptr(t.buf), t.slots, stream())
+        return t
+
+    @classmethod
+    def from_coords(cls, coords: torch.Tensor, status: Optional[torch.Tensor] = None) -> "Table":
+        coords = coords.contiguous()
+        t = cls(coords.shape[0], coords.device)
+        t.status = status if status is not None else _status(coords.device)
+        call("tsg_coord_table_build", ptr(coords), t.n, ptr(t.buf), t.slots, ptr(t.status), stream())
+        return t
+
+    def query(self, queries: torch.Tensor) -> torch.Tensor:
+        q = queries.contiguous()
+        out = torch.empty_like(q)
+        call("tsg_table_query", ptr(self.buf), self.slots, ptr(q), q.numel(), ptr(out), stream())
+        return out
+
+
+def sphashquery(queries: torch.Tensor, references: torch.Tensor) -> torch.Tensor:
+    L.require_cuda(queries, references)
+    return Table.from_keys(references).query(queries)
+
+
+# ------------------------------------------------------------------------------- kernel maps
+class KernelMap:
+    """Kernel map of one (tensor stride, kernel, stride, dilation): the output-stationary neighbour table the
+    convolution kernels consume, plus lazily materialised reference-format views.
+
+    Indexable like the reference's `[nbmaps, nbsizes, (n_in, n_out)]` list (TS/nn/functional/conv.py:174-176)."""
+
+    def __init__(self, nbr, nbsizes, blockcnt, n_in, n_out, k):
+        self.nbr, self.nbsizes32, self.blockcnt = nbr, nbsizes, blockcnt
+        self.n_in, self.n_out, self.k = int(n_in), int(n_out), int(k)
+        self._nbmaps = None
+        self._nbr_t = None
+        self._tile_mask = None
+        self._tile_mask_t = None
+
+    @property
+    def sizes(self) -> Tuple[int, int]:
+        return (self.n_in, self.n_out)
+
+    @property
+    def nbsizes(self) -> torch.Tensor:
+        return self.nbsizes32.to(torch.int64)
+
+    @property
+    def nbmaps(self) -> torch.Tensor:
+        if self._nbmaps is None:
+            total = int(self.nbsizes32.sum().item())  # sync: P is data dependent
+            out = torch.empty((total, 2), dtype=torch.int64, device=self.nbr.device)
+            if total:
+                call("tsg_kmap_pairs", ptr(self.nbr), self.k, self.n_out, ptr(self.blockcnt.clone()), ptr(out), stream())
+            self._nbmaps = out
+        return self._nbmaps
+
+    @property
+    def nbr_t(self) -> torch.Tensor:
+        if self._nbr_t is None:
+            out = torch.empty((self.k, self.n_in), dtype=torch.int32, device=self.nbr.device)
+            call("tsg_kmap_transpose", ptr(self.nbr), self.k, self.n_out, self.n_in, ptr(out), stream())
+            self._nbr_t = out
+        return self._nbr_t
+
+    def tile_mask(self, transposed: bool = False) -> torch.Tensor:
+        attr = "_tile_mask_t" if transposed else "_tile_mask"
+        if getattr(self, attr) is None:
+            nbr = self.nbr_t if transposed else self.nbr
+            rows = self.n_in if transposed else self.n_out
+            out = torch.empty(((rows + 127) // 128,), dtype=torch.int32, device=nbr.device)
+            call("tsg_kmap_tile_mask", ptr(nbr), self.k, rows, ptr(out), stream())
+            setattr(self, attr, out)
+        return getattr(self, attr)
+
+    def __getitem__(self, i):
+        return (self.nbmaps, self.nbsizes, self.sizes)[i]
+
+    def __iter__(self):
+        return iter((self.nbmaps, self.nbsizes, self.sizes))
+
+    def __len__(self):
+        return 3
+
+
+def build_kmap(table: Table, n_in: int, out_coords: torch.Tensor, offsets: np.ndarray) -> KernelMap:
+    out_coords = out_coords.contiguous()
+    n_out = out_coords.shape[0]
+    offs = np.ascontiguousarray(offsets, dtype=np.int32)
+    k = offs.shape[0]
+    dev = out_coords.device
+    nbr = torch.empty((k, n_out), dtype=torch.int32, device=dev)
+    nbsizes = torch.empty((k,), dtype=torch.int32, device=dev)
+    blockcnt = torch.empty((k * max(int(L.lib().tsg_kmap_blocks(n_out)), 1),), dtype=torch.int32, device=dev)
+    call("tsg_kmap_build", ptr(table.buf), table.slots, ptr(out_coords), n_out,
+         offs.ctypes.data_as(ctypes.c_void_p), k, ptr(nbr), ptr(nbsizes), ptr(blockcnt), stream())
+    return KernelMap(nbr, nbsizes, blockcnt, n_in, n_out, k)
+
+
+def kmap_from_pairs(nbmaps: torch.Tensor, nbsizes: torch.Tensor, k: int, transposed: bool, n_rows_out: int) -> torch.Tensor:
+    """Reference-format pairs -> neighbour table (for callers holding torchsparse-style kmaps)."""
+    nbmaps = _i32(nbmaps).contiguous()
+    ns = np.ascontiguousarray(nbsizes.detach().cpu().numpy(), dtype=np.int32)
+    nbr = torch.empty((k, n_rows_out), dtype=torch.int32, device=nbmaps.device)
+    call("tsg_kmap_from_pairs", ptr(nbmaps), ns.ctypes.data_as(ctypes.c_void_p), k, int(transposed), n_rows_out,
+         ptr(nbr), stream())
+    return nbr
+
+
+# ------------------------------------------------------------------------------- unique voxels
+def unique_coords(coords: torch.Tensor, trunc_stride: int = 0, want_index: bool = False, want_inverse: bool = False,
+                  by_hash: bool = False):
+    """Unique voxel rows ordered by (b,x,y,z) (or by ascending FNV hash); returns (coords[, first_idx][, inverse])."""
+    L.require_cuda(coords)
+    coords = _i32(coords).contiguous()
+    n = coords.shape[0]
+    dev = coords.device
+    out_c = torch.empty((n, 4), dtype=torch.int32, device=dev)
+    first = torch.empty((n,), dtype=torch.int32, device=dev) if want_index else None
+    inv = torch.empty((n,), dtype=torch.int32, device=dev) if want_inverse else None
+    m_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+    ws_bytes = int(L.lib().tsg_unique_ws_bytes(n))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    if by_hash:
+        call("tsg_unique_hash", ptr(coords), n, ptr(out_c), ptr(first), ptr(inv), ptr(m_dev), ptr(ws), ws_bytes, stream())
+        m = int(m_dev.item())  # sync
+    else:
+        status = _status(dev)
+        call("tsg_unique_coords", ptr(coords), n, int(trunc_stride), ptr(out_c), ptr(first), ptr(inv), ptr(m_dev),
+             ptr(status), ptr(ws), ws_bytes, stream())
+        m, st = torch.cat([m_dev, status]).tolist()  # sync
+        if st & 1:
+            raise RuntimeError("unique_coords: coordinate outside the packable range (|x|,|y|,|z| < 2^18, 0 <= b < 128)")
+    res = [out_c[:m]]
+    if want_index:
+        res.append(first[:m])
+    if want_inverse:
+        res.append(inv)
+    return res[0] if len(res) == 1 else tuple(res)
+
+
+def sort_pairs(keys: torch.Tensor, vals: Optional[torch.Tensor] = None, begin_bit: int = 0, end_bit: int = 64):
+    keys = keys.contiguous()
+    n = keys.numel()
+    ko = torch.empty_like(keys)
+    vo = torch.empty((n,), dtype=torch.int32, device=keys.device)
+    ws_bytes = int(L.lib().tsg_sort_ws_bytes(n))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=keys.device)
+    call("tsg_sort_pairs", ptr(keys), ptr(vals), n, begin_bit, end_bit, ptr(ko), ptr(vo), ptr(ws), ws_bytes, stream())
+    return ko, vo
+
+
+# ------------------------------------------------------------------------------- point <-> voxel
+def spcount(idx: torch.Tensor, num: int) -> torch.Tensor:
+    L.require_cuda(idx)
+    idx = _i32(idx).contiguous()
+    out = torch.empty((int(num),), dtype=torch.int32, device=idx.device)
+    call("tsg_count", ptr(idx), idx.numel(), ptr(out), int(num), stream())
+    return out
+
+
+def voxelize_forward(feats: torch.Tensor, idx: torch.Tensor, counts: torch.Tensor) -> torch.Tensor:
+    L.require_cuda(feats, idx, counts)
+    feats = feats.contiguous()
+    idx, counts = _i32(idx).contiguous(), _i32(counts).contiguous()
+    n, c = feats.shape
+    m = counts.shape[0]
+    out = torch.empty((m, c), dtype=feats.dtype, device=feats.device)
+    acc = None if feats.dtype == torch.float32 else torch.empty((m, c), dtype=torch.float32, device=feats.device)
+    call("tsg_voxelize_fwd", ptr(feats), L.DTYPES[feats.dtype], ptr(idx), ptr(counts), n, c, m, ptr(out), ptr(acc), stream())
+    return out
+
+
+def voxelize_backward(top_grad: torch.Tensor, idx: torch.Tensor, counts: torch.Tensor, n: int) -> torch.Tensor:
+    top_grad = top_grad.contiguous()
+    idx, counts = _i32(idx).contiguous(), _i32(counts).contiguous()
+    c = top_grad.shape[1]
+    out = torch.empty((n, c), dtype=top_grad.dtype, device=top_grad.device)
+    call("tsg_voxelize_bwd", ptr(top_grad), L.DTYPES[top_grad.dtype], ptr(idx), ptr(counts), n, c, ptr(out), stream())
+    return out
+
+
+def devoxelize_forward(feats: torch.Tensor, idx8: torch.Tensor, w8: torch.Tensor) -> torch.Tensor:
+    L.require_cuda(feats, idx8, w8)
+    feats = feats.contiguous()
+    idx8, w8 = _i32(idx8).contiguous(), w8.float().contiguous()
+    n, c = idx8.shape[0], feats.shape[1]
+    out = torch.empty((n, c), dtype=feats.dtype, device=feats.device)
+    call("tsg_devoxelize_fwd", ptr(feats), L.DTYPES[feats.dtype], ptr(idx8), ptr(w8), n, c, ptr(out), stream())
+    return out
+
+
+def devoxelize_backward(top_grad: torch.Tensor, idx8: torch.Tensor, w8: torch.Tensor, m: int) -> torch.Tensor:
+    top_grad = top_grad.contiguous()
+    idx8, w8 = _i32(idx8).contiguous(), w8.float().contiguous()
+    n, c = top_grad.shape
+    out = torch.empty((m, c), dtype=top_grad.dtype, device=top_grad.device)
+    acc = None if top_grad.dtype == torch.float32 else torch.empty((m, c), dtype=torch.float32, device=top_grad.device)
+    call("tsg_devoxelize_bwd", ptr(top_grad), L.DTYPES[top_grad.dtype], ptr(idx8), ptr(w8), n, c, m, ptr(out), ptr(acc), stream())
+    return out
+
+
+def point_query(table: Table, pcoords: torch.Tensor, stride: int) -> torch.Tensor:
+    pc = pcoords.float().contiguous()
+    out = torch.empty((pc.shape[0],), dtype=torch.int32, device=pc.device)
+    call("tsg_point_query", ptr(table.buf), table.slots, ptr(pc), pc.shape[0], int(stride), ptr(out), stream())
+    return out
+
+
+def trilinear_query(table: Table, pcoords: torch.Tensor, stride: int, nearest: bool = False):
+    pc = pcoords.float().contiguous()
+    n = pc.shape[0]
+    idx8 = torch.empty((n, 8), dtype=torch.int32, device=pc.device)
+    w8 = torch.empty((n, 8), dtype=torch.float32, device=pc.device)
+    call("tsg_trilinear_query", ptr(table.buf), table.slots, ptr(pc), n, int(stride), int(nearest), ptr(idx8), ptr(w8), stream())
+    return idx8, w8
+
+
+def rescale_coords(pcoords: torch.Tensor, init_res: float, after_res: float):
+    pc = pcoords.float().contiguous()
+    n = pc.shape[0]
+    out_f = torch.empty((n, 4), dtype=torch.float32, device=pc.device)
+    out_i = torch.empty((n, 4), dtype=torch.int32, device=pc.device)
+    call("tsg_rescale_coords", ptr(pc), n, float(init_res), float(after_res), ptr(out_f), ptr(out_i), stream())
+    return out_f, out_i
+
+
+def gather_rows(src: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """out[i] = src[idx[i]] for rows of 4-byte elements (fp32 / int32)."""
+    assert src.element_size() == 4
+    src = src.contiguous()
+    idx = _i32(idx).contiguous()
+    width = src.shape[1] if src.dim() > 1 else 1
+    out = torch.empty((idx.shape[0],) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
+    call("tsg_gather_rows", ptr(src), width, ptr(idx), idx.shape[0], ptr(out), stream())
+    return out
+
+
+def compact_rows(flags: torch.Tensor, rows_a: Optional[torch.Tensor], rows_b: Optional[torch.Tensor] = None,
+                 want_pos: bool = False):
+    """Stable compaction by a uint8 flag; returns (out_a, out_b, pos, m)."""
+    n = flags.numel()
+    dev = flags.device
+    wa = rows_a.shape[1] if rows_a is not None else 0
+    wb = rows_b.shape[1] if rows_b is not None else 0
+    out_a = torch.empty_like(rows_a) if rows_a is not None else None
+    out_b = torch.empty_like(rows_b) if rows_b is not None else None
+    pos = torch.empty((n,), dtype=torch.int32, device=dev) if want_pos else None
+    m_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+    ws_bytes = int(L.lib().tsg_compact_ws_bytes(n))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    call("tsg_compact_rows", ptr(flags), n, ptr(rows_a), wa, ptr(out_a), ptr(rows_b), wb, ptr(out_b), ptr(pos), ptr(m_dev),
+         ptr(ws), ws_bytes, stream())
+    m = int(m_dev.item())  # sync
+    return (out_a[:m] if out_a is not None else None, out_b[:m] if out_b is not None else None, pos, m)
+
+
+# ------------------------------------------------------------------------------- convolution
+def conv_forward(feats: torch.Tensor, weight: torch.Tensor, nbr: torch.Tensor, n_out: int,
+                 scale: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
+                 residual: Optional[torch.Tensor] = None, relu: bool = False) -> torch.Tensor:
+    """CUDA-core implicit GEMM (fp32/bf16/fp16 storage, fp32 accumulate)."""
+    L.require_cuda(feats, weight, nbr)
+    feats = feats.contiguous()
+    weight = weight.contiguous().to(feats.dtype)
+    if weight.dim() == 2:
+        weight = weight.unsqueeze(0)
+    k, c_in_w, c_out = weight.shape
+    out = torch.empty((n_out, c_out), dtype=feats.dtype, device=feats.device)
+    call("tsg_conv_fwd", ptr(feats), L.DTYPES[feats.dtype], feats.shape[0], feats.shape[1], ptr(weight), k, c_in_w, c_out,
+         ptr(nbr), int(n_out), ptr(out), ptr(scale), ptr(bias), ptr(residual), int(relu), stream())
+    return out
+
+
+def conv_dgrad(grad_out: torch.Tensor, weight: torch.Tensor, nbr_t: torch.Tensor, n_in: int) -> torch.Tensor:
+    grad_out = grad_out.float().contiguous()
+    weight = weight.float().contiguous()
+    k, c_in, c_out = weight.shape
+    out = torch.empty((n_in, c_in), dtype=torch.float32, device=grad_out.device)
+    call("tsg_conv_dgrad", ptr(grad_out), grad_out.shape[0], c_out, ptr(weight), k, c_in, ptr(nbr_t), int(n_in), ptr(out), stream())
+    return out
+
+
+def conv_wgrad(feats: torch.Tensor, grad_out: torch.Tensor, nbr: torch.Tensor, k: int) -> torch.Tensor:
+    feats = feats.float().contiguous()
+    grad_out = grad_out.float().contiguous()
+    c_in, c_out = feats.shape[1], grad_out.shape[1]
+    gw = torch.empty((k, c_in, c_out), dtype=torch.float32, device=feats.device)
+    call("tsg_conv_wgrad", ptr(feats), feats.shape[0], c_in, ptr(grad_out), grad_out.shape[0], c_out, ptr(nbr), k, ptr(gw), stream())
+    return gw
+
+
+def pad16(c: int) -> int:
+    return (c + 15) // 16 * 16
+
+
+def pack_weights(weight: torch.Tensor, c0: int, c1: int = 0, out_scale: Optional[torch.Tensor] = None,
+                 c_out_pad: Optional[int] = None) -> torch.Tensor:
+    """(K, c_in, c_out) fp32 -> tcgen05 shared-memory image (bf16, swizzled), optionally BN-scale folded and with the
+    output channels zero-padded to c_out_pad."""
+    w = weight.detach().float()
+    if w.dim() == 2:
+        w = w.unsqueeze(0)
+    k, c_in, c_out = w.shape
+    if out_scale is not None:
+        out_scale = out_scale.detach().float().contiguous()
+    if c_out_pad is not None and c_out_pad != c_out:
+        w = torch.nn.functional.pad(w, (0, c_out_pad - c_out))
+        if out_scale is not None:
+            out_scale = torch.nn.functional.pad(out_scale, (0, c_out_pad - c_out))
+        c_out = c_out_pad
+    w = w.contiguous()
+    nbytes = int(L.lib().tsg_conv_pack_bytes(k, c0, c1, c_out))
+    packed = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
+    call("tsg_conv_pack_weights", ptr(w), k, c_in, c_out, c0, c1, ptr(out_scale), ptr(packed), stream())
+    return packed
+
+
+def cast_pad_bf16(feats: torch.Tensor, c_pad: int) -> torch.Tensor:
+    feats = feats.float().contiguous()
+    n, c = feats.shape
+    out = torch.empty((n, c_pad), dtype=torch.bfloat16, device=feats.device)
+    call("tsg_cast_pad_bf16", ptr(feats), n, c, c_pad, ptr(out), stream())
+    return out
+
+
+def conv_forward_tc(in0: torch.Tensor, in1: Optional[torch.Tensor], packed_w: torch.Tensor, k: int, c_out: int,
+                    nbr: torch.Tensor, tile_mask: torch.Tensor, n_out: int, bias: Optional[torch.Tensor] = None,
+                    residual: Optional[torch.Tensor] = None, relu: bool = False, out_dtype=torch.bfloat16,
+                    num_sms: int = 0) -> torch.Tensor:
+    """tcgen05/TMEM implicit GEMM; in0/in1 bf16 (n_in, c) with c % 16 == 0."""
+    assert in0.dtype == torch.bfloat16 and in0.is_contiguous()
+    c0 = in0.shape[1]
+    c1 = 0
+    if in1 is not None:
+        assert in1.dtype == torch.bfloat16 and in1.is_contiguous() and in1.shape[0] == in0.shape[0]
+        c1 = in1.shape[1]
+    if residual is not None:
+        assert residual.dtype == torch.bfloat16 and residual.is_contiguous() and residual.shape == (n_out, c_out)
+    out = torch.empty((n_out, c_out), dtype=out_dtype, device=in0.device)
+    call("tsg_conv_fwd_tc", ptr(in0), c0, ptr(in1), c1, in0.shape[0], ptr(packed_w), k, c_out, ptr(nbr), ptr(tile_mask),
+         int(n_out), ptr(out), L.DTYPES[out_dtype], ptr(bias), ptr(residual), int(relu), int(num_sms), stream())
+    return out
+
+
+# ------------------------------------------------------------------------------- multi-frame front end
+def fuse_multi_scan(points: torch.Tensor, pose0, pose) -> torch.Tensor:
+    L.require_cuda(points)
+    pts = points.float().contiguous()
+    p0 = (ctypes.c_float * 16)(*np.asarray(pose0, np.float32).reshape(-1).tolist())
+    p1 = (ctypes.c_float * 16)(*np.asarray(pose, np.float32).reshape(-1).tolist())
+    out = torch.empty_like(pts)
+    call("tsg_fuse_multi_scan", ptr(pts), pts.shape[0], pts.shape[1], p0, p1, ptr(out), stream())
+    return out
+
+
+def transform_point(points: torch.Tensor, R, T) -> torch.Tensor:
+    L.require_cuda(points)
+    pts = points.float().contiguous()
+    r = (ctypes.c_double * 9)(*np.asarray(R, np.float64).reshape(-1).tolist())
+    t = (ctypes.c_double * 3)(*np.asarray(T, np.float64).reshape(-1).tolist())
+    out = torch.empty_like(pts)
+    call("tsg_transform_point", ptr(pts), pts.shape[0], pts.shape[1], r, t, ptr(out), stream())
+    return out
+
+
+def aggregate_quantize(points: torch.Tensor, frames: Sequence[dict], n_samples: int, voxel_size: float,
+                       keep: Optional[torch.Tensor] = None):
+    """points (sum n, c_in) fp32, frames: dicts(offset,count,sample,is_cur,pose0,pose).
+    Returns feats (sum n, c_in+1), coords (sum n, 4) int32, flags (sum n) uint8."""
+    L.require_cuda(points, keep)
+    pts = points.float().contiguous()
+    n, c_in = pts.shape
+    arr = (L.Frame * len(frames))()
+    ident = np.eye(4, dtype=np.float32).reshape(-1)
+    for i, f in enumerate(frames):
+        arr[i].offset, arr[i].count, arr[i].sample, arr[i].is_cur = int(f["offset"]), int(f["count"]), int(f["sample"]), int(f["is_cur"])
+        p0 = np.asarray(f.get("pose0", ident), np.float32).reshape(-1)
+        p1 = np.asarray(f.get("pose", ident), np.float32).reshape(-1)
+        for j in range(16):
+            arr[i].pose0[j] = float(p0[j])
+            arr[i].pose[j] = float(p1[j])
+    feats = torch.empty((n, c_in + 1), dtype=torch.float32, device=pts.device)
+    coords = torch.empty((n, 4), dtype=torch.int32, device=pts.device)
+    flags = torch.empty((n,), dtype=torch.uint8, device=pts.device)
+    ws_bytes = int(L.lib().tsg_aggregate_ws_bytes(n_samples))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=pts.device)
+    call("tsg_aggregate_quantize", ptr(pts), c_in, arr, len(frames), n_samples, ptr(keep), float(voxel_size), ptr(feats),
+         ptr(coords), ptr(flags), ptr(ws), ws_bytes, stream())
+    return feats, coords, flags

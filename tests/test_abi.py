@@ -1,0 +1,88 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds, loads and exports every symbol the header
+declares; the host mirror exposes the reference's import surface; host-only entry points behave."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from taseg_b200 import build, _lib
+    build.build()
+    return _lib.lib()
+
+
+def test_every_declared_symbol_is_exported(lib):
+    from taseg_b200 import _lib
+    protos = _lib.parse_header()
+    assert len(protos) >= 40
+    for name in protos:
+        assert hasattr(lib, name), name
+    assert lib.tsg_version() >= 100
+    assert lib.tsg_last_error() is not None
+
+
+def test_host_only_entry_points(lib):
+    for n in (0, 1, 511, 512, 513, 100000):
+        s = lib.tsg_table_slots(n)
+        assert s >= 2 * n and s & (s - 1) == 0
+    assert lib.tsg_kmap_blocks(1) == 1 and lib.tsg_kmap_blocks(1025) == 2
+    assert lib.tsg_sort_ws_bytes(1000) > 1000 * 12
+    assert lib.tsg_unique_ws_bytes(1000) > lib.tsg_sort_ws_bytes(1000)
+    assert lib.tsg_conv_pack_bytes(27, 64, 0, 64) == 27 * 64 * 64 * 2
+    assert lib.tsg_conv_pack_bytes(27, 96, 32, 96) == 27 * 3 * 96 * 64 * 2
+
+
+def test_no_cpu_fallback():
+    import taseg_b200
+    from taseg_b200.nn import functional as F
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        F.sphash(torch.zeros((4, 4), dtype=torch.int32))
+    x = taseg_b200.SparseTensor(torch.zeros(4, 4), torch.zeros((4, 4), dtype=torch.int32))
+    with pytest.raises(RuntimeError):
+        F.conv3d(x, torch.zeros(27, 4, 8), 3)
+
+
+def test_import_surface_matches_reference():
+    """Names pcseg imports (SURVEY §8b 'import surface')."""
+    import sys
+    import taseg_b200
+    taseg_b200.install_as_torchsparse()
+    import torchsparse
+    import torchsparse.nn as spnn
+    import torchsparse.nn.functional as F
+    from torchsparse import PointTensor, SparseTensor  # noqa: F401
+    from torchsparse.nn.utils import fapply, get_kernel_offsets  # noqa: F401
+    from torchsparse.utils import make_ntuple
+    from torchsparse.utils.collate import sparse_collate, sparse_collate_fn  # noqa: F401
+    from torchsparse.utils.quantize import sparse_quantize  # noqa: F401
+    for name in ["conv3d", "sphash", "sphashquery", "spcount", "spvoxelize", "spdevoxelize", "calc_ti_weights",
+                 "spdownsample", "relu"]:
+        assert hasattr(F, name), name
+    for name in ["Conv3d", "BatchNorm", "ReLU", "LeakyReLU"]:
+        assert hasattr(spnn, name), name
+    assert torchsparse.cat is taseg_b200.cat and make_ntuple(2, 3) == (2, 2, 2)
+    conv = spnn.Conv3d(4, 8, 3)
+    assert tuple(conv.kernel.shape) == (27, 4, 8) and conv.bias is None
+    assert tuple(spnn.Conv3d(4, 8, 1).kernel.shape) == (4, 8)
+    assert set(spnn.Conv3d(4, 8, 2, stride=2, bias=True).state_dict()) == {"kernel", "bias"}
+    off = get_kernel_offsets(3)
+    assert off.dtype == torch.int32 and off[0].tolist() == [-1, -1, -1] and off[1].tolist() == [0, -1, -1] and off[13].tolist() == [0, 0, 0]
+    assert get_kernel_offsets(2, 4)[1].tolist() == [0, 0, 4]
+
+
+def test_collate_and_containers():
+    import taseg_b200
+    from taseg_b200.utils.collate import sparse_collate_fn
+    a = taseg_b200.SparseTensor(np.ones((3, 2), np.float32), np.zeros((3, 3), np.int32))
+    b = taseg_b200.SparseTensor(np.ones((2, 2), np.float32), np.ones((2, 3), np.int32))
+    out = sparse_collate_fn([{"lidar": a, "n": np.array([3]), "name": "a"}, {"lidar": b, "n": np.array([2]), "name": "b"}])
+    assert out["lidar"].C.dtype == torch.int32 and out["lidar"].C[:, 3].tolist() == [0, 0, 0, 1, 1]
+    assert out["n"].shape == (2, 1) and out["name"] == ["a", "b"] and out["lidar"].s == (1, 1, 1)
+    s = out["lidar"] + out["lidar"]
+    assert s.kmaps is out["lidar"].kmaps and s.cmaps is out["lidar"].cmaps and float(s.F.sum()) == 20.0
+    z = taseg_b200.PointTensor(torch.zeros(2, 2), torch.zeros(2, 4))
+    assert z.additional_features == {"idx_query": {}, "counts": {}} and (z + z).idx_query is z.idx_query

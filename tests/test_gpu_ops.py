@@ -1,0 +1,286 @@
+"""GPU parity tests, op level: every C-ABI entry point against the oracle / golden fixtures.
+Bit-exact for hashes, tables, kernel maps, voxel sets, indices; fp32 features within 1e-3 relative
+(max|a-b|/max|b|); bf16 tensor-core path within 2e-2."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+from oracle import data_oracle as D
+from oracle import ts_oracle as T
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ts():
+    import taseg_b200
+    taseg_b200.install_as_torchsparse()
+    return taseg_b200
+
+
+def cu(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    return t if dtype is None else t.to(dtype)
+
+
+def npy(t):
+    return t.detach().float().cpu().numpy() if t.is_floating_point() else t.detach().cpu().numpy()
+
+
+def random_cloud(seed, n=20000, span=60, batches=3, neg=True):
+    rng = np.random.default_rng(seed)
+    c = rng.integers(-span if neg else 0, span, (n, 3)).astype(np.int32)
+    b = rng.integers(0, batches, (n, 1)).astype(np.int32)
+    return np.concatenate([c, b], 1), rng
+
+
+def test_hash_and_query(ts, golden):
+    from taseg_b200.nn import functional as F
+    g = golden("ops_kat")
+    assert np.array_equal(npy(F.sphash(cu(g["hash_kat_in"]))), g["hash_kat"])
+    assert np.array_equal(npy(F.sphash(cu(g["coords"]))), g["hash"])
+    kh = F.sphash(cu(g["coords"]), cu(g["offsets_k3_s1"]))
+    assert np.array_equal(npy(kh), g["khash27"])
+    assert np.array_equal(npy(F.sphashquery(kh, cu(g["hash"]))), g["query27"])
+    # batch > 0 rows keep their own batch index (hash_cuda.cu:42-46)
+    c, _ = random_cloud(1)
+    off = T.get_kernel_offsets(2, 4)
+    assert np.array_equal(npy(F.sphash(cu(c), cu(off))), T.sphash(c, off))
+    # duplicates in references: first position wins; empty query
+    ref = np.array([5, 7, 5, 9, 7], np.int64)
+    q = np.array([[7, 5], [1, 9]], np.int64)
+    assert np.array_equal(npy(F.sphashquery(cu(q), cu(ref))), T.sphashquery(q, ref))
+    assert F.sphashquery(cu(np.zeros((0,), np.int64)), cu(ref)).numel() == 0
+
+
+def test_sort_pairs(ts):
+    from taseg_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for n, bits in [(1, 64), (257, 64), (5000, 40), (300001, 64)]:
+        keys = torch.randint(0, 2 ** 62, (n,), generator=g, device="cuda", dtype=torch.int64)
+        if bits < 64:
+            keys = keys & ((1 << bits) - 1)
+        keys[::7] = keys[0]                                   # duplicates: stability matters
+        ko, vo = ops.sort_pairs(keys, None, 0, bits)
+        ref_k, ref_i = torch.sort(keys, stable=True)
+        assert torch.equal(ko, ref_k) and torch.equal(vo.long(), ref_i), (n, bits)
+
+
+def test_unique_and_quantize(ts, golden):
+    from taseg_b200 import ops
+    from taseg_b200.nn import functional as F
+    from taseg_b200.utils.quantize import sparse_quantize
+    g = golden("ops_kat")
+    c, i, v = sparse_quantize(g["q_in"], 1, return_index=True, return_inverse=True)   # numpy in -> numpy out
+    assert np.array_equal(c, g["q_coords"]) and np.array_equal(i, g["q_inds"]) and np.array_equal(v, g["q_inv"])
+    c2 = sparse_quantize(cu(g["q_in"]))                                               # tensor in -> tensor out
+    assert c2.is_cuda and np.array_equal(npy(c2), g["q_coords"])
+    fc = np.random.default_rng(0).uniform(-3, 3, (5000, 3))
+    a = sparse_quantize(fc, 0.25, return_index=True, return_inverse=True)
+    b = T.sparse_quantize(fc, 0.25, return_index=True, return_inverse=True)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    # spdownsample: batches, negative coordinates (trunc toward zero), all strides on the path
+    c, _ = random_cloud(2)
+    cur = T.sparse_collate([np.unique(c[c[:, 3] == b][:, :3], axis=0) for b in range(3)], [np.zeros((1, 1))] * 3)[0]
+    for s in (1, 2, 4, 8):
+        want = T.spdownsample(cur, 2, 2, s)
+        got = F.spdownsample(cu(cur), 2, 2, s)
+        assert np.array_equal(npy(got), want), s
+        cur = want
+    # hash order (initial_voxelize)
+    uc, first, inv = ops.unique_coords(cu(c), want_index=True, want_inverse=True, by_hash=True)
+    h = T.sphash(c)
+    uh, fi, iv = np.unique(h, return_index=True, return_inverse=True)
+    assert np.array_equal(npy(uc), c[fi]) and np.array_equal(npy(first), fi) and np.array_equal(npy(inv), iv)
+    with pytest.raises(RuntimeError):
+        ops.unique_coords(cu(np.array([[1 << 20, 0, 0, 0]], np.int32)))
+    assert ops.unique_coords(cu(np.zeros((0, 4), np.int32))).shape == (0, 4)
+
+
+def test_kernel_maps_and_convs(ts, golden):
+    from taseg_b200 import SparseTensor
+    from taseg_b200.nn import functional as F
+    g = golden("ops_kat")
+    x = SparseTensor(cu(g["conv_in"]), cu(g["coords"]), 1)
+    y = F.conv3d(x, cu(g["conv_w3"]), 3)
+    nb, ns, sz = x.kmaps[((1, 1, 1), (3, 3, 3), (1, 1, 1), (1, 1, 1))]
+    assert nb.dtype == torch.int64 and np.array_equal(npy(nb), g["kmap3_nbmaps"]) and np.array_equal(npy(ns), g["kmap3_nbsizes"])
+    assert sz == (len(g["coords"]),) * 2
+    assert rel_err(npy(y.F), g["conv_out3"]) < 1e-3
+    y2 = F.conv3d(y, cu(g["conv_w2"]), 2, stride=2)
+    assert np.array_equal(npy(y2.C), g["coords_s2"]) and y2.s == (2, 2, 2)
+    nb, ns, _ = x.kmaps[((1, 1, 1), (2, 2, 2), (2, 2, 2), (1, 1, 1))]
+    assert np.array_equal(npy(nb), g["kmap2_nbmaps"]) and np.array_equal(npy(ns), g["kmap2_nbsizes"])
+    assert rel_err(npy(y2.F), g["conv_out2"]) < 1e-3
+    y3 = F.conv3d(y2, cu(g["conv_w3b"]), 3)
+    nb, ns, _ = x.kmaps[((2, 2, 2), (3, 3, 3), (1, 1, 1), (1, 1, 1))]
+    assert np.array_equal(npy(nb), g["kmap3s2_nbmaps"]) and np.array_equal(npy(ns), g["kmap3s2_nbsizes"])
+    assert rel_err(npy(y3.F), g["conv_out3b"]) < 1e-3
+    y4 = F.conv3d(y3, cu(g["conv_w1"]), 1)
+    assert rel_err(npy(y4.F), g["conv_out1"]) < 1e-3
+    y5 = F.conv3d(y4, cu(g["conv_wt"]), 2, stride=2, transposed=True)
+    assert y5.C is x.C and y5.s == (1, 1, 1) and rel_err(npy(y5.F), g["conv_outT"]) < 1e-3
+    with pytest.raises(KeyError):
+        F.conv3d(SparseTensor(cu(g["conv_in"]), cu(g["coords"]), 2), cu(g["conv_wt"][:, :5]), 2, stride=2, transposed=True)
+    with pytest.raises(ValueError):
+        F.conv3d(SparseTensor(cu(g["conv_in"][:, :3]), cu(g["coords"]), 1), cu(g["conv_w3"]), 3)
+    b = F.conv3d(x, cu(g["conv_w3"]), 3, bias=torch.ones(8, device="cuda"))
+    assert rel_err(npy(b.F), g["conv_out3"] + 1) < 1e-3
+
+
+def test_conv_backward(ts, golden):
+    from taseg_b200 import SparseTensor
+    from taseg_b200.nn import functional as F
+    g = golden("ops_kat")
+    xi = cu(g["conv_in"]).requires_grad_(True)
+    w = cu(g["conv_w3"]).requires_grad_(True)
+    x = SparseTensor(xi, cu(g["coords"]), 1)
+    y = F.conv3d(x, w, 3)
+    y.F.backward(cu(g["bwd_gy"]))
+    assert rel_err(npy(xi.grad), g["bwd_gx"]) < 1e-3 and rel_err(npy(w.grad), g["bwd_gw"]) < 1e-3
+    yi = cu(g["conv_out3"]).requires_grad_(True)
+    w2 = cu(g["conv_w2"]).requires_grad_(True)
+    yy = x.derive(yi)
+    F.conv3d(yy, w2, 2, stride=2).F.backward(cu(g["bwd2_gy"]))
+    assert rel_err(npy(yi.grad), g["bwd2_gx"]) < 1e-3 and rel_err(npy(w2.grad), g["bwd2_gw"]) < 1e-3
+    # transposed conv backward against the oracle
+    rng = np.random.default_rng(3)
+    nb, ns = g["kmap2_nbmaps"], g["kmap2_nbsizes"]
+    n_c = len(g["coords_s2"])
+    xin = rng.normal(size=(n_c, 16)).astype(np.float32)
+    wt = (rng.normal(size=(8, 16, 8)) * 0.2).astype(np.float32)
+    gy = rng.normal(size=(len(g["coords"]), 8)).astype(np.float32)
+    gx_ref, gw_ref = T.conv_backward(xin, gy, wt, nb, ns, transposed=True)
+    xt = cu(xin).requires_grad_(True)
+    wtt = cu(wt).requires_grad_(True)
+    coarse = SparseTensor(xt, cu(g["coords_s2"]), 2)
+    coarse.cmaps, coarse.kmaps = x.cmaps, x.kmaps
+    out = F.conv3d(coarse, wtt, 2, stride=2, transposed=True)
+    assert rel_err(npy(out.F), T.conv_forward(xin, wt, nb, ns, (len(g["coords"]), n_c), True)) < 1e-3
+    out.F.backward(cu(gy))
+    assert rel_err(npy(xt.grad), gx_ref) < 1e-3 and rel_err(npy(wtt.grad), gw_ref) < 1e-3
+
+
+def test_point_voxel_ops(ts, golden):
+    from taseg_b200 import ops
+    from taseg_b200.nn import functional as F
+    g = golden("ops_kat")
+    p = cu(g["pv_points"])
+    for s, cs in [(1, g["coords"]), (2, g["coords_s2"])]:
+        fl = torch.cat([torch.floor(p[:, :3] / s).int() * s, p[:, -1].int().view(-1, 1)], 1)
+        off = cu(T.get_kernel_offsets(2, s))
+        idx = F.sphashquery(F.sphash(fl, off), F.sphash(cu(cs)))
+        w = F.calc_ti_weights(p, idx, scale=s).transpose(0, 1).contiguous()
+        idx = idx.transpose(0, 1).contiguous()
+        assert np.array_equal(npy(idx), g[f"dv{s}_idx"]) and np.abs(npy(w) - g[f"dv{s}_w"]).max() < 1e-6
+        out = F.spdevoxelize(cu(g[f"dv{s}_feat"]), idx, w)
+        assert rel_err(npy(out), g[f"dv{s}_out"]) < 1e-5
+        # fused query (one kernel instead of hash+hash+table+~30 elementwise launches)
+        tab = ops.Table.from_coords(cu(cs))
+        i8, w8 = ops.trilinear_query(tab, p, s)
+        assert np.array_equal(npy(i8), g[f"dv{s}_idx"]) and np.abs(npy(w8) - g[f"dv{s}_w"]).max() < 1e-6
+        i8n, w8n = ops.trilinear_query(tab, p, s, nearest=True)
+        assert (npy(i8n)[:, 1:] == -1).all() and (npy(w8n)[:, 1:] == 0).all() and np.array_equal(npy(i8n)[:, 0], g[f"dv{s}_idx"][:, 0])
+        iq = F.sphashquery(F.sphash(fl), F.sphash(cu(cs)))
+        assert np.array_equal(npy(ops.point_query(tab, p, s)), npy(iq))
+        assert np.array_equal(npy(F.spcount(iq.int(), len(cs))), g[f"vx{s}_cnt"])
+        vo = F.spvoxelize(cu(g[f"vx{s}_feat"]), cu(g[f"vx{s}_idx"]), cu(g[f"vx{s}_cnt"]))
+        assert rel_err(npy(vo), g[f"vx{s}_out"]) < 1e-5
+        # backward of both against the oracle
+        gyv = np.random.default_rng(s).normal(size=g[f"vx{s}_out"].shape).astype(np.float32)
+        f_in = cu(g[f"vx{s}_feat"]).requires_grad_(True)
+        F.spvoxelize(f_in, cu(g[f"vx{s}_idx"]), cu(g[f"vx{s}_cnt"])).backward(cu(gyv))
+        assert rel_err(npy(f_in.grad), T.spvoxelize_backward(gyv, g[f"vx{s}_idx"], g[f"vx{s}_cnt"], len(g[f"vx{s}_idx"]))) < 1e-5
+        gyd = np.random.default_rng(s + 9).normal(size=g[f"dv{s}_out"].shape).astype(np.float32)
+        vf = cu(g[f"dv{s}_feat"]).requires_grad_(True)
+        F.spdevoxelize(vf, idx, w).backward(cu(gyd))
+        assert rel_err(npy(vf.grad), T.spdevoxelize_backward(gyd, g[f"dv{s}_idx"], g[f"dv{s}_w"], len(cs))) < 1e-5
+    # 16-bit storage paths
+    hf = F.spdevoxelize(cu(g["dv1_feat"]).bfloat16(), cu(g["dv1_idx"]), cu(g["dv1_w"]))
+    assert hf.dtype == torch.bfloat16 and rel_err(npy(hf), g["dv1_out"]) < 2e-2
+
+
+def test_fuse_and_aggregate(ts, golden):
+    from taseg_b200 import ops
+    g = golden("fuse_kat")
+    for sfx, psfx in [("", ""), ("2", "_2")]:
+        out = ops.fuse_multi_scan(cu(g["points" + sfx]), g["pose0" + psfx], g["pose" + psfx])
+        assert np.array_equal(npy(out).view(np.uint32), g["fused" + sfx].view(np.uint32))
+    # nuScenes-style float64 transform
+    rng = np.random.default_rng(0)
+    R = np.linalg.qr(rng.normal(size=(3, 3)))[0]
+    Tt = rng.normal(size=3) * 10
+    pts = rng.normal(size=(5000, 5)).astype(np.float32) * 30
+    got = npy(ops.transform_point(cu(pts), R, Tt))
+    want = D.transform_point(pts, R, Tt)
+    assert (got.view(np.uint32) != want.view(np.uint32)).mean() < 1e-4 and np.abs(got - want).max() < 1e-5
+    # whole front end, batch of 2 samples x 3 frames, against the data oracle
+    from taseg_b200 import synth
+    spec = synth.SensorSpec(16, -24.8, 2.0, 300, 1.73, 60.0)
+    frames_all, descr, want_feats, want_coords, want_n0 = [], [], [], [], []
+    off = 0
+    for b in range(2):
+        frames, poses = synth.kitti_sample(100 + b, 3, spec=spec, n_boxes=30)
+        ms, n0 = D.aggregate_kitti(frames, poses)
+        q = D.quantize_ms(ms[:n0], ms, 0.05)
+        want_feats.append(q["point_ms"])
+        want_coords.append(np.concatenate([q["pc_ms_"], np.full((len(q["pc_ms_"]), 1), b, np.int32)], 1))
+        order = [0] + list(range(len(frames) - 1, 0, -1))       # current first, then history oldest first
+        for j in order:
+            descr.append(dict(offset=off, count=len(frames[j]), sample=b, is_cur=int(j == 0), pose0=poses[0], pose=poses[j]))
+            frames_all.append(frames[j])
+            off += len(frames[j])
+    feats, coords, flags = ops.aggregate_quantize(cu(np.concatenate(frames_all)), descr, 2, 0.05)
+    f2, c2, _, m = ops.compact_rows(flags, feats, coords)
+    wf, wc = np.concatenate(want_feats), np.concatenate(want_coords)
+    assert m == len(wf)
+    assert np.array_equal(npy(f2).view(np.uint32), wf.view(np.uint32)) and np.array_equal(npy(c2), wc)
+
+
+def _tc_case(seed, n, c0, c1, c_out, ks, relu, residual, out_dtype, dense_span):
+    from taseg_b200 import ops
+    rng = np.random.default_rng(seed)
+    c = np.unique(rng.integers(0, dense_span, (n, 3)).astype(np.int32), axis=0)
+    c = np.concatenate([c, np.zeros((len(c), 1), np.int32)], 1)
+    n = len(c)
+    offs = T.get_kernel_offsets(ks, 1)
+    k = len(offs)
+    tab = ops.Table.from_coords(cu(c))
+    km = ops.build_kmap(tab, n, cu(c), offs)
+    x0 = torch.randn(n, c0, device="cuda").bfloat16()
+    x1 = torch.randn(n, c1, device="cuda").bfloat16() if c1 else None
+    w = (torch.randn(k, c0 + c1, c_out, device="cuda") * 0.1)
+    bias = torch.randn(c_out, device="cuda")
+    res = torch.randn(n, c_out, device="cuda").bfloat16() if residual else None
+    packed = ops.pack_weights(w, c0, c1)
+    got = ops.conv_forward_tc(x0, x1, packed, k, c_out, km.nbr, km.tile_mask(), n, bias=bias, residual=res, relu=relu,
+                              out_dtype=out_dtype)
+    xin = torch.cat([x0, x1], 1).float() if c1 else x0.float()
+    want = ops.conv_forward(xin, w.bfloat16().float(), km.nbr, n, bias=bias, residual=res.float() if residual else None, relu=relu)
+    torch.cuda.synchronize()
+    return rel_err(npy(got), npy(want)), n
+
+
+@pytest.mark.parametrize("c0,c1,c_out,ks", [(16, 0, 32, 3), (32, 0, 32, 3), (64, 0, 64, 3), (96, 32, 96, 3), (128, 0, 128, 3),
+                                            (256, 128, 256, 3), (32, 0, 32, 2), (128, 64, 128, 1), (256, 0, 256, 3)])
+def test_conv_tensor_core(ts, c0, c1, c_out, ks):
+    err, n = _tc_case(c0 + c_out, 30000, c0, c1, c_out, ks, True, True, torch.bfloat16, 40)
+    assert err < 2e-2, (err, n)
+    err, n = _tc_case(c0 + c_out + 1, 700, c0, c1, c_out, ks, False, False, torch.float32, 12)   # partial last tile
+    assert err < 1e-2, (err, n)
+
+
+def test_backend_mirror(ts, golden):
+    from taseg_b200 import backend as B
+    g = golden("ops_kat")
+    x, w = cu(g["conv_in"]), cu(g["conv_w3"])
+    out = torch.zeros(len(g["coords"]), 8, device="cuda")
+    B.convolution_forward_cuda(x, out, w, cu(g["kmap3_nbmaps"]).int(), torch.from_numpy(g["kmap3_nbsizes"]).int(), False)
+    assert rel_err(npy(out), g["conv_out3"]) < 1e-3
+    gx, gw = torch.zeros_like(x), torch.zeros_like(w)
+    B.convolution_backward_cuda(x, gx, cu(g["bwd_gy"]), w, gw, cu(g["kmap3_nbmaps"]).int(), torch.from_numpy(g["kmap3_nbsizes"]).int(), False)
+    assert rel_err(npy(gx), g["bwd_gx"]) < 1e-3 and rel_err(npy(gw), g["bwd_gw"]) < 1e-3
+    q = B.hash_query_cuda(cu(g["khash27"]).reshape(-1), cu(g["hash"]), torch.arange(len(g["hash"]), device="cuda"))
+    assert np.array_equal(npy(q).reshape(27, -1) - 1, g["query27"])
+    assert np.array_equal(npy(B.hash_cuda(cu(g["coords"]))), g["hash"])
