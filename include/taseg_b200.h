@@ -212,6 +212,8 @@ int tsg_conv_wgrad(const float *in, int64_t n_in, int c_in, const float *grad_ou
  * The A operand may come from two feature tensors (channel concat of a decoder feature and its encoder skip,
  * TS/operators.py:10-17, without materialising the concat): in0 (n_in, c0) then in1 (n_in, c1); c1 may be 0.
  * c0, c1, c_out multiples of 16; c_out <= 256.  tile_mask (ceil(n_out/128)) uint32 from tsg_kmap_tile_mask.
+ * nbr == NULL means the identity map (row o reads row o for every k: 1x1x1 convolutions and point MLPs) and
+ * tile_mask == NULL means every offset is active.
  * out dtype TSG_BF16 or TSG_F32. */
 size_t tsg_conv_pack_bytes(int k, int c0, int c1, int c_out);
 int tsg_conv_pack_weights(const float *weight, int k, int c_in, int c_out, int c0, int c1,

@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
     uint32_t it = 0;
     for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const uint32_t buf = it & 1, ph = (it >> 1) & 1;
-      const unsigned mask = p.tile_mask[tile];
+      const unsigned mask = p.tile_mask ? p.tile_mask[tile] : 0xffffffffu;
       mbar_wait(tfull0 + 8 * buf, ph);
       tc_fence_after();
       const long long row = tile * TC_BM + warp * 32 + lane;
@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
       uint32_t it = 0, unit = 0;
       for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
         const uint32_t buf = it & 1, ph = (it >> 1) & 1;
-        const unsigned mask = p.tile_mask[tile];
+        const unsigned mask = p.tile_mask ? p.tile_mask[tile] : 0xffffffffu;
         mbar_wait(tempty0 + 8 * buf, ph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * (uint32_t)p.c_out;
@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
     const int chunk = pt & 7, rsub = pt >> 3;              // 8 lanes cover one 128-byte row; 16 rows per pass
     uint32_t unit = 0, arrived = 0;                        // units issued / units signalled on their full barrier
     for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const unsigned mask = p.tile_mask[tile];
+      const unsigned mask = p.tile_mask ? p.tile_mask[tile] : 0xffffffffu;
       const long long m0 = tile * TC_BM;
       for (int k = 0; k < p.K; ++k) {
         if (!((mask >> k) & 1u)) continue;
@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           const long long o = m0 + rsub + 16 * q;
-          src[q] = o < p.n_out ? __ldg(p.nbr + (long long)k * p.n_out + o) : -1;
+          src[q] = o < p.n_out ? (p.nbr ? __ldg(p.nbr + (long long)k * p.n_out + o) : (int)o) : -1;
         }
         for (int j = 0; j < KB; ++j, ++unit) {
           const uint32_t s = unit % p.stages, sph = (unit / p.stages) & 1;

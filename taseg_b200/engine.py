@@ -1,0 +1,224 @@
+"""Eval-mode inference engine: the backbone forward as a fused bf16 tcgen05 pipeline.
+
+`Engine(model)` walks a MinkUNet / MinkUNetMs / SPVCNN from taseg_b200.segmentor (reference parameter names) and
+compiles every Conv3d+BatchNorm(+ReLU)(+residual add) group into ONE tensor-core launch:
+  * BatchNorm running statistics are folded: scale into the packed bf16 weights, shift into the epilogue bias;
+  * ReLU and the residual add run in the epilogue on the fp32 accumulator read from TMEM;
+  * `torchsparse.cat([y, skip])` is never materialised — the next convolution gathers from both tensors;
+  * 1x1x1 shortcut convolutions and point MLPs use the same kernel with the identity map;
+  * the classifier is applied per scale at VOXEL level (Linear is linear: devox(F) @ W == devox(F @ W)), so the
+    trilinear devoxelisation moves num_class instead of 256+128+96 channels per point (voxel nets only).
+Activations stay bf16 (N, C) with C padded to a multiple of 16; accumulation is fp32.  Results agree with the fp32
+module path to bf16 round-off (tests state the bound); kernel maps / voxel sets are the same bit-exact objects.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+from torch import nn
+
+from . import ops
+from .nn.modules.conv import Conv3d
+from .nn.utils.kernel import kernel_offsets_np
+from .segmentor.unet import _SparseUNet
+
+pad16 = ops.pad16
+
+
+def _fold(bn: Optional[nn.Module], c_out: int, device):
+    if bn is None:
+        return torch.ones(c_out, device=device), torch.zeros(c_out, device=device)
+    scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+    return scale, bn.bias.detach().float() - bn.running_mean.detach().float() * scale
+
+
+class FusedConv:
+    """Conv3d (+BN) compiled for tsg_conv_fwd_tc.  r0/r1 = real channels of the (up to) two input tensors."""
+
+    def __init__(self, kernel: torch.Tensor, bn, r0: int, r1: int = 0, relu: bool = False, bias: Optional[torch.Tensor] = None):
+        w = kernel.detach().float()
+        if w.dim() == 2:
+            w = w.unsqueeze(0)
+        k, c_in, c_out = w.shape
+        assert c_in == r0 + r1, (c_in, r0, r1)
+        self.k, self.c_out, self.relu = k, c_out, relu
+        self.c0, self.c1, self.c_out_pad = pad16(r0), pad16(r1) if r1 else 0, pad16(c_out)
+        scale, shift = _fold(bn, c_out, w.device)
+        if bias is not None:
+            shift = shift + bias.detach().float() * scale
+        wp = torch.zeros((k, self.c0 + self.c1, self.c_out_pad), device=w.device)
+        wp[:, :r0, :c_out] = w[:, :r0] * scale
+        if r1:
+            wp[:, self.c0:self.c0 + r1, :c_out] = w[:, r0:] * scale
+        self.packed = ops.pack_weights(wp, self.c0, self.c1)
+        self.bias = torch.zeros(self.c_out_pad, device=w.device)
+        self.bias[:c_out] = shift
+
+    def __call__(self, x0, x1, nbr, tile_mask, n_out, residual=None, out_dtype=torch.bfloat16):
+        return ops.conv_forward_tc(x0, x1, self.packed, self.k, self.c_out_pad, nbr, tile_mask, n_out, bias=self.bias,
+                                   residual=residual, relu=self.relu, out_dtype=out_dtype)
+
+
+class FusedBlock:
+    """ResidualBlock: conv-BN-ReLU, conv-BN, (+ 1x1 conv-BN shortcut), add, ReLU."""
+
+    def __init__(self, block, r0: int, r1: int = 0):
+        net = block.net
+        assert isinstance(net[0], Conv3d) and len(net) == 5, "engine supports ResBlock (the only block TASeg configures)"
+        self.a = FusedConv(net[0].kernel, net[1], r0, r1, relu=True)
+        self.b = FusedConv(net[3].kernel, net[4], net[3].in_channels, 0, relu=True)
+        self.shortcut = None
+        if not isinstance(block.downsample, nn.Identity):
+            self.shortcut = FusedConv(block.downsample[0].kernel, block.downsample[1], r0, r1, relu=False)
+
+    def __call__(self, x0, x1, km):
+        n = km.n_out
+        h = self.a(x0, x1, km.nbr, km.tile_mask(), n)
+        res = self.shortcut(x0, x1, None, None, n) if self.shortcut is not None else x0
+        return self.b(h, None, km.nbr, km.tile_mask(), n, residual=res)
+
+
+class Level:
+    __slots__ = ("stride", "coords", "n", "table", "km3", "km2")
+
+
+class Geometry:
+    """Voxel pyramid of one batch: coordinates, tables and kernel maps at tensor strides 1..16."""
+
+    def __init__(self, coords: torch.Tensor, n_levels: int = 5):
+        self.levels: List[Level] = []
+        c = coords.contiguous()
+        for l in range(n_levels):
+            lv = Level()
+            lv.stride, lv.coords, lv.n = 2 ** l, c, c.shape[0]
+            lv.table = ops.Table.from_coords(c)
+            lv.km3 = ops.build_kmap(lv.table, lv.n, c, kernel_offsets_np(3, lv.stride))
+            lv.km2 = None
+            if l + 1 < n_levels:
+                nxt = ops.unique_coords(c, trunc_stride=2 * lv.stride)
+                lv.km2 = ops.build_kmap(lv.table, lv.n, nxt, kernel_offsets_np(2, lv.stride))
+                c = nxt
+            self.levels.append(lv)
+
+
+class Engine:
+    def __init__(self, model: _SparseUNet):
+        assert not model.training, "Engine folds BatchNorm running statistics: call model.eval() first"
+        self.model = model
+        self.spv, self.voxelize_input = model.point_branch, model.voxelize_input
+        self.in_dim, self.num_class = model.in_feature_dim, model.num_class
+        self.pres, self.vres = model.pres, model.vres
+        st = model.stem
+        c = st[0].out_channels
+        self.stem = [FusedConv(st[0].kernel, st[1], self.in_dim, relu=True), FusedConv(st[3].kernel, st[4], c, relu=True)]
+        self.down, self.enc = [], []
+        width = c
+        skip_w = [c]
+        for i in range(4):
+            stage = getattr(model, f"stage{i + 1}")
+            self.down.append(FusedConv(stage[0].net[0].kernel, stage[0].net[1], width, relu=True))
+            blocks = []
+            for blk in list(stage)[1:]:
+                blocks.append(FusedBlock(blk, width))
+                width = blk.net[3].out_channels
+            self.enc.append(blocks)
+            skip_w.append(width)
+        self.up, self.dec = [], []
+        for i in range(4):
+            up = getattr(model, f"up{i + 1}")
+            self.up.append(FusedConv(up[0].net[0].kernel, up[0].net[1], width, relu=True))
+            width = up[0].net[0].out_channels
+            skip = skip_w[3 - i]
+            blocks = []
+            for j, blk in enumerate(up[1]):
+                blocks.append(FusedBlock(blk, width, skip) if j == 0 else FusedBlock(blk, width))
+                width = blk.net[3].out_channels
+            self.dec.append(blocks)
+        lin = model.classifier[0]
+        self.head_dims = [skip_w[4], self.dec[1][-1].b.c_out, self.dec[3][-1].b.c_out]
+        wt = lin.weight.detach().float().t().contiguous()                 # (480, num_class)
+        if self.spv:
+            self.head = FusedConv(wt, None, wt.shape[0], bias=lin.bias)
+            self.mlps = []
+            for seq in model.point_transforms:
+                self.mlps.append(FusedConv(seq[0].weight.detach().float().t().contiguous(), seq[1], seq[0].in_features,
+                                           relu=True, bias=seq[0].bias))
+        else:
+            offs = [0, self.head_dims[0], self.head_dims[0] + self.head_dims[1]]
+            self.heads = [FusedConv(wt[offs[i]:offs[i] + self.head_dims[i]], None, self.head_dims[i],
+                                    bias=lin.bias if i == 2 else None) for i in range(3)]
+
+    # ------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def __call__(self, coords: torch.Tensor, feats: torch.Tensor, return_geometry: bool = False):
+        """coords (N,4) int32 [x,y,z,b], feats (N,>=in_dim) fp32 -> logits (N, num_class) fp32, one row per input row."""
+        feats = feats[:, :self.in_dim].float().contiguous()
+        zc = coords.float().contiguous()
+        if self.voxelize_input:      # initial_voxelize (minkunet/utils.py:11-36)
+            zc, floor_c = ops.rescale_coords(zc, self.pres, self.vres)
+            vox, _, inv0 = ops.unique_coords(floor_c, want_index=True, want_inverse=True, by_hash=True)
+            cnt0 = ops.spcount(inv0, vox.shape[0])
+            x_f = ops.voxelize_forward(feats, inv0, cnt0)
+            vox = vox.contiguous()
+        else:
+            vox, x_f = coords.contiguous(), feats
+        geo = Geometry(vox)
+        L = geo.levels
+        x = ops.cast_pad_bf16(x_f, self.stem[0].c0)
+        for conv in self.stem:
+            x = conv(x, None, L[0].km3.nbr, L[0].km3.tile_mask(), L[0].n)
+        x0 = x
+        q1 = ops.trilinear_query(L[0].table, zc, 1)
+        q16 = ops.trilinear_query(L[4].table, zc, 16)
+        q4 = ops.trilinear_query(L[2].table, zc, 4)
+        if self.spv:
+            z0 = ops.devoxelize_forward(x0, *q1)
+            p2v1 = (inv0, cnt0)
+            x = ops.voxelize_forward(z0, *p2v1)
+        skips = [x0]
+        for i in range(4):
+            km2 = L[i].km2
+            x = self.down[i](x, None, km2.nbr, km2.tile_mask(), km2.n_out)
+            for blk in self.enc[i]:
+                x = blk(x, None, L[i + 1].km3)
+            skips.append(x)
+        x4 = x
+        if self.spv:
+            z1 = ops.devoxelize_forward(x4, *q16) + self.mlps[0](z0, None, None, None, z0.shape[0])
+            i16 = ops.point_query(L[4].table, zc, 16)
+            x = ops.voxelize_forward(z1, i16, ops.spcount(i16, L[4].n))
+        ys = []
+        for i in range(4):
+            lv = L[3 - i]
+            km2 = lv.km2
+            x = self.up[i](x, None, km2.nbr_t, km2.tile_mask(True), lv.n)
+            skip = skips[3 - i]
+            for j, blk in enumerate(self.dec[i]):
+                x = blk(x, skip if j == 0 else None, lv.km3)
+            ys.append(x)
+            if self.spv and i == 1:
+                z2 = ops.devoxelize_forward(x, *q4) + self.mlps[1](z1, None, None, None, z1.shape[0])
+                i4 = ops.point_query(L[2].table, zc, 4)
+                x = ops.voxelize_forward(z2, i4, ops.spcount(i4, L[2].n))
+        y2, y4 = ys[1], ys[3]
+        if self.spv:
+            z3 = ops.devoxelize_forward(y4, *q1) + self.mlps[2](z2, None, None, None, z2.shape[0])
+            cat = torch.cat([z1[:, :self.head_dims[0]], z2[:, :self.head_dims[1]], z3[:, :self.head_dims[2]]], dim=1)
+            if cat.shape[1] % 16:
+                cat = torch.nn.functional.pad(cat, (0, pad16(cat.shape[1]) - cat.shape[1]))
+            logits = self.head(cat.contiguous(), None, None, None, cat.shape[0], out_dtype=torch.float32)
+        else:
+            l16 = self.heads[0](x4, None, None, None, L[4].n, out_dtype=torch.float32)
+            l4 = self.heads[1](y2, None, None, None, L[2].n, out_dtype=torch.float32)
+            l1 = self.heads[2](y4, None, None, None, L[0].n, out_dtype=torch.float32)
+            logits = ops.devoxelize_forward(l16, *q16) + ops.devoxelize_forward(l4, *q4) + ops.devoxelize_forward(l1, *q1)
+        logits = logits[:, :self.num_class]
+        return (logits, geo) if return_geometry else logits
+
+    @torch.no_grad()
+    def forward_batch(self, batch_dict, return_logit=False, return_tta=False):
+        """Same batch_dict in / result dict out as the reference model's eval forward."""
+        x = batch_dict[self.model.lidar_key]
+        out = self(x.C, x.F)
+        return self.model.eval_outputs(batch_dict, x, out, return_logit or return_tta)

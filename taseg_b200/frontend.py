@@ -1,0 +1,57 @@
+"""Device-side data front end of the multi-frame path: raw per-frame points + poses -> collated, de-duplicated
+voxels ready for MinkUNetMs, replacing the reference's CPU DataLoader work
+(R/pcseg/data/dataset/semantickitti/semantickitti_ms.py:140-149,253-320 multiscan_fuse/append_time_flag,
+ R/pcseg/data/dataset/semantickitti/semantickitti_voxel_ms.py:121-187 clamp/round/shift/sparse_quantize,
+ :189-212 collate_batch).  Three device passes + one radix sort per BATCH instead of numpy per sample.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import ops
+from .tensor import SparseTensor
+
+
+class MultiFrameBatch:
+    """Host-side description of a batch: sample b = [current scan, history scans oldest first]."""
+
+    def __init__(self, samples: Sequence[Sequence[np.ndarray]], poses: Sequence[Sequence[np.ndarray]]):
+        self.frames: List[dict] = []
+        chunks, cur_idx, self.n_cur = [], [], []
+        off = 0
+        for b, (frs, pss) in enumerate(zip(samples, poses)):
+            order = [0] + list(range(len(frs) - 1, 0, -1))     # delta = -MULTISCAN..-1 (semantickitti_ms.py:271)
+            for j in order:
+                n = len(frs[j])
+                self.frames.append(dict(offset=off, count=n, sample=b, is_cur=int(j == 0), pose0=pss[0], pose=pss[j]))
+                chunks.append(np.asarray(frs[j], np.float32))
+                if j == 0:
+                    cur_idx.append(np.arange(off, off + n, dtype=np.int64))
+                    self.n_cur.append(n)
+                off += n
+        self.n_samples = len(samples)
+        self.points = np.ascontiguousarray(np.concatenate(chunks, 0))
+        self.cur_idx = np.concatenate(cur_idx)
+        self.total = off
+
+
+def aggregate_voxelize(points: torch.Tensor, batch: MultiFrameBatch, voxel_size: float, cur_idx: torch.Tensor,
+                       keep: Optional[torch.Tensor] = None):
+    """points (sum n, 4) fp32 on the device (layout of `batch`).  Returns dict:
+    coords (M,4) int32 [x,y,z,b] / feats (M,5) [x,y,z,i,t] of the de-duplicated voxels (lidar_ms),
+    inverse (N') voxel row of every kept point, cur_rows (sum n_cur) voxel row of every current-scan point,
+    point_ms (N',5), pc_ms (N',4), inds (M)."""
+    feats, coords, flags = ops.aggregate_quantize(points, batch.frames, batch.n_samples, voxel_size, keep)
+    point_ms, pc_ms, pos, _ = ops.compact_rows(flags, feats, coords, want_pos=True)
+    vox, first, inverse = ops.unique_coords(pc_ms, want_index=True, want_inverse=True)
+    vfeat = ops.gather_rows(point_ms, first)
+    cur_rows = inverse[pos[cur_idx].long()]
+    return dict(coords=vox, feats=vfeat, inverse=inverse, cur_rows=cur_rows, point_ms=point_ms, pc_ms=pc_ms, inds=first,
+                pos=pos)
+
+
+def as_lidar_ms(out: dict) -> SparseTensor:
+    return SparseTensor(out["feats"], out["coords"], 1)

@@ -61,7 +61,7 @@ def test_sort_pairs(ts):
         keys = torch.randint(0, 2 ** 62, (n,), generator=g, device="cuda", dtype=torch.int64)
         if bits < 64:
             keys = keys & ((1 << bits) - 1)
-        keys[::7] = keys[0]                                   # duplicates: stability matters
+        keys[::7] = keys[0].clone()                                   # duplicates: stability matters
         ko, vo = ops.sort_pairs(keys, None, 0, bits)
         ref_k, ref_i = torch.sort(keys, stable=True)
         assert torch.equal(ko, ref_k) and torch.equal(vo.long(), ref_i), (n, bits)
