@@ -1,0 +1,268 @@
+#!/usr/bin/env python3
+"""Benchmark of the hot path: scans/sec of the TASeg multi-frame MinkUNet backbone forward (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one batch of B=4 three-frame SemanticKITTI-shaped samples per GPU through
+  device front end (pose warp + time flag + clamp + quantise + dedup/collate)  ->  MinkUNetMs mk34 cr1.0 (63 sparse
+  convolutions, bf16 tcgen05 engine)  ->  per-point logits of the current scans.
+`value` times it with raw points resident in HBM; `e2e` includes the pinned-host -> device copy of the points and the
+device -> host copy of the logits every step.  `--impl reference` times the reference's own CPU implementation
+(oracle/_ref torchsparse backend + restated Python glue) on a bounded sample, rank 0 only.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "scans/sec (TASeg backbone fwd, 3-frame KITTI-shape)"
+UNIT = "scans/s"
+BATCH = 4
+N_FRAMES = 3
+VOXEL = 0.05
+SECTOR = 1.0 / 16      # bounded sample for the CPU arms
+WORKLOAD = ("configs[1]: TASeg MinkUNetMs mk34 cr1.0 (IN_FEATURE_DIM 5, 20 classes), 3-frame temporal aggregation, "
+            "SemanticKITTI shape (64x2048 rays/scan, 0.05 m voxels), batch 4 per GPU")
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return dict(bf16=d.get("bf16_tflops_sustained", 1391.8), hbm=d.get("hbm_gbs", 6455.6), source="measured")
+    return dict(bf16=1400.0, hbm=6650.0, source="fallback")
+
+
+def make_model(device="cuda"):
+    import torch
+    from taseg_b200.segmentor import MinkUNetMs, ModelCfg
+    torch.manual_seed(0)
+    cfg = ModelCfg(IN_FEATURE_DIM=5, BLOCK="ResBlock", NUM_LAYER=[2, 3, 4, 6, 2, 2, 2, 2], cr=1.0,
+                   PLANES=[32, 32, 64, 128, 256, 256, 128, 96, 96], pres=0.05, vres=0.05, IF_DIST=False, IGNORE_LABEL=0,
+                   DROPOUT_P=0.0)
+    model = MinkUNetMs(cfg, 20)
+    g = torch.Generator().manual_seed(1)
+    for m in model.modules():
+        if isinstance(m, torch.nn.BatchNorm1d):     # non-trivial eval-mode BN
+            m.running_mean.copy_(torch.randn(m.num_features, generator=g) * 0.1)
+            m.running_var.copy_(torch.rand(m.num_features, generator=g) + 0.5)
+    return model.to(device).eval()
+
+
+def make_samples(first_seed, count):
+    from concurrent.futures import ProcessPoolExecutor
+    from taseg_b200 import synth
+    with ProcessPoolExecutor(max_workers=min(count, os.cpu_count() or 1)) as ex:
+        return list(ex.map(synth.kitti_sample, [first_seed + i for i in range(count)], [N_FRAMES] * count))
+
+
+class ClockSampler(threading.Thread):
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.rows, self.proc, self.index = [], None, index
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+
+    def summary(self, t0, t1):
+        rows = [r for t, r in self.rows if t0 <= t <= t1 and len(r) >= 7] or [r for _, r in self.rows if len(r) >= 7]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in rows)]
+        f = lambda v: float(v) if v.replace(".", "", 1).isdigit() else float("nan")
+        return {"sm_mhz": statistics.median(f(r[0]) for r in rows), "sm_max_mhz": f(rows[0][1]),
+                "power_w_max": max(f(r[2]) for r in rows), "samples": len(rows), "reasons": reasons}
+
+
+def cpu_reference_step(frames, poses, net):
+    """The reference CPU path for one bounded sample: numpy fuse + round + sparse_quantize + collate, then the backbone on
+    the reference's compiled torchsparse CPU backend (oracle/_ref).  Returns seconds."""
+    from oracle import data_oracle as D
+    from oracle import ts_oracle as T
+    t0 = time.perf_counter()
+    ms, n0 = D.aggregate_kitti(frames, poses)
+    q = D.quantize_ms(ms[:n0], ms, VOXEL)
+    coords, feats = T.sparse_collate([q["pc_ms"]], [q["feat_ms"]])
+    logits = net.minkunet_ms(coords, feats)
+    _ = logits[q["inverse_map_ms"]][:n0]
+    return time.perf_counter() - t0, len(coords)
+
+
+def cpu_arm(steps, warmup, seed=2000):
+    import torch
+    from oracle import net_oracle as N
+    from oracle import ref_backend as RB
+    from taseg_b200 import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    kind = "reference" if RB.available() else "port"
+    ops = RB.RefOps if kind == "reference" else N.NumpyOps
+    model = make_model("cpu")
+    net = N.Net({k: v.numpy() for k, v in model.state_dict().items()}, ops=ops)
+    frames, poses = synth.kitti_sample(seed, N_FRAMES)
+    frames = [synth.sector(f, SECTOR) for f in frames]
+    times, nvox = [], 0
+    for i in range(warmup + steps):
+        t, nvox = cpu_reference_step(frames, poses, net)
+        if i >= warmup:
+            times.append(t)
+    t = statistics.median(times)
+    sample = ("one 3-frame scan restricted to a %.1f deg azimuth sector (1/%d of the rays, %d voxels); "
+              "scans/s = (1/%d scan)/t, t = median of %d runs" % (360 * SECTOR, round(1 / SECTOR), nvox, round(1 / SECTOR), len(times)))
+    return dict(value=SECTOR / t, unit=UNIT, cores=cores, kind=kind, sample=sample, seconds_per_sample=t)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    config = {"workload": WORKLOAD, "batch_per_gpu": BATCH, "frames": N_FRAMES, "voxel_size": VOXEL,
+              "l2": "no flush: every step streams >1 GB of activations and kernel maps through the 126 MB L2"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cb = cpu_arm(max(1, args.steps), max(0, min(args.warmup, 1)))
+        line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["seconds_per_sample"] * 1e3,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": config, "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from taseg_b200 import _lib, frontend, ops
+    from taseg_b200.engine import Engine
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    _lib.lib()
+    model = make_model()
+    engine = Engine(model)
+    samples = make_samples(2000 + rank * BATCH, BATCH)          # seed = 1000*config_id + sample_idx
+    mfb = frontend.MultiFrameBatch([s[0] for s in samples], [s[1] for s in samples])
+    host_pts = torch.from_numpy(mfb.points).pin_memory()
+    pts = host_pts.cuda()
+    cur_idx = torch.from_numpy(mfb.cur_idx).cuda()
+    n_cur = int(sum(mfb.n_cur))
+    host_out = torch.empty((n_cur, 20), dtype=torch.float32).pin_memory()
+
+    def step():
+        out = frontend.aggregate_voxelize(pts, mfb, VOXEL, cur_idx)
+        logits = engine(out["coords"], out["feats"])
+        return ops.gather_rows(logits.contiguous(), out["cur_rows"])
+
+    def step_e2e():
+        pts.copy_(host_pts, non_blocking=True)
+        host_out.copy_(step(), non_blocking=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0 = time.time()
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), w0, time.time()
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else
+                           int(os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local_rank]))
+    sampler.start()
+    time.sleep(0.3)
+    launches0 = _lib.launch_count
+    ms, w0, w1 = timed(step, args.steps)
+    launches = _lib.launch_count - launches0
+    for _ in range(2):
+        step_e2e()
+    ms_e2e, _, w2 = timed(step_e2e, args.steps)
+    sampler.stop()
+    clocks = sampler.summary(w0, w2)
+
+    # roofline of the dominant kernel (conv_tc_kernel): algorithmic FLOPs / CUDA-event time of its launches in one step
+    ops.PROFILE = []
+    torch.cuda.synchronize()
+    es, ee = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    es.record()
+    step()
+    ee.record()
+    torch.cuda.synchronize()
+    prof, ops.PROFILE = ops.PROFILE, None
+    conv_ms = sum(e0.elapsed_time(e1) for _, e0, e1, *_ in prof)
+    flops = sum(2.0 * float(p.item()) * cin * cout for _, _, _, p, cin, cout, _ in prof)
+    pk = peaks()
+    achieved = flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("conv_tc_kernel_dram_bytes_per_step")
+    roofline = {"bound": "tensor", "kernel": "conv_tc_kernel (all %d launches of one step)" % len(prof),
+                "achieved": achieved, "peak": pk["bf16"], "unit": "TFLOP/s", "frac": achieved / pk["bf16"],
+                "peak_source": pk["source"] + " bf16_tflops_sustained", "traffic": traffic,
+                "algorithmic_gflop_per_step": flops / 1e9, "kernel_ms_per_step": conv_ms,
+                "kernel_share_of_step": conv_ms / es.elapsed_time(ee)}
+
+    if rank == 0:
+        scans = BATCH * world * args.steps
+        line = {"metric": METRIC, "value": scans / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config,
+                "e2e": {"value": scans / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": host_pts.numel() * 4,
+                        "d2h_bytes_per_step": host_out.numel() * 4, "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+                "points_per_step": int(mfb.total), "current_points_per_step": n_cur}
+        if world == 1 and not args.no_cpu_baseline:
+            cb = cpu_arm(1, 0)
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -89,7 +89,16 @@ def check(status: int, what: str = "") -> None:
     raise RuntimeError(f"{what}: status {status}: {msg}")
 
 
+# kernels launched per C-ABI call (for the benchmark's gpu_launches claim); sort = 3 kernels x 8 passes
+KERNELS_PER_CALL = {"tsg_table_build": 2, "tsg_coord_table_build": 2, "tsg_kmap_pairs": 2, "tsg_kmap_transpose": 2,
+                    "tsg_sort_pairs": 24, "tsg_unique_coords": 28, "tsg_unique_hash": 28, "tsg_aggregate_quantize": 4,
+                    "tsg_compact_rows": 3}
+launch_count = 0
+
+
 def call(name: str, *args) -> None:
+    global launch_count
+    launch_count += KERNELS_PER_CALL.get(name, 1)
     check(getattr(lib(), name)(*args), name)
 
 

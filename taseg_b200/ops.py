@@ -385,6 +385,9 @@ def cast_pad_bf16(feats: torch.Tensor, c_pad: int) -> torch.Tensor:
     return out
 
 
+PROFILE = None   # set to a list to record (tag, start_event, end_event, pairs, c_in, c_out) per tensor-core launch
+
+
 def conv_forward_tc(in0: torch.Tensor, in1: Optional[torch.Tensor], packed_w: torch.Tensor, k: int, c_out: int,
                     nbr: torch.Tensor, tile_mask: torch.Tensor, n_out: int, bias: Optional[torch.Tensor] = None,
                     residual: Optional[torch.Tensor] = None, relu: bool = False, out_dtype=torch.bfloat16,
@@ -399,8 +402,15 @@ def conv_forward_tc(in0: torch.Tensor, in1: Optional[torch.Tensor], packed_w: to
     if residual is not None:
         assert residual.dtype == torch.bfloat16 and residual.is_contiguous() and residual.shape == (n_out, c_out)
     out = torch.empty((n_out, c_out), dtype=out_dtype, device=in0.device)
+    if PROFILE is not None:
+        pairs = (nbr >= 0).sum() if nbr is not None else torch.tensor(n_out * k, device=in0.device)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     call("tsg_conv_fwd_tc", ptr(in0), c0, ptr(in1), c1, in0.shape[0], ptr(packed_w), k, c_out, ptr(nbr), ptr(tile_mask),
          int(n_out), ptr(out), L.DTYPES[out_dtype], ptr(bias), ptr(residual), int(relu), int(num_sms), stream())
+    if PROFILE is not None:
+        e1.record()
+        PROFILE.append((k, e0, e1, pairs, c0 + c1, c_out, n_out))
     return out
 
 

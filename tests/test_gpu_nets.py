@@ -45,8 +45,12 @@ def tap(model):
 
 
 def bf16_ok(got, want):
+    """bf16 bound: relative l2 error of the logits, and arg-max agreement over the points whose reference decision is
+    not a numerical tie (top-2 margin > 1 % of max|logit|; random-init nets emit many near-ties)."""
     l2 = float(np.linalg.norm(got - want) / np.linalg.norm(want))
-    agree = float((got.argmax(1) == want.argmax(1)).mean())
+    top2 = np.sort(want, axis=1)[:, -2:]
+    decided = (top2[:, 1] - top2[:, 0]) > 0.01 * np.abs(want).max()
+    agree = float((got.argmax(1) == want.argmax(1))[decided].mean()) if decided.any() else 1.0
     return l2, agree
 
 
