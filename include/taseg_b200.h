@@ -107,11 +107,14 @@ int tsg_sort_pairs(const uint64_t *keys_in, const uint32_t *vals_in, int64_t n, 
  *   spdownsample (after truncation)    TS/nn/functional/downsample.py:47-52
  * in_coords (N,4) [x,y,z,b]; if trunc_stride > 0 every x,y,z is first truncated toward zero to a multiple of it
  * (downsample.py:27-29).  Outputs (any may be NULL): out_coords (<=N,4), first_idx (<=N) = first occurrence in
- * input order, inverse (N) = voxel row of every input point; *m_dev = number of unique voxels. */
+ * input order, inverse (N) = voxel row of every input point; *m_dev = number of unique voxels.
+ * field_bits_host: NULL, or HOST int32[4] = bit widths of x,y,z,b when the caller knows 0 <= coordinate < 2^bits
+ * (true after the loader's min-shift): sort keys are then packed densely and the radix sort runs
+ * ceil(sum/8) passes instead of 8; a coordinate outside the promise raises bit 0 of *status. */
 size_t tsg_unique_ws_bytes(int64_t n);
-int tsg_unique_coords(const int32_t *in_coords, int64_t n, int trunc_stride, int32_t *out_coords,
-                      int32_t *first_idx, int32_t *inverse, int32_t *m_dev, int32_t *status, void *ws,
-                      size_t ws_bytes, tsg_stream_t stream);
+int tsg_unique_coords(const int32_t *in_coords, int64_t n, int trunc_stride, const int32_t *field_bits_host,
+                      int32_t *out_coords, int32_t *first_idx, int32_t *inverse, int32_t *m_dev, int32_t *status,
+                      void *ws, size_t ws_bytes, tsg_stream_t stream);
 /* Unique by ascending 60-bit FNV hash — the voxel order of initial_voxelize
  * (R/pcseg/model/segmentor/voxel/minkunet/utils.py:17-18: torch.unique(pc_hash)). */
 int tsg_unique_hash(const int32_t *in_coords, int64_t n, int32_t *out_coords, int32_t *first_idx,
@@ -137,7 +140,9 @@ int tsg_transform_point(const float *pts, int64_t n, int c, const double *R, con
  * apply the optional keep mask (FSA, `keep` (sum n) uint8 or NULL), clamp history to the current scan's min corner,
  * quantise round-half-even(xyz / voxel) in fp32, shift by the per-sample min over kept points.
  * Outputs: feats (sum n, c_in+1), coords (sum n,4) [x,y,z,b], flags (sum n) uint8 = kept.
- * ws: tsg_aggregate_ws_bytes(n_samples). */
+ * ws: tsg_aggregate_ws_bytes(n_samples); on return its first n_samples records of 12 x 4 bytes hold, per sample,
+ * float cur_min[4], int32 ms_min[4], int32 ms_max[4] (quantised extent before the shift; the caller may read it to
+ * derive field_bits for tsg_unique_coords). */
 typedef struct {
   int64_t offset, count;
   int32_t sample, is_cur;

@@ -1,17 +1,21 @@
 // Sparse convolution on the 5th-generation tensor cores (sm_100a): output-stationary implicit GEMM,
 //   out[o,:] = epilogue( sum_k in[nbr[k,o],:] @ W[k] ),   bf16 operands, fp32 accumulation in TMEM.
 //
-// One persistent CTA per SM walks 128-row output tiles.  Warp roles (288 threads):
-//   warps 0-3  epilogue   tcgen05.ld the 128 x c_out fp32 accumulator (one TMEM lane quadrant per warp),
+// One persistent CTA per SM walks "super tiles" of G x 128 output rows (G in {1,2,4}).  Warp roles (288 threads):
+//   warps 0-3  epilogue   tcgen05.ld the G 128 x c_out fp32 accumulators (one TMEM lane quadrant per warp),
 //                         + bias + residual, ReLU, store bf16/fp32 rows
 //   warp  4    MMA        one elected thread issues tcgen05.mma (M=128, N=c_out, K=16) per 16 input channels and
-//                         commits to mbarriers; also owns the TMEM allocation (2 accumulator buffers)
-//   warps 5-8  producers  gather the 128 neighbour rows of (tile, offset k) with 16-byte cp.async (zero-fill for
-//                         missing neighbours) into a 128B-swizzled K-major tile; one thread starts the bulk copy
-//                         (cp.async.bulk -> UBLKCP) of the pre-swizzled W[k] slice, completing on the same mbarrier
-// A "unit" is one (offset k, 64-channel slice): 16 KB of A + c_out*128 B of B per pipeline stage.  Offsets for
-// which no row of the tile has a neighbour are skipped by all roles (tile_mask).  The accumulator is double
-// buffered in TMEM so the epilogue of tile t overlaps the mainloop of tile t+1.
+//                         commits to mbarriers; also owns the TMEM allocation (2 buffers x G accumulators)
+//   warps 5-8  producers  gather the 128 neighbour rows of (sub-tile g, offset k) with 16-byte cp.async (zero-fill
+//                         for missing neighbours) into a 128B-swizzled K-major A slot and hand it to the MMA warp
+//                         with cp.async.mbarrier.arrive (no wait in the producer: the ring depth is the only limit
+//                         on loads in flight); thread 0 also streams the pre-swizzled W[k] slices through a
+//                         separate B ring with cp.async.bulk (UBLKCP).  Neighbour indices of offset k+1 are
+//                         prefetched while offset k is being issued.
+// W[k] (c_out*128 B per 64-channel slice) is loaded ONCE per super tile and reused by its G sub-tiles, which divides
+// the dominant L2->SMEM stream of the narrow layers by G.  Offsets for which a sub-tile has no neighbour at all are
+// skipped by every role (tile_mask).  Accumulators are double buffered in TMEM so the epilogue of super tile t
+// overlaps the mainloop of t+1.
 #include "common.cuh"
 
 namespace tsg {
@@ -19,10 +23,9 @@ namespace tsg {
 constexpr int TC_BM = 128;
 constexpr int TC_KB = 64;                       // channels per unit (128 B of bf16)
 constexpr int TC_A_BYTES = TC_BM * TC_KB * 2;   // 16 KB
-constexpr int TC_MAX_STAGES = 8;
+constexpr int TC_MAX_A = 12, TC_MAX_B = 4;     // ring depths (slots)
 constexpr int TC_EPI_WARPS = 4, TC_PROD_WARPS = 4;
 constexpr int TC_THREADS = 32 * (TC_EPI_WARPS + 1 + TC_PROD_WARPS);
-constexpr int TC_LAG = 2;                       // cp.async groups kept in flight per producer thread
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -60,9 +63,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// arrive on `bar` once every cp.async issued so far by this thread has landed (counts against the expected arrivals)
+__device__ __forceinline__ void cp_async_arrive(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
@@ -102,7 +109,7 @@ struct TcParams {
   const __nv_bfloat16 *in0, *in1;
   int c0, c1, kb0, kb1;
   const uint8_t *packed_w;
-  int K, c_out, stages;
+  int K, c_out, na, nb;
   const int *nbr;
   const unsigned *tile_mask;
   long long n_out;
@@ -114,24 +121,37 @@ struct TcParams {
   uint32_t tmem_cols;
 };
 
+__device__ __forceinline__ int next_bit(unsigned mask, int after) {  // first set bit strictly above `after`, or 32
+  const unsigned m = after >= 31 ? 0u : (mask & (0xffffffffu << (after + 1)));
+  return m ? __ffs(m) - 1 : 32;
+}
+
+template <int G>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[2 * TC_MAX_STAGES + 4];
+  __shared__ __align__(8) uint64_t bars[2 * TC_MAX_A + 2 * TC_MAX_B + 4];
   __shared__ uint32_t tmem_base_slot;
 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KB = p.kb0 + p.kb1;
   const uint32_t b_bytes = (uint32_t)p.c_out * 128u;
-  const uint32_t stage_bytes = TC_A_BYTES + b_bytes;
+  const uint32_t a_base = smem_base + (uint32_t)p.nb * b_bytes;  // B ring first (b_bytes is a multiple of 2048)
   const long long num_tiles = (p.n_out + TC_BM - 1) / TC_BM;
-  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[TC_MAX_STAGES]);
-  const uint32_t tfull0 = smem_u32(&bars[2 * TC_MAX_STAGES]), tempty0 = smem_u32(&bars[2 * TC_MAX_STAGES + 2]);
+  const long long num_super = (num_tiles + G - 1) / G;
+  const unsigned kmask = p.K >= 32 ? 0xffffffffu : ((1u << p.K) - 1u);
+  const uint32_t afull0 = smem_u32(&bars[0]), aempty0 = smem_u32(&bars[TC_MAX_A]);
+  const uint32_t bfull0 = smem_u32(&bars[2 * TC_MAX_A]), bempty0 = smem_u32(&bars[2 * TC_MAX_A + TC_MAX_B]);
+  const uint32_t tfull0 = smem_u32(&bars[2 * TC_MAX_A + 2 * TC_MAX_B]), tempty0 = tfull0 + 16;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < p.stages; ++s) {
-      mbar_init(full0 + 8 * s, TC_PROD_WARPS * 32);
-      mbar_init(empty0 + 8 * s, 1);
+    for (int s = 0; s < p.na; ++s) {
+      mbar_init(afull0 + 8 * s, TC_PROD_WARPS * 32);
+      mbar_init(aempty0 + 8 * s, 1);
+    }
+    for (int s = 0; s < p.nb; ++s) {
+      mbar_init(bfull0 + 8 * s, 1);
+      mbar_init(bempty0 + 8 * s, 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull0 + 8 * b, 1);
@@ -153,57 +173,62 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
   if (warp < TC_EPI_WARPS) {
     // ================================================================= epilogue
     uint32_t it = 0;
-    for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (long long st = blockIdx.x; st < num_super; st += gridDim.x, ++it) {
       const uint32_t buf = it & 1, ph = (it >> 1) & 1;
-      const unsigned mask = p.tile_mask ? p.tile_mask[tile] : 0xffffffffu;
       mbar_wait(tfull0 + 8 * buf, ph);
       tc_fence_after();
-      const long long row = tile * TC_BM + warp * 32 + lane;
-      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + buf * (uint32_t)p.c_out;
-      for (int c = 0; c < p.c_out; c += 16) {
-        uint32_t v[16];
-        if (mask) {
-          tmem_ld16(taddr + c, v);
-        } else {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = 0u;
-        }
-        if (row < p.n_out) {
-          float f[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
-          if (p.bias) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] += __ldg(p.bias + c + j);
-          }
-          if (p.residual) {
-            const uint4 *rp = reinterpret_cast<const uint4 *>(p.residual + row * p.c_out + c);
-            const uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
-            const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              f[2 * j] += __uint_as_float(rw[j] << 16);
-              f[2 * j + 1] += __uint_as_float(rw[j] & 0xffff0000u);
-            }
-          }
-          if (p.relu) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
-          }
-          if (p.out_f32) {
-            float4 *op = reinterpret_cast<float4 *>(reinterpret_cast<float *>(p.out) + row * p.c_out + c);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+      for (int g = 0; g < G; ++g) {
+        const long long tile = st * G + g;
+        if (tile >= num_tiles) break;
+        const unsigned mask = (p.tile_mask ? p.tile_mask[tile] : 0xffffffffu) & kmask;
+        const long long row = tile * TC_BM + warp * 32 + lane;
+        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (buf * G + g) * (uint32_t)p.c_out;
+        for (int c = 0; c < p.c_out; c += 16) {
+          uint32_t v[16];
+          if (mask) {
+            tmem_ld16(taddr + c, v);
           } else {
-            uint32_t w[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-              w[j] = *reinterpret_cast<const uint32_t *>(&h);
+            for (int j = 0; j < 16; ++j) v[j] = 0u;
+          }
+          if (row < p.n_out) {
+            float f[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+            if (p.bias) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) f[j] += __ldg(p.bias + c + j);
             }
-            uint4 *op = reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(p.out) + row * p.c_out + c);
-            op[0] = make_uint4(w[0], w[1], w[2], w[3]);
-            op[1] = make_uint4(w[4], w[5], w[6], w[7]);
+            if (p.residual) {
+              const uint4 *rp = reinterpret_cast<const uint4 *>(p.residual + row * p.c_out + c);
+              const uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+              const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                f[2 * j] += __uint_as_float(rw[j] << 16);
+                f[2 * j + 1] += __uint_as_float(rw[j] & 0xffff0000u);
+              }
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+            }
+            if (p.out_f32) {
+              float4 *op = reinterpret_cast<float4 *>(reinterpret_cast<float *>(p.out) + row * p.c_out + c);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            } else {
+              uint32_t w[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+                w[j] = *reinterpret_cast<const uint32_t *>(&h);
+              }
+              uint4 *op = reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(p.out) + row * p.c_out + c);
+              op[0] = make_uint4(w[0], w[1], w[2], w[3]);
+              op[1] = make_uint4(w[4], w[5], w[6], w[7]);
+            }
           }
         }
       }
@@ -214,30 +239,45 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
     // ================================================================= MMA issuer
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.c_out >> 3) << 17) | ((TC_BM >> 4) << 24);
-      uint32_t it = 0, unit = 0;
-      for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      uint32_t it = 0, a_unit = 0, b_unit = 0;
+      for (long long st = blockIdx.x; st < num_super; st += gridDim.x, ++it) {
         const uint32_t buf = it & 1, ph = (it >> 1) & 1;
-        const unsigned mask = p.tile_mask ? p.tile_mask[tile] : 0xffffffffu;
+        unsigned masks[G], umask = 0;
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const long long tile = st * G + g;
+          masks[g] = tile < num_tiles ? ((p.tile_mask ? p.tile_mask[tile] : 0xffffffffu) & kmask) : 0u;
+          umask |= masks[g];
+        }
         mbar_wait(tempty0 + 8 * buf, ph ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + buf * (uint32_t)p.c_out;
-        uint32_t first = 1;
-        for (int k = 0; k < p.K; ++k) {
-          if (!((mask >> k) & 1u)) continue;
-          for (int j = 0; j < KB; ++j, ++unit) {
-            const uint32_t s = unit % p.stages, sph = (unit / p.stages) & 1;
+        unsigned started = 0;
+        for (int k = next_bit(umask, -1); k < 32; k = next_bit(umask, k)) {
+          for (int j = 0; j < KB; ++j, ++b_unit) {
+            const uint32_t bs = b_unit % p.nb, bph = (b_unit / p.nb) & 1;
             const int kc = j < p.kb0 ? min(TC_KB, p.c0 - j * TC_KB) : min(TC_KB, p.c1 - (j - p.kb0) * TC_KB);
-            mbar_wait(full0 + 8 * s, sph);
-            tc_fence_after();
-            const uint32_t a_addr = smem_base + s * stage_bytes, b_addr = a_addr + TC_A_BYTES;
-            for (int ks = 0; ks < kc; ks += 16) {
-              umma_bf16(d_tmem, umma_desc(a_addr + ks * 2), umma_desc(b_addr + ks * 2), idesc, first ? 0u : 1u);
-              first = 0;
+            mbar_wait(bfull0 + 8 * bs, bph);
+            const uint32_t b_addr = smem_base + bs * b_bytes;
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+              if (!((masks[g] >> k) & 1u)) continue;
+              const uint32_t as = a_unit % p.na, aph = (a_unit / p.na) & 1;
+              ++a_unit;
+              mbar_wait(afull0 + 8 * as, aph);
+              fence_async_proxy();  // cp.async wrote through the generic proxy; the MMA reads through the async proxy
+              tc_fence_after();
+              const uint32_t a_addr = a_base + as * TC_A_BYTES;
+              const uint32_t d_tmem = tmem_base + (buf * G + g) * (uint32_t)p.c_out;
+              for (int ks = 0; ks < kc; ks += 16) {
+                umma_bf16(d_tmem, umma_desc(a_addr + ks * 2), umma_desc(b_addr + ks * 2), idesc, (started >> g) & 1u);
+                started |= 1u << g;
+              }
+              umma_commit(aempty0 + 8 * as);  // frees the A slot once these MMAs have read it
             }
-            umma_commit(empty0 + 8 * s);  // frees the stage once these MMAs have read it
+            umma_commit(bempty0 + 8 * bs);
           }
         }
-        umma_commit(tfull0 + 8 * buf);  // accumulator complete (arrives immediately if the tile had no work)
+        umma_commit(tfull0 + 8 * buf);  // accumulators complete (arrives immediately if the super tile had no work)
       }
     }
     __syncwarp();
@@ -245,53 +285,72 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
     // ================================================================= producers
     const int pt = threadIdx.x - 32 * (TC_EPI_WARPS + 1);  // 0..127
     const int chunk = pt & 7, rsub = pt >> 3;              // 8 lanes cover one 128-byte row; 16 rows per pass
-    uint32_t unit = 0, arrived = 0;                        // units issued / units signalled on their full barrier
-    for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const unsigned mask = p.tile_mask ? p.tile_mask[tile] : 0xffffffffu;
-      const long long m0 = tile * TC_BM;
-      for (int k = 0; k < p.K; ++k) {
-        if (!((mask >> k) & 1u)) continue;
-        int src[8];
+    uint32_t a_unit = 0, b_unit = 0;
+    for (long long st = blockIdx.x; st < num_super; st += gridDim.x) {
+      unsigned masks[G], umask = 0;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const long long o = m0 + rsub + 16 * q;
-          src[q] = o < p.n_out ? (p.nbr ? __ldg(p.nbr + (long long)k * p.n_out + o) : (int)o) : -1;
+      for (int g = 0; g < G; ++g) {
+        const long long tile = st * G + g;
+        masks[g] = tile < num_tiles ? ((p.tile_mask ? p.tile_mask[tile] : 0xffffffffu) & kmask) : 0u;
+        umask |= masks[g];
+      }
+      const long long m0 = st * G * TC_BM;
+      int cur[G][8], nxt[G][8];
+      auto load_idx = [&](int (&dst)[G][8], int k) {
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const bool act = (masks[g] >> k) & 1u;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const long long o = m0 + g * TC_BM + rsub + 16 * q;
+            dst[g][q] = (act && o < p.n_out) ? (p.nbr ? __ldg(p.nbr + (long long)k * p.n_out + o) : (int)o) : -1;
+          }
         }
-        for (int j = 0; j < KB; ++j, ++unit) {
-          const uint32_t s = unit % p.stages, sph = (unit / p.stages) & 1;
-          mbar_wait(empty0 + 8 * s, sph ^ 1);
-          const uint32_t a_addr = smem_base + s * stage_bytes;
+      };
+      int k = next_bit(umask, -1);
+      if (k < 32) load_idx(cur, k);
+      while (k < 32) {
+        const int kn = next_bit(umask, k);
+        if (kn < 32) load_idx(nxt, kn);  // prefetch the next offset's neighbour rows while this one is issued
+        for (int j = 0; j < KB; ++j, ++b_unit) {
           const bool second = j >= p.kb0;
           const __nv_bfloat16 *base = second ? p.in1 : p.in0;
           const int cs = second ? p.c1 : p.c0;
           const int ch0 = (second ? j - p.kb0 : j) * TC_KB;
           if (pt == 0) {
-            mbar_expect_tx(full0 + 8 * s, b_bytes);
-            bulk_g2s(a_addr + TC_A_BYTES, p.packed_w + ((size_t)k * KB + j) * b_bytes, b_bytes, full0 + 8 * s);
+            const uint32_t bs = b_unit % p.nb, bph = (b_unit / p.nb) & 1;
+            mbar_wait(bempty0 + 8 * bs, bph ^ 1);
+            mbar_arrive_expect_tx(bfull0 + 8 * bs, b_bytes);
+            bulk_g2s(smem_base + bs * b_bytes, p.packed_w + ((size_t)k * KB + j) * b_bytes, b_bytes, bfull0 + 8 * bs);
           }
-          if (ch0 + chunk * 8 < cs) {
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const int r = rsub + 16 * q;
-              const uint32_t dst = a_addr + r * 128 + ((chunk ^ (r & 7)) << 4);
-              const bool ok = src[q] >= 0;
-              const __nv_bfloat16 *g = ok ? base + (size_t)src[q] * cs + ch0 + chunk * 8 : base;
-              cp_async16(dst, g, ok ? 16u : 0u);
+          for (int g = 0; g < G; ++g) {
+            if (!((masks[g] >> k) & 1u)) continue;
+            const uint32_t as = a_unit % p.na, aph = (a_unit / p.na) & 1;
+            ++a_unit;
+            mbar_wait(aempty0 + 8 * as, aph ^ 1);
+            const uint32_t a_addr = a_base + as * TC_A_BYTES;
+            if (ch0 + chunk * 8 < cs) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const int r = rsub + 16 * q;
+                const uint32_t dst = a_addr + r * 128 + ((chunk ^ (r & 7)) << 4);
+                const bool ok = cur[g][q] >= 0;
+                const __nv_bfloat16 *gp = ok ? base + (size_t)cur[g][q] * cs + ch0 + chunk * 8 : base;
+                cp_async16(dst, gp, ok ? 16u : 0u);
+              }
             }
-          }
-          cp_async_commit();
-          if (unit >= TC_LAG) {  // the group issued TC_LAG units ago has landed: publish it
-            cp_async_wait<TC_LAG>();
-            fence_async_proxy();
-            mbar_arrive(full0 + 8 * (arrived % p.stages));
-            ++arrived;
+            cp_async_arrive(afull0 + 8 * as);
           }
         }
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+#pragma unroll
+          for (int q = 0; q < 8; ++q) cur[g][q] = nxt[g][q];
+        k = kn;
       }
     }
-    cp_async_wait<0>();
-    fence_async_proxy();
-    for (; arrived < unit; ++arrived) mbar_arrive(full0 + 8 * (arrived % p.stages));
+    asm volatile("cp.async.wait_all;" ::: "memory");
   }
 
   tc_fence_before();
@@ -377,28 +436,37 @@ int tsg_conv_fwd_tc(const void *in0, int c0, const void *in1, int c1, int64_t n_
   p.bias = bias;
   p.residual = (const __nv_bfloat16 *)residual;
   p.relu = relu;
+  const int sms = num_sms_hint > 0 ? num_sms_hint : num_sms();
+  const long long num_tiles = (n_out + TC_BM - 1) / TC_BM;
+  // G sub-tiles share every weight slice; bounded by TMEM (2 buffers x G x c_out fp32 columns <= 512) and by the
+  // number of super tiles needed to keep every SM busy
+  int G = c_out <= 64 ? 4 : (c_out <= 128 ? 2 : 1);
+  while (G > 1 && (num_tiles + G - 1) / G < 2LL * sms) G >>= 1;
   uint32_t cols = 32;
-  while (cols < 2u * (uint32_t)c_out) cols <<= 1;
+  while (cols < 2u * (uint32_t)G * (uint32_t)c_out) cols <<= 1;
   p.tmem_cols = cols;
-  const size_t stage_bytes = TC_A_BYTES + (size_t)c_out * 128;
-  const size_t budget = 200 * 1024;
-  int stages = (int)(budget / stage_bytes);
-  if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
-  if (stages < TC_LAG + 1) {
+  const size_t b_bytes = (size_t)c_out * 128, budget = 200 * 1024;
+  p.nb = b_bytes * 3 + 4 * TC_A_BYTES <= budget ? 3 : 2;
+  int na = (int)((budget - p.nb * b_bytes) / TC_A_BYTES);
+  if (na > TC_MAX_A) na = TC_MAX_A;
+  if (na < 2) {
     set_error("tsg_conv_fwd_tc: not enough shared memory for the pipeline");
     return TSG_ERR_UNSUPPORTED;
   }
-  p.stages = stages;
-  const size_t smem = stages * stage_bytes + 1024;
-  static size_t configured = 0;
-  if (smem > configured) {
-    TSG_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
-    configured = 220 * 1024;
+  p.na = na;
+  const size_t smem = p.nb * b_bytes + (size_t)na * TC_A_BYTES + 1024;
+  static bool configured = false;
+  if (!configured) {
+    TSG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    TSG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    TSG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    configured = true;
   }
-  const long long num_tiles = (n_out + TC_BM - 1) / TC_BM;
-  int sms = num_sms_hint > 0 ? num_sms_hint : num_sms();
-  const unsigned grid = (unsigned)(num_tiles < sms ? num_tiles : sms);
-  conv_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(p);
+  const long long num_super = (num_tiles + G - 1) / G;
+  const unsigned grid = (unsigned)(num_super < sms ? num_super : sms);
+  if (G == 4) conv_tc_kernel<4><<<grid, TC_THREADS, smem, stream>>>(p);
+  else if (G == 2) conv_tc_kernel<2><<<grid, TC_THREADS, smem, stream>>>(p);
+  else conv_tc_kernel<1><<<grid, TC_THREADS, smem, stream>>>(p);
   return check_launch("tsg_conv_fwd_tc");
 }
 

@@ -68,6 +68,7 @@ __device__ inline void atomic_min_float(float *addr, float v) {
 struct AggWs {  // per sample
   float cur_min[4];
   int ms_min[4];
+  int ms_max[4];
 };
 
 __global__ void agg_init_kernel(AggWs *ws, int n_samples) {
@@ -76,6 +77,7 @@ __global__ void agg_init_kernel(AggWs *ws, int n_samples) {
     for (int j = 0; j < 4; ++j) {
       ws[i].cur_min[j] = __int_as_float(0x7f800000);
       ws[i].ms_min[j] = 0x7fffffff;
+      ws[i].ms_max[j] = -0x7fffffff;
     }
   }
 }
@@ -117,6 +119,7 @@ __global__ void agg_quant_kernel(const float *__restrict__ feats, int c_out, con
   const tsg_frame f = frames[blockIdx.y];
   const float cx = ws[f.sample].cur_min[0], cy = ws[f.sample].cur_min[1], cz = ws[f.sample].cur_min[2];
   int mn[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff};
+  int mx[3] = {-0x7fffffff, -0x7fffffff, -0x7fffffff};
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < f.count; t += (int64_t)gridDim.x * blockDim.x) {
     const int64_t i = f.offset + t;
     const float *r = feats + i * c_out;
@@ -130,13 +133,20 @@ __global__ void agg_quant_kernel(const float *__restrict__ feats, int c_out, con
     flags[i] = k ? 1 : 0;
     if (k) {
       mn[0] = min(mn[0], qx); mn[1] = min(mn[1], qy); mn[2] = min(mn[2], qz);
+      mx[0] = max(mx[0], qx); mx[1] = max(mx[1], qy); mx[2] = max(mx[2], qz);
     }
   }
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
-    int v = mn[j];
-    for (int s = 16; s; s >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, s));
-    if ((threadIdx.x & 31) == 0 && v != 0x7fffffff) atomicMin(&ws[f.sample].ms_min[j], v);
+    int v = mn[j], u = mx[j];
+    for (int s = 16; s; s >>= 1) {
+      v = min(v, __shfl_xor_sync(0xffffffffu, v, s));
+      u = max(u, __shfl_xor_sync(0xffffffffu, u, s));
+    }
+    if ((threadIdx.x & 31) == 0 && v != 0x7fffffff) {
+      atomicMin(&ws[f.sample].ms_min[j], v);
+      atomicMax(&ws[f.sample].ms_max[j], u);
+    }
   }
 }
 

@@ -158,7 +158,21 @@ static int sort_pairs(const unsigned long long *keys_in, const unsigned *vals_in
 }
 
 // ---------------------------------------------------------------- unique voxels
-__global__ void make_coord_keys_kernel(const int4 *__restrict__ coords, int64_t n, int trunc_stride,
+// fb = bit widths of (x, y, z, b) when the caller knows every coordinate lies in [0, 2^bits): keys are then packed
+// densely so the sort needs ceil(sum/8) passes instead of 8; fb.x == 0 selects the general 64-bit packing.
+__device__ inline unsigned long long pack_dense(int4 c, int4 fb) {
+  return ((((unsigned long long)(unsigned)c.w << fb.x | (unsigned)c.x) << fb.y | (unsigned)c.y) << fb.z) | (unsigned)c.z;
+}
+__device__ inline int4 unpack_dense(unsigned long long k, int4 fb) {
+  int4 c;
+  c.z = (int)(k & ((1ull << fb.z) - 1)); k >>= fb.z;
+  c.y = (int)(k & ((1ull << fb.y) - 1)); k >>= fb.y;
+  c.x = (int)(k & ((1ull << fb.x) - 1)); k >>= fb.x;
+  c.w = (int)k;
+  return c;
+}
+
+__global__ void make_coord_keys_kernel(const int4 *__restrict__ coords, int64_t n, int trunc_stride, int4 fb,
                                        unsigned long long *__restrict__ keys, int *status) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     int4 c = __ldg(coords + i);
@@ -166,6 +180,14 @@ __global__ void make_coord_keys_kernel(const int4 *__restrict__ coords, int64_t 
       c.x = (c.x / trunc_stride) * trunc_stride;
       c.y = (c.y / trunc_stride) * trunc_stride;
       c.z = (c.z / trunc_stride) * trunc_stride;
+    }
+    if (fb.x > 0) {
+      if ((unsigned)c.x >> fb.x || (unsigned)c.y >> fb.y || (unsigned)c.z >> fb.z || (unsigned)c.w >> fb.w) {
+        if (status) atomicOr(status, 1);
+        c = make_int4(0, 0, 0, 0);
+      }
+      keys[i] = pack_dense(c, fb);
+      continue;
     }
     if (!coord_in_range(c.x, c.y, c.z, c.w)) {
       if (status) atomicOr(status, 1);
@@ -218,7 +240,7 @@ __global__ void __launch_bounds__(1024) uq_scan_kernel(int *data, int64_t n, int
 // hash_mode: coordinates are not recoverable from the key -> copy them from the first member of the run
 __global__ void __launch_bounds__(256) uq_write_kernel(const unsigned long long *__restrict__ skeys,
                                                        const unsigned *__restrict__ sidx, int64_t n,
-                                                       const int *__restrict__ blockoff, int hash_mode,
+                                                       const int *__restrict__ blockoff, int hash_mode, int4 fb,
                                                        const int4 *__restrict__ in_coords, int4 *__restrict__ out_coords,
                                                        int *__restrict__ first_idx, int *__restrict__ inverse) {
   const int64_t base = (int64_t)blockIdx.x * UQ_ROWS + threadIdx.x * 4;
@@ -238,7 +260,8 @@ __global__ void __launch_bounds__(256) uq_write_kernel(const unsigned long long 
     const unsigned src = sidx[j];
     if (head[r]) {
       ++vid;
-      if (out_coords) out_coords[vid] = hash_mode ? __ldg(in_coords + src) : unpack_coord(skeys[j]);
+      if (out_coords)
+        out_coords[vid] = hash_mode ? __ldg(in_coords + src) : (fb.x > 0 ? unpack_dense(skeys[j], fb) : unpack_coord(skeys[j]));
       if (first_idx) first_idx[vid] = (int)src;
     }
     if (inverse) inverse[src] = vid;
@@ -272,7 +295,7 @@ static size_t unique_ws_layout(int64_t n, char *base, UniqueWs *ws) {
   return off;
 }
 
-static int unique_impl(const int32_t *in_coords, int64_t n, int trunc_stride, bool hash_mode, int32_t *out_coords,
+static int unique_impl(const int32_t *in_coords, int64_t n, int trunc_stride, bool hash_mode, int4 fb, int32_t *out_coords,
                        int32_t *first_idx, int32_t *inverse, int32_t *m_dev, int32_t *status, void *ws_mem,
                        size_t ws_bytes, cudaStream_t stream) {
   if (n <= 0) {
@@ -287,14 +310,15 @@ static int unique_impl(const int32_t *in_coords, int64_t n, int trunc_stride, bo
   if (hash_mode)
     make_hash_keys_kernel<<<grid_for(n, 256), 256, 0, stream>>>((const int4 *)in_coords, n, ws.keys);
   else
-    make_coord_keys_kernel<<<grid_for(n, 256), 256, 0, stream>>>((const int4 *)in_coords, n, trunc_stride, ws.keys,
+    make_coord_keys_kernel<<<grid_for(n, 256), 256, 0, stream>>>((const int4 *)in_coords, n, trunc_stride, fb, ws.keys,
                                                                 status);
-  int rc = sort_pairs(ws.keys, nullptr, n, 0, hash_mode ? 60 : 64, ws.skeys, ws.sidx, ws.sort_ws, ws.sort_bytes, stream);
+  const int key_bits = hash_mode ? 60 : (fb.x > 0 ? fb.x + fb.y + fb.z + fb.w : 64);
+  int rc = sort_pairs(ws.keys, nullptr, n, 0, key_bits, ws.skeys, ws.sidx, ws.sort_ws, ws.sort_bytes, stream);
   if (rc) return rc;
   const int64_t nblk = (n + UQ_ROWS - 1) / UQ_ROWS;
   uq_count_kernel<<<(unsigned)nblk, 256, 0, stream>>>(ws.skeys, n, ws.blocksum);
   uq_scan_kernel<<<1, 1024, 0, stream>>>(ws.blocksum, nblk, m_dev);
-  uq_write_kernel<<<(unsigned)nblk, 256, 0, stream>>>(ws.skeys, ws.sidx, n, ws.blocksum, hash_mode ? 1 : 0,
+  uq_write_kernel<<<(unsigned)nblk, 256, 0, stream>>>(ws.skeys, ws.sidx, n, ws.blocksum, hash_mode ? 1 : 0, fb,
                                                       (const int4 *)in_coords, (int4 *)out_coords, first_idx, inverse);
   return check_launch("tsg_unique");
 }
@@ -315,16 +339,25 @@ int tsg_sort_pairs(const uint64_t *keys_in, const uint32_t *vals_in, int64_t n, 
 
 size_t tsg_unique_ws_bytes(int64_t n) { return unique_ws_layout(n > 0 ? n : 1, nullptr, nullptr); }
 
-int tsg_unique_coords(const int32_t *in_coords, int64_t n, int trunc_stride, int32_t *out_coords, int32_t *first_idx,
-                      int32_t *inverse, int32_t *m_dev, int32_t *status, void *ws, size_t ws_bytes,
-                      tsg_stream_t stream) {
-  return unique_impl(in_coords, n, trunc_stride, false, out_coords, first_idx, inverse, m_dev, status, ws, ws_bytes,
-                     stream);
+int tsg_unique_coords(const int32_t *in_coords, int64_t n, int trunc_stride, const int32_t *field_bits_host,
+                      int32_t *out_coords, int32_t *first_idx, int32_t *inverse, int32_t *m_dev, int32_t *status,
+                      void *ws, size_t ws_bytes, tsg_stream_t stream) {
+  int4 fb = make_int4(0, 0, 0, 0);
+  if (field_bits_host) {
+    fb = make_int4(field_bits_host[0], field_bits_host[1], field_bits_host[2], field_bits_host[3]);
+    if (fb.x <= 0 || fb.y <= 0 || fb.z <= 0 || fb.w <= 0 || fb.x > 19 || fb.y > 19 || fb.z > 19 || fb.w > 7) {
+      set_error("tsg_unique_coords: field bits must be in 1..19 (x,y,z) and 1..7 (b)");
+      return TSG_ERR_INVALID;
+    }
+  }
+  return unique_impl(in_coords, n, trunc_stride, false, fb, out_coords, first_idx, inverse, m_dev, status, ws,
+                     ws_bytes, stream);
 }
 
 int tsg_unique_hash(const int32_t *in_coords, int64_t n, int32_t *out_coords, int32_t *first_idx, int32_t *inverse,
                     int32_t *m_dev, void *ws, size_t ws_bytes, tsg_stream_t stream) {
-  return unique_impl(in_coords, n, 0, true, out_coords, first_idx, inverse, m_dev, nullptr, ws, ws_bytes, stream);
+  return unique_impl(in_coords, n, 0, true, make_int4(0, 0, 0, 0), out_coords, first_idx, inverse, m_dev, nullptr, ws,
+                     ws_bytes, stream);
 }
 
 }  // extern "C"

@@ -86,7 +86,7 @@ class Level:
 class Geometry:
     """Voxel pyramid of one batch: coordinates, tables and kernel maps at tensor strides 1..16."""
 
-    def __init__(self, coords: torch.Tensor, n_levels: int = 5):
+    def __init__(self, coords: torch.Tensor, n_levels: int = 5, field_bits=None):
         self.levels: List[Level] = []
         c = coords.contiguous()
         for l in range(n_levels):
@@ -96,7 +96,7 @@ class Geometry:
             lv.km3 = ops.build_kmap(lv.table, lv.n, c, kernel_offsets_np(3, lv.stride))
             lv.km2 = None
             if l + 1 < n_levels:
-                nxt = ops.unique_coords(c, trunc_stride=2 * lv.stride)
+                nxt = ops.unique_coords(c, trunc_stride=2 * lv.stride, field_bits=field_bits)
                 lv.km2 = ops.build_kmap(lv.table, lv.n, nxt, kernel_offsets_np(2, lv.stride))
                 c = nxt
             self.levels.append(lv)
@@ -151,8 +151,9 @@ class Engine:
 
     # ------------------------------------------------------------------------------------------------
     @torch.no_grad()
-    def __call__(self, coords: torch.Tensor, feats: torch.Tensor, return_geometry: bool = False):
-        """coords (N,4) int32 [x,y,z,b], feats (N,>=in_dim) fp32 -> logits (N, num_class) fp32, one row per input row."""
+    def __call__(self, coords: torch.Tensor, feats: torch.Tensor, return_geometry: bool = False, field_bits=None):
+        """coords (N,4) int32 [x,y,z,b], feats (N,>=in_dim) fp32 -> logits (N, num_class) fp32, one row per input row.
+        field_bits: optional (bx,by,bz,bb) promise 0 <= coordinate < 2^bits (shorter radix sorts in the pyramid)."""
         feats = feats[:, :self.in_dim].float().contiguous()
         zc = coords.float().contiguous()
         if self.voxelize_input:      # initial_voxelize (minkunet/utils.py:11-36)
@@ -163,7 +164,7 @@ class Engine:
             vox = vox.contiguous()
         else:
             vox, x_f = coords.contiguous(), feats
-        geo = Geometry(vox)
+        geo = Geometry(vox, field_bits=field_bits if not self.voxelize_input else None)
         L = geo.levels
         x = ops.cast_pad_bf16(x_f, self.stem[0].c0)
         for conv in self.stem:

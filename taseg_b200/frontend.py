@@ -44,13 +44,17 @@ def aggregate_voxelize(points: torch.Tensor, batch: MultiFrameBatch, voxel_size:
     coords (M,4) int32 [x,y,z,b] / feats (M,5) [x,y,z,i,t] of the de-duplicated voxels (lidar_ms),
     inverse (N') voxel row of every kept point, cur_rows (sum n_cur) voxel row of every current-scan point,
     point_ms (N',5), pc_ms (N',4), inds (M)."""
-    feats, coords, flags = ops.aggregate_quantize(points, batch.frames, batch.n_samples, voxel_size, keep)
-    point_ms, pc_ms, pos, _ = ops.compact_rows(flags, feats, coords, want_pos=True)
-    vox, first, inverse = ops.unique_coords(pc_ms, want_index=True, want_inverse=True)
+    feats, coords, flags, extent = ops.aggregate_quantize(points, batch.frames, batch.n_samples, voxel_size, keep)
+    point_ms, pc_ms, pos, m_dev = ops.compact_rows(flags, feats, coords, want_pos=True, sync=False)
+    span = (extent[:, 8:11] - extent[:, 4:7]).amax(dim=0)                  # quantised extent per axis over the batch
+    m, sx, sy, sz = torch.cat([m_dev, span]).tolist()                      # the one host sync of the front end
+    point_ms, pc_ms = point_ms[:m], pc_ms[:m]
+    bits = [max(1, int(v).bit_length()) for v in (sx, sy, sz, batch.n_samples - 1)]
+    vox, first, inverse = ops.unique_coords(pc_ms, want_index=True, want_inverse=True, field_bits=bits)
     vfeat = ops.gather_rows(point_ms, first)
     cur_rows = inverse[pos[cur_idx].long()]
     return dict(coords=vox, feats=vfeat, inverse=inverse, cur_rows=cur_rows, point_ms=point_ms, pc_ms=pc_ms, inds=first,
-                pos=pos)
+                pos=pos, field_bits=bits)
 
 
 def as_lidar_ms(out: dict) -> SparseTensor:

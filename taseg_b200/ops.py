@@ -170,8 +170,9 @@ def kmap_from_pairs(nbmaps: torch.Tensor, nbsizes: torch.Tensor, k: int, transpo
 
 # ------------------------------------------------------------------------------- unique voxels
 def unique_coords(coords: torch.Tensor, trunc_stride: int = 0, want_index: bool = False, want_inverse: bool = False,
-                  by_hash: bool = False):
-    """Unique voxel rows ordered by (b,x,y,z) (or by ascending FNV hash); returns (coords[, first_idx][, inverse])."""
+                  by_hash: bool = False, field_bits: Optional[Sequence[int]] = None):
+    """Unique voxel rows ordered by (b,x,y,z) (or by ascending FNV hash); returns (coords[, first_idx][, inverse]).
+    field_bits = (bx,by,bz,bb): promise that 0 <= coordinate < 2^bits, which shortens the radix sort."""
     L.require_cuda(coords)
     coords = _i32(coords).contiguous()
     n = coords.shape[0]
@@ -187,11 +188,13 @@ def unique_coords(coords: torch.Tensor, trunc_stride: int = 0, want_index: bool 
         m = int(m_dev.item())  # sync
     else:
         status = _status(dev)
-        call("tsg_unique_coords", ptr(coords), n, int(trunc_stride), ptr(out_c), ptr(first), ptr(inv), ptr(m_dev),
+        fb = (ctypes.c_int32 * 4)(*[int(b) for b in field_bits]) if field_bits is not None else None
+        call("tsg_unique_coords", ptr(coords), n, int(trunc_stride), fb, ptr(out_c), ptr(first), ptr(inv), ptr(m_dev),
              ptr(status), ptr(ws), ws_bytes, stream())
         m, st = torch.cat([m_dev, status]).tolist()  # sync
         if st & 1:
-            raise RuntimeError("unique_coords: coordinate outside the packable range (|x|,|y|,|z| < 2^18, 0 <= b < 128)")
+            raise RuntimeError("unique_coords: coordinate outside the packable range (|x|,|y|,|z| < 2^18, 0 <= b < 128) "
+                               "or outside the promised field_bits")
     res = [out_c[:m]]
     if want_index:
         res.append(first[:m])
@@ -298,8 +301,9 @@ def gather_rows(src: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
 
 
 def compact_rows(flags: torch.Tensor, rows_a: Optional[torch.Tensor], rows_b: Optional[torch.Tensor] = None,
-                 want_pos: bool = False):
-    """Stable compaction by a uint8 flag; returns (out_a, out_b, pos, m)."""
+                 want_pos: bool = False, sync: bool = True):
+    """Stable compaction by a uint8 flag; returns (out_a, out_b, pos, m).  With sync=False the outputs keep their
+    upper-bound length and m is the device counter (the caller slices after its own readback)."""
     n = flags.numel()
     dev = flags.device
     wa = rows_a.shape[1] if rows_a is not None else 0
@@ -312,6 +316,8 @@ def compact_rows(flags: torch.Tensor, rows_a: Optional[torch.Tensor], rows_b: Op
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     call("tsg_compact_rows", ptr(flags), n, ptr(rows_a), wa, ptr(out_a), ptr(rows_b), wb, ptr(out_b), ptr(pos), ptr(m_dev),
          ptr(ws), ws_bytes, stream())
+    if not sync:
+        return out_a, out_b, pos, m_dev
     m = int(m_dev.item())  # sync
     return (out_a[:m] if out_a is not None else None, out_b[:m] if out_b is not None else None, pos, m)
 
@@ -438,7 +444,8 @@ def transform_point(points: torch.Tensor, R, T) -> torch.Tensor:
 def aggregate_quantize(points: torch.Tensor, frames: Sequence[dict], n_samples: int, voxel_size: float,
                        keep: Optional[torch.Tensor] = None):
     """points (sum n, c_in) fp32, frames: dicts(offset,count,sample,is_cur,pose0,pose).
-    Returns feats (sum n, c_in+1), coords (sum n, 4) int32, flags (sum n) uint8."""
+    Returns feats (sum n, c_in+1), coords (sum n, 4) int32, flags (sum n) uint8, extent (n_samples, 12) int32 view of
+    the per-sample records [cur_min(4 f32 bits), ms_min(4), ms_max(4)]."""
     L.require_cuda(points, keep)
     pts = points.float().contiguous()
     n, c_in = pts.shape
@@ -458,4 +465,5 @@ def aggregate_quantize(points: torch.Tensor, frames: Sequence[dict], n_samples: 
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=pts.device)
     call("tsg_aggregate_quantize", ptr(pts), c_in, arr, len(frames), n_samples, ptr(keep), float(voxel_size), ptr(feats),
          ptr(coords), ptr(flags), ptr(ws), ws_bytes, stream())
-    return feats, coords, flags
+    extent = ws[:n_samples * 48].view(torch.int32).view(n_samples, 12)
+    return feats, coords, flags, extent

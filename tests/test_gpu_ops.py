@@ -95,6 +95,14 @@ def test_unique_and_quantize(ts, golden):
     assert np.array_equal(npy(uc), c[fi]) and np.array_equal(npy(first), fi) and np.array_equal(npy(inv), iv)
     with pytest.raises(RuntimeError):
         ops.unique_coords(cu(np.array([[1 << 20, 0, 0, 0]], np.int32)))
+    # dense sort keys (caller-promised coordinate widths): same result, fewer radix passes; a broken promise raises
+    pos = np.abs(c).astype(np.int32)
+    bits = [int(pos[:, j].max()).bit_length() for j in range(4)]
+    a = ops.unique_coords(cu(pos), trunc_stride=4, want_index=True, want_inverse=True, field_bits=bits)
+    b = ops.unique_coords(cu(pos), trunc_stride=4, want_index=True, want_inverse=True)
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
+    with pytest.raises(RuntimeError):
+        ops.unique_coords(cu(pos), field_bits=[bits[0] - 1, bits[1], bits[2], bits[3]])
     assert ops.unique_coords(cu(np.zeros((0, 4), np.int32))).shape == (0, 4)
 
 
@@ -231,7 +239,7 @@ def test_fuse_and_aggregate(ts, golden):
             descr.append(dict(offset=off, count=len(frames[j]), sample=b, is_cur=int(j == 0), pose0=poses[0], pose=poses[j]))
             frames_all.append(frames[j])
             off += len(frames[j])
-    feats, coords, flags = ops.aggregate_quantize(cu(np.concatenate(frames_all)), descr, 2, 0.05)
+    feats, coords, flags, extent = ops.aggregate_quantize(cu(np.concatenate(frames_all)), descr, 2, 0.05)
     f2, c2, _, m = ops.compact_rows(flags, feats, coords)
     wf, wc = np.concatenate(want_feats), np.concatenate(want_coords)
     assert m == len(wf)
