@@ -16,115 +16,9 @@
 // the dominant L2->SMEM stream of the narrow layers by G.  Offsets for which a sub-tile has no neighbour at all are
 // skipped by every role (tile_mask).  Accumulators are double buffered in TMEM so the epilogue of super tile t
 // overlaps the mainloop of t+1.
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace tsg {
-
-constexpr int TC_BM = 128;
-constexpr int TC_KB = 64;                       // channels per unit (128 B of bf16)
-constexpr int TC_A_BYTES = TC_BM * TC_KB * 2;   // 16 KB
-constexpr int TC_MAX_A = 12, TC_MAX_B = 4;     // ring depths (slots)
-constexpr int TC_EPI_WARPS = 4, TC_PROD_WARPS = 4;
-constexpr int TC_THREADS = 32 * (TC_EPI_WARPS + 1 + TC_PROD_WARPS);
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ uint64_t global_ns() {
-  uint64_t t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0;
-  uint64_t t0 = 0;
-  while (true) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (done) break;
-    const uint64_t now = global_ns();
-    if (!t0) t0 = now;
-    else if (now - t0 > 4000000000ull) __trap();  // 4 s: a protocol bug must fail loudly, never hang the GPU
-  }
-}
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-// arrive on `bar` once every cp.async issued so far by this thread has landed (counts against the expected arrivals)
-__device__ __forceinline__ void cp_async_arrive(uint32_t bar) {
-  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): rows of 128 B, 8-row groups
-// 1024 B apart (SBO), version 1, layout type 2.  `addr` may be advanced by 32 B per K=16 step inside the row.
-__device__ __forceinline__ uint64_t umma_desc(uint32_t addr) {
-  return (uint64_t)((addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
-}
-
-struct TcParams {
-  const __nv_bfloat16 *in0, *in1;
-  int c0, c1, kb0, kb1;
-  const uint8_t *packed_w;
-  int K, c_out, na, nb;
-  const int *nbr;
-  const unsigned *tile_mask;
-  long long n_out;
-  void *out;
-  int out_f32;
-  const float *bias;
-  const __nv_bfloat16 *residual;
-  int relu;
-  uint32_t tmem_cols;
-};
-
-__device__ __forceinline__ int next_bit(unsigned mask, int after) {  // first set bit strictly above `after`, or 32
-  const unsigned m = after >= 31 ? 0u : (mask & (0xffffffffu << (after + 1)));
-  return m ? __ffs(m) - 1 : 32;
-}
 
 template <int G>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p) {
@@ -408,7 +302,11 @@ int tsg_conv_pack_weights(const float *weight, int k, int c_in, int c_out, int c
   return check_launch("tsg_conv_pack_weights");
 }
 
-int tsg_conv_fwd_tc(const void *in0, int c0, const void *in1, int c1, int64_t n_in, const void *packed_w, int k,
+}  // extern "C"
+
+namespace tsg {
+// cp.async producer variant (kept as the fallback when a TMA tensor map cannot be encoded, and for A/B timing)
+int conv_fwd_tc_cpasync(const void *in0, int c0, const void *in1, int c1, int64_t n_in, const void *packed_w, int k,
                     int c_out, const int32_t *nbr, const uint32_t *tile_mask, int64_t n_out, void *out, int out_dtype,
                     const float *bias, const void *residual, int relu, int num_sms_hint, tsg_stream_t stream) {
   (void)n_in;
@@ -467,7 +365,6 @@ int tsg_conv_fwd_tc(const void *in0, int c0, const void *in1, int c1, int64_t n_
   if (G == 4) conv_tc_kernel<4><<<grid, TC_THREADS, smem, stream>>>(p);
   else if (G == 2) conv_tc_kernel<2><<<grid, TC_THREADS, smem, stream>>>(p);
   else conv_tc_kernel<1><<<grid, TC_THREADS, smem, stream>>>(p);
-  return check_launch("tsg_conv_fwd_tc");
+  return check_launch("tsg_conv_fwd_tc(cp.async)");
 }
-
-}  // extern "C"
+}  // namespace tsg

@@ -1,0 +1,180 @@
+// Inline-PTX helpers shared by the tensor-core convolution kernels (mbarrier, cp.async, bulk/TMA copies, tcgen05).
+#pragma once
+#include "common.cuh"
+
+namespace tsg {
+
+constexpr int TC_BM = 128;
+constexpr int TC_KB = 64;                       // channels per unit (128 B of bf16)
+constexpr int TC_A_BYTES = TC_BM * TC_KB * 2;   // 16 KB
+constexpr int TC_MAX_A = 12, TC_MAX_B = 4;     // ring depths (slots)
+constexpr int TC_EPI_WARPS = 4, TC_PROD_WARPS = 4;
+constexpr int TC_THREADS = 32 * (TC_EPI_WARPS + 1 + TC_PROD_WARPS);
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Spin on an mbarrier phase.  try_wait suspends the thread in hardware for a bounded time, so the loop is not hot;
+// the watchdog reads the cheap SM cycle counter (never %globaltimer, whose read costs ~1 us) once per 4096 failed
+// polls and traps after ~2^33 cycles (~4 s): a protocol bug must fail loudly, never hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  long long t0 = 0;
+  for (uint32_t spin = 1;; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if ((spin & 0xfffu) == 0) {
+      const long long now = clock64();
+      if (!t0) t0 = now;
+      else if (now - t0 > (1ll << 33)) __trap();
+    }
+  }
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+// arrive on `bar` once every cp.async issued so far by this thread has landed (counts against the expected arrivals)
+__device__ __forceinline__ void cp_async_arrive(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): rows of 128 B, 8-row groups
+// 1024 B apart (SBO), version 1, layout type 2.  `addr` may be advanced by 32 B per K=16 step inside the row.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t addr) {
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+struct TcParams {
+  const __nv_bfloat16 *in0, *in1;
+  int c0, c1, kb0, kb1;
+  const uint8_t *packed_w;
+  int K, c_out, na, nb;
+  const int *nbr;
+  const unsigned *tile_mask;
+  long long n_out;
+  void *out;
+  int out_f32;
+  const float *bias;
+  const __nv_bfloat16 *residual;
+  int relu;
+  uint32_t tmem_cols;
+};
+
+__device__ __forceinline__ int next_bit(unsigned mask, int after) {  // first set bit strictly above `after`, or 32
+  const unsigned m = after >= 31 ? 0u : (mask & (0xffffffffu << (after + 1)));
+  return m ? __ffs(m) - 1 : 32;
+}
+
+// Long waits (an epilogue warp waiting for a whole mainloop): back off between polls so the idle warp does not
+// compete for issue slots with the producer / MMA warps that share its scheduler.
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  long long t0 = 0;
+  for (uint32_t spin = 1;; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    __nanosleep(200);
+    if ((spin & 0x3ffu) == 0) {
+      const long long now = clock64();
+      if (!t0) t0 = now;
+      else if (now - t0 > (1ll << 33)) __trap();
+    }
+  }
+}
+
+// Epilogue for 16 consecutive output channels of one row: + bias, + residual (bf16), ReLU, store bf16 or fp32.
+__device__ __forceinline__ void epilogue_store16(const TcParams &p, long long row, int c, const uint32_t (&v)[16]) {
+  float f[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+  if (p.bias) {
+    const float4 *bp = reinterpret_cast<const float4 *>(p.bias + c);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 b = __ldg(bp + j);
+      f[4 * j] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
+    }
+  }
+  if (p.residual) {
+    const uint4 *rp = reinterpret_cast<const uint4 *>(p.residual + row * p.c_out + c);
+    const uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+    const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      f[2 * j] += __uint_as_float(rw[j] << 16);
+      f[2 * j + 1] += __uint_as_float(rw[j] & 0xffff0000u);
+    }
+  }
+  if (p.relu) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+  }
+  if (p.out_f32) {
+    float4 *op = reinterpret_cast<float4 *>(reinterpret_cast<float *>(p.out) + row * p.c_out + c);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+  } else {
+    uint32_t w[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+      w[j] = *reinterpret_cast<const uint32_t *>(&h);
+    }
+    uint4 *op = reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(p.out) + row * p.c_out + c);
+    op[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    op[1] = make_uint4(w[4], w[5], w[6], w[7]);
+  }
+}
+
+}  // namespace tsg
