@@ -219,15 +219,24 @@ int tsg_conv_wgrad(const float *in, int64_t n_in, int c_in, const float *grad_ou
  * c0, c1, c_out multiples of 16; c_out <= 256.  tile_mask (ceil(n_out/128)) uint32 from tsg_kmap_tile_mask.
  * nbr == NULL means the identity map (row o reads row o for every k: 1x1x1 convolutions and point MLPs) and
  * tile_mask == NULL means every offset is active.
+ * perm == NULL: tile row r is output row r.  Otherwise nbr / tile_mask describe tile rows in the order produced by
+ * tsg_kmap_sort_rows and row r is written to out[perm[r]] (residual read from residual[perm[r]]): rows with the same
+ * neighbour pattern share a tile, so most (tile, offset) pairs are empty and skipped.
  * out dtype TSG_BF16 or TSG_F32. */
 size_t tsg_conv_pack_bytes(int k, int c0, int c1, int c_out);
 int tsg_conv_pack_weights(const float *weight, int k, int c_in, int c_out, int c0, int c1,
                           const float *out_scale, void *packed, tsg_stream_t stream);
 int tsg_kmap_tile_mask(const int32_t *nbr, int k, int64_t n_out, uint32_t *tile_mask, tsg_stream_t stream);
 int tsg_conv_fwd_tc(const void *in0, int c0, const void *in1, int c1, int64_t n_in, const void *packed_w, int k,
-                    int c_out, const int32_t *nbr, const uint32_t *tile_mask, int64_t n_out, void *out,
-                    int out_dtype, const float *bias, const void *residual, int relu, int num_sms,
+                    int c_out, const int32_t *nbr, const uint32_t *tile_mask, const int32_t *perm, int64_t n_out,
+                    void *out, int out_dtype, const float *bias, const void *residual, int relu, int num_sms,
                     tsg_stream_t stream);
+/* Tile-row order for tsg_conv_fwd_tc: stable sort of the n_out output rows by their K-bit neighbour mask
+ * (bit k set iff nbr[k, o] >= 0).  Outputs: perm (n_out) int32 = output row of tile row r, nbr_sorted (K, n_out) with
+ * nbr_sorted[k, r] = nbr[k, perm[r]], tile_mask (ceil(n_out/128)) of the sorted table.  ws: tsg_kmap_sort_ws_bytes. */
+size_t tsg_kmap_sort_ws_bytes(int64_t n_out);
+int tsg_kmap_sort_rows(const int32_t *nbr, int k, int64_t n_out, int32_t *perm, int32_t *nbr_sorted,
+                       uint32_t *tile_mask, void *ws, size_t ws_bytes, tsg_stream_t stream);
 
 /* fp32 -> bf16 with zero padding of the channel dimension to c_pad (first-layer input, 4/5 -> 16 channels). */
 int tsg_cast_pad_bf16(const float *in, int64_t n, int c, int c_pad, void *out, tsg_stream_t stream);

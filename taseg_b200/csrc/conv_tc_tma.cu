@@ -1,4 +1,6 @@
-// Sparse convolution on tcgen05 with a TMA-gather producer (sm_100a) — the default tensor-core path.
+// Sparse convolution on tcgen05 with a TMA-gather producer (sm_100a) — opt-in variant (TSG_TC_IMPL=tma).
+// Measured on B200 (profiles/conv_layers_r01_*.txt): 2x SLOWER than the cp.async producer of conv_tc.cu — the TMA
+// unit serialises the 128-byte rows of a gather4 (~18 cycles per row), so the default path gathers with LDGSTS.
 //
 // Same output-stationary implicit GEMM as conv_tc.cu (G sub-tiles of 128 rows share every weight slice, fp32
 // accumulators double buffered in TMEM, fused bias/residual/ReLU epilogue), but the A operand is staged by the TMA
@@ -16,11 +18,6 @@
 #include "tc_common.cuh"
 
 namespace tsg {
-
-int conv_fwd_tc_cpasync(const void *in0, int c0, const void *in1, int c1, int64_t n_in, const void *packed_w, int k,
-                        int c_out, const int32_t *nbr, const uint32_t *tile_mask, int64_t n_out, void *out,
-                        int out_dtype, const float *bias, const void *residual, int relu, int num_sms_hint,
-                        tsg_stream_t stream);
 
 constexpr int T3_THREADS = 7 * 32;
 constexpr int T3_NI = 8;  // index ring slots (offsets)
@@ -45,16 +42,6 @@ __device__ __forceinline__ int4 lds128(uint32_t addr) {
   asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
   return v;
 }
-
-struct Ring {  // slot + phase of a circular mbarrier pipeline
-  uint32_t slot = 0, phase = 0;
-  __device__ __forceinline__ void advance(uint32_t n) {
-    if (++slot == n) {
-      slot = 0;
-      phase ^= 1;
-    }
-  }
-};
 
 template <int G>
 __global__ void __launch_bounds__(T3_THREADS, 1) conv_tma_kernel(const __grid_constant__ CUtensorMap tmap0,
@@ -306,28 +293,14 @@ static bool make_feature_map(CUtensorMap *m, const void *base, int c, int64_t n)
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-}  // namespace tsg
-
-using namespace tsg;
-
-extern "C" {
-
-int tsg_conv_fwd_tc(const void *in0, int c0, const void *in1, int c1, int64_t n_in, const void *packed_w, int k,
+// Returns a tsg_status, or -1 when no tensor map could be encoded (the caller then uses the cp.async producer).
+int conv_fwd_tc_tma(const void *in0, int c0, const void *in1, int c1, int64_t n_in, const void *packed_w, int k,
                     int c_out, const int32_t *nbr, const uint32_t *tile_mask, int64_t n_out, void *out, int out_dtype,
                     const float *bias, const void *residual, int relu, int num_sms_hint, tsg_stream_t stream) {
-  if (c0 % 16 || c1 % 16 || c_out % 16 || c_out > 256 || c_out <= 0 || c0 <= 0 || k <= 0 || k > 32 ||
-      (out_dtype != TSG_BF16 && out_dtype != TSG_F32)) {
-    set_error("tsg_conv_fwd_tc: need c0,c1,c_out multiples of 16, c_out<=256, K<=32, out bf16/f32");
-    return TSG_ERR_UNSUPPORTED;
-  }
-  if (n_out <= 0) return TSG_OK;
-  static const char *impl = getenv("TSG_TC_IMPL");
   CUtensorMap tm0, tm1;
-  bool tma = !(impl && strcmp(impl, "cpasync") == 0) && n_in > 0 && make_feature_map(&tm0, in0, c0, n_in);
+  bool tma = n_in > 0 && make_feature_map(&tm0, in0, c0, n_in);
   if (tma && c1 > 0) tma = make_feature_map(&tm1, in1, c1, n_in);
-  if (!tma)
-    return conv_fwd_tc_cpasync(in0, c0, in1, c1, n_in, packed_w, k, c_out, nbr, tile_mask, n_out, out, out_dtype, bias,
-                               residual, relu, num_sms_hint, stream);
+  if (!tma) return -1;
   if (c1 == 0) tm1 = tm0;
 
   TcParams p;
@@ -342,6 +315,7 @@ int tsg_conv_fwd_tc(const void *in0, int c0, const void *in1, int c1, int64_t n_
   p.c_out = c_out;
   p.nbr = nbr;
   p.tile_mask = tile_mask;
+  p.perm = nullptr;
   p.n_out = n_out;
   p.out = out;
   p.out_f32 = out_dtype == TSG_F32;
@@ -381,7 +355,7 @@ int tsg_conv_fwd_tc(const void *in0, int c0, const void *in1, int c1, int64_t n_
   if (G == 4) conv_tma_kernel<4><<<grid, T3_THREADS, smem, stream>>>(tm0, tm1, p);
   else if (G == 2) conv_tma_kernel<2><<<grid, T3_THREADS, smem, stream>>>(tm0, tm1, p);
   else conv_tma_kernel<1><<<grid, T3_THREADS, smem, stream>>>(tm0, tm1, p);
-  return check_launch("tsg_conv_fwd_tc");
+  return check_launch("tsg_conv_fwd_tc(tma)");
 }
 
-}  // extern "C"
+}  // namespace tsg

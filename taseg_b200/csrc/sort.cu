@@ -157,6 +157,26 @@ static int sort_pairs(const unsigned long long *keys_in, const unsigned *vals_in
   return check_launch("tsg_sort_pairs");
 }
 
+
+// ---------------------------------------------------------------- mask-sorted tile rows for the tensor-core convolution
+// key[o] = K-bit mask "offset k has a neighbour" of output row o (coalesced k-major reads of nbr)
+__global__ void row_mask_keys_kernel(const int *__restrict__ nbr, int K, int64_t n_out,
+                                     unsigned long long *__restrict__ keys) {
+  for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < n_out; o += (int64_t)gridDim.x * blockDim.x) {
+    unsigned long long m = 0;
+    for (int k = 0; k < K; ++k) m |= (unsigned long long)(__ldg(nbr + (int64_t)k * n_out + o) >= 0) << k;
+    keys[o] = m;
+  }
+}
+// nbr_sorted[k, r] = nbr[k, perm[r]]
+__global__ void permute_nbr_kernel(const int *__restrict__ nbr, const int *__restrict__ perm, int K, int64_t n_out,
+                                   int *__restrict__ nbr_sorted) {
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n_out; r += (int64_t)gridDim.x * blockDim.x) {
+    const int o = __ldg(perm + r);
+    for (int k = 0; k < K; ++k) nbr_sorted[(int64_t)k * n_out + r] = __ldg(nbr + (int64_t)k * n_out + o);
+  }
+}
+
 // ---------------------------------------------------------------- unique voxels
 // fb = bit widths of (x, y, z, b) when the caller knows every coordinate lies in [0, 2^bits): keys are then packed
 // densely so the sort needs ceil(sum/8) passes instead of 8; fb.x == 0 selects the general 64-bit packing.
@@ -335,6 +355,34 @@ int tsg_sort_pairs(const uint64_t *keys_in, const uint32_t *vals_in, int64_t n, 
                    uint64_t *keys_out, uint32_t *vals_out, void *ws, size_t ws_bytes, tsg_stream_t stream) {
   return sort_pairs((const unsigned long long *)keys_in, vals_in, n, begin_bit, end_bit, (unsigned long long *)keys_out,
                     vals_out, ws, ws_bytes, stream);
+}
+
+size_t tsg_kmap_sort_ws_bytes(int64_t n_out) {
+  const int64_t n = n_out > 0 ? n_out : 1;
+  return 2 * align256((size_t)n * 8) + sort_ws_layout(n, nullptr, nullptr);
+}
+
+int tsg_kmap_sort_rows(const int32_t *nbr, int k, int64_t n_out, int32_t *perm, int32_t *nbr_sorted,
+                       uint32_t *tile_mask, void *ws, size_t ws_bytes, tsg_stream_t stream) {
+  if (k <= 0 || k > 32) {
+    set_error("tsg_kmap_sort_rows: need 1 <= K <= 32");
+    return TSG_ERR_INVALID;
+  }
+  if (n_out <= 0) return TSG_OK;
+  if (ws_bytes < tsg_kmap_sort_ws_bytes(n_out)) {
+    set_error("tsg_kmap_sort_rows: workspace too small");
+    return TSG_ERR_WORKSPACE;
+  }
+  char *base = (char *)ws;
+  unsigned long long *keys = (unsigned long long *)base;
+  unsigned long long *keys_sorted = (unsigned long long *)(base + align256((size_t)n_out * 8));
+  char *sort_ws = base + 2 * align256((size_t)n_out * 8);
+  row_mask_keys_kernel<<<grid_for(n_out, 256), 256, 0, stream>>>(nbr, k, n_out, keys);
+  const int rc = sort_pairs(keys, nullptr, n_out, 0, k, keys_sorted, (unsigned *)perm, sort_ws,
+                            ws_bytes - 2 * align256((size_t)n_out * 8), stream);
+  if (rc != TSG_OK) return rc;
+  permute_nbr_kernel<<<grid_for(n_out, 256), 256, 0, stream>>>(nbr, perm, k, n_out, nbr_sorted);
+  return tsg_kmap_tile_mask(nbr_sorted, k, n_out, tile_mask, stream);
 }
 
 size_t tsg_unique_ws_bytes(int64_t n) { return unique_ws_layout(n > 0 ? n : 1, nullptr, nullptr); }

@@ -96,6 +96,7 @@ struct TcParams {
   int K, c_out, na, nb;
   const int *nbr;
   const unsigned *tile_mask;
+  const int *perm;  // tile row r -> output row (NULL = identity); nbr / tile_mask are indexed by tile row
   long long n_out;
   void *out;
   int out_f32;
@@ -103,6 +104,16 @@ struct TcParams {
   const __nv_bfloat16 *residual;
   int relu;
   uint32_t tmem_cols;
+};
+
+struct Ring {  // slot + phase of a circular mbarrier pipeline
+  uint32_t slot = 0, phase = 0;
+  __device__ __forceinline__ void advance(uint32_t n) {
+    if (++slot == n) {
+      slot = 0;
+      phase ^= 1;
+    }
+  }
 };
 
 __device__ __forceinline__ int next_bit(unsigned mask, int after) {  // first set bit strictly above `after`, or 32

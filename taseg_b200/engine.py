@@ -13,6 +13,7 @@ module path to bf16 round-off (tests state the bound); kernel maps / voxel sets 
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional
 
 import torch
@@ -31,6 +32,16 @@ def _fold(bn: Optional[nn.Module], c_out: int, device):
         return torch.ones(c_out, device=device), torch.zeros(c_out, device=device)
     scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
     return scale, bn.bias.detach().float() - bn.running_mean.detach().float() * scale
+
+
+SORT_ROWS = os.environ.get("TSG_SORT_ROWS", "1") != "0"   # mask-sorted tile rows (A/B switch for profiling)
+
+
+def conv_map(km, transposed: bool = False):
+    """(nbr, tile_mask, perm) the tensor-core convolution consumes for kernel map `km`."""
+    if SORT_ROWS:
+        return km.sorted(transposed)
+    return (km.nbr_t if transposed else km.nbr, km.tile_mask(transposed), None)
 
 
 class FusedConv:
@@ -55,9 +66,11 @@ class FusedConv:
         self.bias = torch.zeros(self.c_out_pad, device=w.device)
         self.bias[:c_out] = shift
 
-    def __call__(self, x0, x1, nbr, tile_mask, n_out, residual=None, out_dtype=torch.bfloat16):
+    def __call__(self, x0, x1, m, n_out, residual=None, out_dtype=torch.bfloat16):
+        """m = (nbr, tile_mask, perm) from conv_map(), or None for the identity map (1x1x1 convolutions, point MLPs)."""
+        nbr, tile_mask, perm = m if m is not None else (None, None, None)
         return ops.conv_forward_tc(x0, x1, self.packed, self.k, self.c_out_pad, nbr, tile_mask, n_out, bias=self.bias,
-                                   residual=residual, relu=self.relu, out_dtype=out_dtype)
+                                   residual=residual, relu=self.relu, out_dtype=out_dtype, perm=perm)
 
 
 class FusedBlock:
@@ -73,10 +86,10 @@ class FusedBlock:
             self.shortcut = FusedConv(block.downsample[0].kernel, block.downsample[1], r0, r1, relu=False)
 
     def __call__(self, x0, x1, km):
-        n = km.n_out
-        h = self.a(x0, x1, km.nbr, km.tile_mask(), n)
-        res = self.shortcut(x0, x1, None, None, n) if self.shortcut is not None else x0
-        return self.b(h, None, km.nbr, km.tile_mask(), n, residual=res)
+        n, m = km.n_out, conv_map(km)
+        h = self.a(x0, x1, m, n)
+        res = self.shortcut(x0, x1, None, n) if self.shortcut is not None else x0
+        return self.b(h, None, m, n, residual=res)
 
 
 class Level:
@@ -168,7 +181,7 @@ class Engine:
         L = geo.levels
         x = ops.cast_pad_bf16(x_f, self.stem[0].c0)
         for conv in self.stem:
-            x = conv(x, None, L[0].km3.nbr, L[0].km3.tile_mask(), L[0].n)
+            x = conv(x, None, conv_map(L[0].km3), L[0].n)
         x0 = x
         q1 = ops.trilinear_query(L[0].table, zc, 1)
         q16 = ops.trilinear_query(L[4].table, zc, 16)
@@ -180,39 +193,39 @@ class Engine:
         skips = [x0]
         for i in range(4):
             km2 = L[i].km2
-            x = self.down[i](x, None, km2.nbr, km2.tile_mask(), km2.n_out)
+            x = self.down[i](x, None, conv_map(km2), km2.n_out)
             for blk in self.enc[i]:
                 x = blk(x, None, L[i + 1].km3)
             skips.append(x)
         x4 = x
         if self.spv:
-            z1 = ops.devoxelize_forward(x4, *q16) + self.mlps[0](z0, None, None, None, z0.shape[0])
+            z1 = ops.devoxelize_forward(x4, *q16) + self.mlps[0](z0, None, None, z0.shape[0])
             i16 = ops.point_query(L[4].table, zc, 16)
             x = ops.voxelize_forward(z1, i16, ops.spcount(i16, L[4].n))
         ys = []
         for i in range(4):
             lv = L[3 - i]
             km2 = lv.km2
-            x = self.up[i](x, None, km2.nbr_t, km2.tile_mask(True), lv.n)
+            x = self.up[i](x, None, conv_map(km2, True), lv.n)
             skip = skips[3 - i]
             for j, blk in enumerate(self.dec[i]):
                 x = blk(x, skip if j == 0 else None, lv.km3)
             ys.append(x)
             if self.spv and i == 1:
-                z2 = ops.devoxelize_forward(x, *q4) + self.mlps[1](z1, None, None, None, z1.shape[0])
+                z2 = ops.devoxelize_forward(x, *q4) + self.mlps[1](z1, None, None, z1.shape[0])
                 i4 = ops.point_query(L[2].table, zc, 4)
                 x = ops.voxelize_forward(z2, i4, ops.spcount(i4, L[2].n))
         y2, y4 = ys[1], ys[3]
         if self.spv:
-            z3 = ops.devoxelize_forward(y4, *q1) + self.mlps[2](z2, None, None, None, z2.shape[0])
+            z3 = ops.devoxelize_forward(y4, *q1) + self.mlps[2](z2, None, None, z2.shape[0])
             cat = torch.cat([z1[:, :self.head_dims[0]], z2[:, :self.head_dims[1]], z3[:, :self.head_dims[2]]], dim=1)
             if cat.shape[1] % 16:
                 cat = torch.nn.functional.pad(cat, (0, pad16(cat.shape[1]) - cat.shape[1]))
-            logits = self.head(cat.contiguous(), None, None, None, cat.shape[0], out_dtype=torch.float32)
+            logits = self.head(cat.contiguous(), None, None, cat.shape[0], out_dtype=torch.float32)
         else:
-            l16 = self.heads[0](x4, None, None, None, L[4].n, out_dtype=torch.float32)
-            l4 = self.heads[1](y2, None, None, None, L[2].n, out_dtype=torch.float32)
-            l1 = self.heads[2](y4, None, None, None, L[0].n, out_dtype=torch.float32)
+            l16 = self.heads[0](x4, None, None, L[4].n, out_dtype=torch.float32)
+            l4 = self.heads[1](y2, None, None, L[2].n, out_dtype=torch.float32)
+            l1 = self.heads[2](y4, None, None, L[0].n, out_dtype=torch.float32)
             logits = ops.devoxelize_forward(l16, *q16) + ops.devoxelize_forward(l4, *q4) + ops.devoxelize_forward(l1, *q1)
         logits = logits[:, :self.num_class]
         return (logits, geo) if return_geometry else logits

@@ -97,6 +97,8 @@ class KernelMap:
         self._nbr_t = None
         self._tile_mask = None
         self._tile_mask_t = None
+        self._sorted = None
+        self._sorted_t = None
 
     @property
     def sizes(self) -> Tuple[int, int]:
@@ -132,6 +134,23 @@ class KernelMap:
             out = torch.empty(((rows + 127) // 128,), dtype=torch.int32, device=nbr.device)
             call("tsg_kmap_tile_mask", ptr(nbr), self.k, rows, ptr(out), stream())
             setattr(self, attr, out)
+        return getattr(self, attr)
+
+    def sorted(self, transposed: bool = False):
+        """(nbr_sorted, tile_mask, perm): tile rows ordered by neighbour bit mask (tsg_kmap_sort_rows), so that the
+        tensor-core convolution skips the (tile, offset) pairs that are empty; perm[r] = output row of tile row r."""
+        attr = "_sorted_t" if transposed else "_sorted"
+        if getattr(self, attr) is None:
+            nbr = self.nbr_t if transposed else self.nbr
+            rows = self.n_in if transposed else self.n_out
+            dev = nbr.device
+            perm = torch.empty((rows,), dtype=torch.int32, device=dev)
+            nbr_s = torch.empty_like(nbr)
+            mask = torch.empty(((rows + 127) // 128,), dtype=torch.int32, device=dev)
+            ws_bytes = int(L.lib().tsg_kmap_sort_ws_bytes(rows))
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            call("tsg_kmap_sort_rows", ptr(nbr), self.k, rows, ptr(perm), ptr(nbr_s), ptr(mask), ptr(ws), ws_bytes, stream())
+            setattr(self, attr, (nbr_s, mask, perm))
         return getattr(self, attr)
 
     def __getitem__(self, i):
@@ -397,8 +416,9 @@ PROFILE = None   # set to a list to record (tag, start_event, end_event, pairs, 
 def conv_forward_tc(in0: torch.Tensor, in1: Optional[torch.Tensor], packed_w: torch.Tensor, k: int, c_out: int,
                     nbr: torch.Tensor, tile_mask: torch.Tensor, n_out: int, bias: Optional[torch.Tensor] = None,
                     residual: Optional[torch.Tensor] = None, relu: bool = False, out_dtype=torch.bfloat16,
-                    num_sms: int = 0) -> torch.Tensor:
-    """tcgen05/TMEM implicit GEMM; in0/in1 bf16 (n_in, c) with c % 16 == 0."""
+                    num_sms: int = 0, perm: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """tcgen05/TMEM implicit GEMM; in0/in1 bf16 (n_in, c) with c % 16 == 0.  With `perm`, nbr/tile_mask are in the
+    mask-sorted tile-row order of KernelMap.sorted() and tile row r is written to out[perm[r]]."""
     assert in0.dtype == torch.bfloat16 and in0.is_contiguous()
     c0 = in0.shape[1]
     c1 = 0
@@ -413,7 +433,7 @@ def conv_forward_tc(in0: torch.Tensor, in1: Optional[torch.Tensor], packed_w: to
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
     call("tsg_conv_fwd_tc", ptr(in0), c0, ptr(in1), c1, in0.shape[0], ptr(packed_w), k, c_out, ptr(nbr), ptr(tile_mask),
-         int(n_out), ptr(out), L.DTYPES[out_dtype], ptr(bias), ptr(residual), int(relu), int(num_sms), stream())
+         ptr(perm), int(n_out), ptr(out), L.DTYPES[out_dtype], ptr(bias), ptr(residual), int(relu), int(num_sms), stream())
     if PROFILE is not None:
         e1.record()
         PROFILE.append((k, e0, e1, pairs, c0 + c1, c_out, n_out))

@@ -264,6 +264,18 @@ def _tc_case(seed, n, c0, c1, c_out, ks, relu, residual, out_dtype, dense_span):
     packed = ops.pack_weights(w, c0, c1)
     got = ops.conv_forward_tc(x0, x1, packed, k, c_out, km.nbr, km.tile_mask(), n, bias=bias, residual=res, relu=relu,
                               out_dtype=out_dtype)
+    # mask-sorted tile rows: a permutation of the same table, and bit-identical output rows (same MMAs per row)
+    nbr_s, mask_s, perm = km.sorted()
+    assert np.array_equal(np.sort(npy(perm)), np.arange(n)), "perm is not a permutation"
+    assert torch.equal(nbr_s, km.nbr[:, perm.long()])
+    keys = ((km.nbr >= 0).long() << torch.arange(k, device="cuda").view(-1, 1)).sum(0)
+    ks_sorted = keys[perm.long()]
+    assert bool((ks_sorted[1:] >= ks_sorted[:-1]).all()), "tile rows are not ordered by neighbour mask"
+    same = ks_sorted[1:] == ks_sorted[:-1]
+    assert bool((perm[1:][same] > perm[:-1][same]).all()), "sort is not stable"
+    got_s = ops.conv_forward_tc(x0, x1, packed, k, c_out, nbr_s, mask_s, n, bias=bias, residual=res, relu=relu,
+                                out_dtype=out_dtype, perm=perm)
+    assert torch.equal(got, got_s), "mask-sorted convolution differs from the unsorted one"
     xin = torch.cat([x0, x1], 1).float() if c1 else x0.float()
     want = ops.conv_forward(xin, w.bfloat16().float(), km.nbr, n, bias=bias, residual=res.float() if residual else None, relu=relu)
     torch.cuda.synchronize()

@@ -23,23 +23,32 @@ def main():
     torch.manual_seed(0)
     cases = [(0, 96, 96), (1, 32, 32), (0, 32, 32), (2, 64, 64), (4, 256, 256), (3, 128, 128)]
     reps = int(os.environ.get("REPS", "1"))
+    if os.environ.get("CASES"):
+        cases = [cases[int(i)] for i in os.environ["CASES"].split(",")]
     for level, cin, cout in cases:
         lv = geo.levels[level]
         x = torch.randn(lv.n, cin, device="cuda").bfloat16()
         w = torch.randn(27, cin, cout, device="cuda") * 0.05
         packed = ops.pack_weights(w, cin)
-        mask = lv.km3.tile_mask()
         pairs = int((lv.km3.nbr >= 0).sum())
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(reps):
-            y = ops.conv_forward_tc(x, None, packed, 27, cout, lv.km3.nbr, mask, lv.n)
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / reps
-        print("level %d (stride %2d) n=%7d pairs=%8d  %3d->%3d : %8.1f us  %6.1f TFLOP/s algorithmic" %
-              (level, lv.stride, lv.n, pairs, cin, cout, ms * 1e3, 2.0 * pairs * cin * cout / ms / 1e9))
+        tiles = (lv.n + 127) // 128
+        for name, (nbr, mask, perm) in (("lex   ", (lv.km3.nbr, lv.km3.tile_mask(), None)), ("sorted", lv.km3.sorted())):
+            if os.environ.get("ONLY") and os.environ["ONLY"] != name.strip():
+                continue
+            active = int(sum(bin(v & 0xffffffff).count("1") for v in mask.tolist()))
+            ops.conv_forward_tc(x, None, packed, 27, cout, nbr, mask, lv.n, perm=perm)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                y = ops.conv_forward_tc(x, None, packed, 27, cout, nbr, mask, lv.n, perm=perm)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / reps
+            dense = 2.0 * active * 128 * cin * cout
+            print("level %d (stride %2d) n=%7d pairs=%8d %s active (tile,offset) %.2f  %3d->%3d : %8.1f us  %6.1f TFLOP/s "
+                  "algorithmic, %6.1f TFLOP/s issued" % (level, lv.stride, lv.n, pairs, name, active / (27.0 * tiles), cin,
+                                                         cout, ms * 1e3, 2.0 * pairs * cin * cout / ms / 1e9, dense / ms / 1e9))
 
 
 if __name__ == "__main__":
