@@ -213,7 +213,8 @@ int tsg_conv_wgrad(const float *in, int64_t n_in, int c_in, const float *grad_ou
 
 /* tcgen05/TMEM path (bf16 operands, fp32 accumulate in tensor memory).
  * Weights are packed once per layer into the shared-memory image the MMA consumes (128B-swizzled K-major
- * [c_out][64] blocks per kernel offset and 64-channel slice): tsg_conv_pack_bytes / tsg_conv_pack_weights.
+ * [c_out][64] blocks per kernel offset and 64-channel slice; single-source layers with c0 of 16 or 32 put 64/c0
+ * kernel offsets side by side in one block): tsg_conv_pack_bytes / tsg_conv_pack_weights.
  * The A operand may come from two feature tensors (channel concat of a decoder feature and its encoder skip,
  * TS/operators.py:10-17, without materialising the concat): in0 (n_in, c0) then in1 (n_in, c1); c1 may be 0.
  * c0, c1, c_out multiples of 16; c_out <= 256.  tile_mask (ceil(n_out/128)) uint32 from tsg_kmap_tile_mask.
@@ -222,6 +223,8 @@ int tsg_conv_wgrad(const float *in, int64_t n_in, int c_in, const float *grad_ou
  * perm == NULL: tile row r is output row r.  Otherwise nbr / tile_mask describe tile rows in the order produced by
  * tsg_kmap_sort_rows and row r is written to out[perm[r]] (residual read from residual[perm[r]]): rows with the same
  * neighbour pattern share a tile, so most (tile, offset) pairs are empty and skipped.
+ * sched: NULL (tiles are dealt to the CTAs round-robin) or two int32 that are ZERO on entry: the kernel hands tiles out
+ * dynamically through them, heaviest first, and leaves them zero again; launches that may overlap need their own pair.
  * out dtype TSG_BF16 or TSG_F32. */
 size_t tsg_conv_pack_bytes(int k, int c0, int c1, int c_out);
 int tsg_conv_pack_weights(const float *weight, int k, int c_in, int c_out, int c0, int c1,
@@ -230,7 +233,7 @@ int tsg_kmap_tile_mask(const int32_t *nbr, int k, int64_t n_out, uint32_t *tile_
 int tsg_conv_fwd_tc(const void *in0, int c0, const void *in1, int c1, int64_t n_in, const void *packed_w, int k,
                     int c_out, const int32_t *nbr, const uint32_t *tile_mask, const int32_t *perm, int64_t n_out,
                     void *out, int out_dtype, const float *bias, const void *residual, int relu, int num_sms,
-                    tsg_stream_t stream);
+                    int32_t *sched, tsg_stream_t stream);
 /* Tile-row order for tsg_conv_fwd_tc: stable sort of the n_out output rows by their K-bit neighbour mask
  * (bit k set iff nbr[k, o] >= 0).  Outputs: perm (n_out) int32 = output row of tile row r, nbr_sorted (K, n_out) with
  * nbr_sorted[k, r] = nbr[k, perm[r]], tile_mask (ceil(n_out/128)) of the sorted table.  ws: tsg_kmap_sort_ws_bytes. */

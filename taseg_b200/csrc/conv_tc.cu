@@ -1,23 +1,33 @@
 // Sparse convolution on the 5th-generation tensor cores (sm_100a): output-stationary implicit GEMM,
 //   out[row(r),:] = epilogue( sum_k in[nbr[k,r],:] @ W[k] ),   bf16 operands, fp32 accumulation in TMEM.
 //
-// One persistent CTA per SM walks "super tiles" of G x 128 tile rows (G in {1,2,4}).  The unit of the shared-memory
-// pipeline is a STAGE = one (kernel offset k, 64-channel slice j): the pre-swizzled weight slice W[k][j] (c_out x 128 B)
-// plus the G gathered 128 x 64 A tiles that multiply it, behind ONE full / ONE empty mbarrier — so the weight slice is
-// loaded once per super tile and the per-stage fixed costs (barrier waits, proxy fence, commit) are paid once per
-// 4G MMAs.  Warp roles (448 threads):
+// One persistent CTA per SM walks "super tiles" of G x 128 tile rows (G in {1,2}), handed out by an in-kernel dynamic
+// scheduler (heaviest tiles first).  The unit of the shared-memory pipeline is a STAGE = one 64-channel K slice: the
+// pre-swizzled weight slice (c_out x 128 B) plus the G gathered 128 x 64 A tiles that multiply it, behind ONE full /
+// ONE empty mbarrier.  For c_in > 32 a slice is (kernel offset k, 64-channel block j); for c_in <= 32 a slice packs
+// PK = 64 / c_in kernel offsets side by side ("virtual offset" kv = k / PK), so narrow layers still issue K=64 MMAs and
+// every producer lane moves useful bytes.  Warp roles (768 threads):
 //   warps 0-3   epilogue   tcgen05.ld the G 128 x c_out fp32 accumulators (one TMEM lane quadrant per warp),
 //                          + bias + residual, ReLU, store bf16/fp32 rows (to row perm[r] when tiles are mask-sorted)
-//   warp  4     MMA        converged warp; one elected lane issues tcgen05.mma (M=128, N=c_out, K=16) per 16 input
-//                          channels and commits the stage; owns the TMEM allocation (2 buffers x G accumulators)
-//   warp  5     weights    one thread streams W[k][j] into the stage with cp.async.bulk (UBLKCP, complete_tx)
-//   warps 6-13  producers  gather the neighbour rows with 16-byte cp.async (LDGSTS, zero-fill for missing neighbours)
-//                          into the 128B-swizzled K-major A tiles and arrive on the stage's full barrier with
-//                          cp.async.mbarrier.arrive.noinc (no wait in the producer: the ring depth is the only limit on
-//                          loads in flight).  Neighbour indices of offset k+1 are prefetched while k is being issued.
-// History (profiles/ncu_conv_r01.md): v1 paid ~200 producer instructions per 16 KB slot (runtime modulo, per-row
-// address arithmetic) and was bound by producer issue; v3 made the producers lean and became bound by the single MMA
-// thread's own instruction latency (two try_waits, MEMBAR + proxy fence, descriptor rebuilds and ELECT loops per slot).
+//   warps 4-5   MMA        one issuing thread per sub-tile: tcgen05.mma (M=128, N=c_out, K=16) per 16 input channels,
+//                          tcgen05.commit on the stage's empty barrier; warp 4 owns the TMEM allocation
+//   warp  6     weights    one thread streams the weight slice into the stage with cp.async.bulk (UBLKCP, complete_tx)
+//   warp  7     scheduler  one thread takes super-tile tickets from a global counter and publishes them in a 4-deep
+//                          shared-memory ring read by every other warp (the last CTA to finish re-zeroes the counter)
+//   warps 8-23  producers  4 independent groups of 4 warps; group g fills every 4th stage: it gathers the neighbour rows
+//                          with 16-byte cp.async (LDGSTS, zero-fill for missing neighbours) into the 128B-swizzled K-major
+//                          A tiles, prefetches the indices of its next stage while the rows land, then cp.async.wait_all,
+//                          fence.proxy.async and ONE mbarrier arrival per warp.
+// History (profiles/README.md): v1 paid ~200 producer instructions per 16 KB slot and was bound by producer issue; v3
+// became bound by the single MMA thread's instruction latency; v4 (8 producer warps, 64-bit address arithmetic, static
+// tile striding) was bound by the producers' own dependent instruction chains (~125 SASS instructions per stage per
+// warp, stall_wait) and by a 2x imbalance between SMs.  v5: 16 producer warps with one IMAD.WIDE per copy, slice
+// packing, dynamic scheduling.  Knock-out runs of v5 (TSG_TC_DEBUG=15: no gathers, weights, MMAs or stores) still took
+// the full kernel time: the per-THREAD cp.async.mbarrier.arrive.noinc (513 arrivals per stage on one barrier word) was
+// the bottleneck suspect; arriving once per warp did not help either, and clock64 traces of the hand-offs (TSG_TC_DEBUG
+// bit 128) showed ~600 cycles between consecutive stages of an EMPTY pipeline: with all 16 producer warps taking part in
+// every stage the per-stage bookkeeping (x16 warps) saturates instruction issue and every hand-off is on the critical
+// path.  v6: producer groups own whole stages (hand-shake amortised over 8 G copies per thread, groups overlap).
 // Offsets for which a sub-tile has no neighbour at all are skipped by every role (tile_mask); with rows sorted by
 // their neighbour bit mask (tsg_kmap_sort_rows) that removes more than half of the (tile, offset) work.
 // Accumulators are double buffered in TMEM so the epilogue of super tile t overlaps the mainloop of t+1.
@@ -28,13 +38,18 @@
 
 namespace tsg {
 
-constexpr int V4_MMA_WARP = TC_EPI_WARPS;        // 4
-constexpr int V4_W_WARP = TC_EPI_WARPS + 1;      // 5
-constexpr int V4_PROD_WARP0 = TC_EPI_WARPS + 2;  // 6
-constexpr int V4_PROD_WARPS = 8;
-constexpr int V4_PROD_THREADS = 32 * V4_PROD_WARPS;
-constexpr int V4_THREADS = 32 * (V4_PROD_WARP0 + V4_PROD_WARPS);  // 448
-constexpr int V4_MAX_STAGES = 8;
+constexpr int V5_MMA_WARP = TC_EPI_WARPS;        // 4, 5 (one per sub-tile)
+constexpr int V5_W_WARP = TC_EPI_WARPS + 2;      // 6
+constexpr int V5_SCHED_WARP = TC_EPI_WARPS + 3;  // 7
+constexpr int V5_PROD_WARP0 = TC_EPI_WARPS + 4;  // 8
+constexpr int V5_GROUPS = 4;                                      // producer groups; each owns every NG-th stage
+constexpr int V5_GROUP_WARPS = 4;
+constexpr int V5_PROD_WARPS = V5_GROUPS * V5_GROUP_WARPS;         // 16
+constexpr int V5_THREADS = 32 * (V5_PROD_WARP0 + V5_PROD_WARPS);  // 768
+constexpr int V5_Q = TC_BM / (V5_GROUP_WARPS * 4);                // 8 passes of 16 rows per tile (8 lanes cover one row)
+constexpr int V5_MAX_STAGES = 8;
+constexpr int V5_SCHED_SLOTS = 3;
+constexpr int V5_CONSUMER_WARPS = V5_PROD_WARPS + TC_EPI_WARPS + 3;  // producers + epilogue + 2 MMA + weights
 
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
@@ -47,10 +62,35 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t lo, uint32_t hi) {
   return d;
 }
 
+// tile mask over real offsets -> mask over virtual offsets (PK real offsets per virtual one)
+__device__ __forceinline__ unsigned virt_mask(unsigned m, int pk, int kv_count) {
+  if (pk == 1) return m;
+  const unsigned sub = (1u << pk) - 1u;
+  unsigned vm = 0;
+  for (int kv = 0; kv < kv_count; ++kv) vm |= ((m >> (kv * pk)) & sub) ? (1u << kv) : 0u;
+  return vm;
+}
+
+// Profiling aid (TSG_TC_DEBUG bit 128): CTA 0 records clock64() at the pipeline hand-offs of its first TRACE_N stages.
+constexpr int TRACE_N = 96;
+__device__ long long g_trace[8][TRACE_N];  // 0 producer group 0 got empty, 1 it arrived on full, 2 MMA got full, 3 MMA committed,
+                                           // 4 weights got empty, 5 MMA starts waiting for full
+#ifdef TSG_TC_TRACE  // profiling build (TSG_TC_TRACE=1 python -m taseg_b200.build): knock-outs and traces cost nothing otherwise
+#define TSG_DBG(bit) (p.dbg & (bit))
+#define TSG_TRACE(role, idx)                                                              \
+  do {                                                                                    \
+    if ((p.dbg & 128) && blockIdx.x == 0 && (idx) < TRACE_N) g_trace[role][idx] = clock64(); \
+  } while (0)
+#else
+#define TSG_DBG(bit) 0
+#define TSG_TRACE(role, idx) do { } while (0)
+#endif
+
 template <int G>
-__global__ void __launch_bounds__(V4_THREADS, 1) conv_tc_kernel(const TcParams p) {
+__global__ void __launch_bounds__(V5_THREADS, 1) conv_tc_kernel(const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[2 * V4_MAX_STAGES + 4];
+  __shared__ __align__(8) uint64_t bars[2 * V5_MAX_STAGES + 4 + 2 * V5_SCHED_SLOTS];
+  __shared__ int sched_tile[V5_SCHED_SLOTS];
   __shared__ uint32_t tmem_base_slot;
 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -59,24 +99,30 @@ __global__ void __launch_bounds__(V4_THREADS, 1) conv_tc_kernel(const TcParams p
   const uint32_t b_bytes = (uint32_t)p.c_out * 128u;                 // multiple of 2048
   const uint32_t stage_bytes = b_bytes + (uint32_t)G * TC_A_BYTES;   // [W slice][A tile 0]..[A tile G-1]
   const uint32_t nst = (uint32_t)p.na;                               // stages
-  const long long num_tiles = (p.n_out + TC_BM - 1) / TC_BM;
-  const long long num_super = (num_tiles + G - 1) / G;
+  const int num_tiles = (int)((p.n_out + TC_BM - 1) / TC_BM);
+  const int num_super = (num_tiles + G - 1) / G;
   const unsigned kmask = p.K >= 32 ? 0xffffffffu : ((1u << p.K) - 1u);
-  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[V4_MAX_STAGES]);
-  const uint32_t tfull0 = smem_u32(&bars[2 * V4_MAX_STAGES]), tempty0 = tfull0 + 16;
+  const int KV = (p.K + p.pk - 1) / p.pk;                            // virtual offsets
+  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[V5_MAX_STAGES]);
+  const uint32_t tfull0 = smem_u32(&bars[2 * V5_MAX_STAGES]), tempty0 = tfull0 + 16;
+  const uint32_t sfull0 = tfull0 + 32, sempty0 = sfull0 + 8 * V5_SCHED_SLOTS;
 
   if (threadIdx.x == 0) {
     for (uint32_t s = 0; s < nst; ++s) {
-      mbar_init(full0 + 8 * s, V4_PROD_THREADS + 1);  // every producer thread (noinc arrive) + the weight thread
-      mbar_init(empty0 + 8 * s, 1);
+      mbar_init(full0 + 8 * s, V5_GROUP_WARPS + 1);  // one arrival per warp of the owning producer group + the weight thread
+      mbar_init(empty0 + 8 * s, G);  // one tcgen05.commit per MMA warp
     }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(tfull0 + 8 * b, 1);
+      mbar_init(tfull0 + 8 * b, G);
       mbar_init(tempty0 + 8 * b, TC_EPI_WARPS * 32);
+    }
+    for (int s = 0; s < V5_SCHED_SLOTS; ++s) {
+      mbar_init(sfull0 + 8 * s, 1);
+      mbar_init(sempty0 + 8 * s, V5_CONSUMER_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == V4_MMA_WARP) {  // TMEM allocation by the MMA warp
+  if (warp == V5_MMA_WARP) {  // TMEM allocation by the MMA warp
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
                  "r"(p.tmem_cols)
                  : "memory");
@@ -87,28 +133,54 @@ __global__ void __launch_bounds__(V4_THREADS, 1) conv_tc_kernel(const TcParams p
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
 
-  auto tile_masks = [&](long long st, unsigned (&masks)[G]) -> unsigned {
+  // next super tile from the scheduler ring (every consumer warp calls this once per super tile, converged)
+  Ring sr;
+  auto next_super = [&]() -> int {
+    mbar_wait(sfull0 + 8 * sr.slot, sr.phase);
+    const int st = *reinterpret_cast<volatile int *>(&sched_tile[sr.slot]);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(sempty0 + 8 * sr.slot);
+    sr.advance(V5_SCHED_SLOTS);
+    return st;
+  };
+  auto next_super_lane = [&]() -> int {  // same, for roles that run in one lane
+    mbar_wait(sfull0 + 8 * sr.slot, sr.phase);
+    const int st = *reinterpret_cast<volatile int *>(&sched_tile[sr.slot]);
+    mbar_arrive(sempty0 + 8 * sr.slot);
+    sr.advance(V5_SCHED_SLOTS);
+    return st;
+  };
+  // real-offset masks of the G tiles of a super tile; returns the union over tiles of their VIRTUAL masks
+  auto tile_masks = [&](int st, unsigned (&masks)[G]) -> unsigned {
     unsigned um = 0;
 #pragma unroll
     for (int g = 0; g < G; ++g) {
-      const long long tile = st * G + g;
+      const int tile = st * G + g;
       masks[g] = tile < num_tiles ? ((p.tile_mask ? __ldg(p.tile_mask + tile) : 0xffffffffu) & kmask) : 0u;
       um |= masks[g];
     }
-    return um;
+    return virt_mask(um, p.pk, KV);
+  };
+  // which of the G tiles take part in virtual offset kv
+  auto active_tiles = [&](const unsigned (&masks)[G], int kv) -> unsigned {
+    const unsigned sub = p.pk >= 32 ? 0xffffffffu : ((1u << p.pk) - 1u);
+    unsigned act = 0;
+#pragma unroll
+    for (int g = 0; g < G; ++g) act |= (((masks[g] >> (kv * p.pk)) & sub) ? 1u : 0u) << g;
+    return act;
   };
 
   if (warp < TC_EPI_WARPS) {
     // ================================================================= epilogue
     uint32_t it = 0;
-    for (long long st = blockIdx.x; st < num_super; st += gridDim.x, ++it) {
+    for (int st = next_super(); st >= 0; st = next_super(), ++it) {
       const uint32_t buf = it & 1, ph = (it >> 1) & 1;
       unsigned masks[G];
       long long rows[G];
       tile_masks(st, masks);
 #pragma unroll
       for (int g = 0; g < G; ++g) {  // destination rows are fetched before the (long) wait for the accumulators
-        const long long r = (st * G + g) * TC_BM + warp * 32 + lane;
+        const long long r = (long long)(st * G + g) * TC_BM + warp * 32 + lane;
         rows[g] = r < p.n_out ? (p.perm ? (long long)__ldg(p.perm + r) : r) : -1;
       }
       mbar_wait_sleep(tfull0 + 8 * buf, ph);
@@ -117,7 +189,21 @@ __global__ void __launch_bounds__(V4_THREADS, 1) conv_tc_kernel(const TcParams p
       for (int g = 0; g < G; ++g) {
         if (st * G + g >= num_tiles) break;
         const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (buf * G + g) * (uint32_t)p.c_out;
-        for (int c = 0; c < p.c_out; c += 16) {
+        int c = 0;
+        for (; c + 32 <= p.c_out; c += 32) {
+          uint32_t v[32];
+          if (masks[g]) {
+            tmem_ld32(taddr + c, v);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0u;
+          }
+          if (rows[g] >= 0 && !TSG_DBG(8)) {
+            epilogue_store16(p, rows[g], c, *reinterpret_cast<const uint32_t(*)[16]>(&v[0]));
+            epilogue_store16(p, rows[g], c + 16, *reinterpret_cast<const uint32_t(*)[16]>(&v[16]));
+          }
+        }
+        if (c < p.c_out) {  // c_out is a multiple of 16
           uint32_t v[16];
           if (masks[g]) {
             tmem_ld16(taddr + c, v);
@@ -131,164 +217,256 @@ __global__ void __launch_bounds__(V4_THREADS, 1) conv_tc_kernel(const TcParams p
       tc_fence_before();
       mbar_arrive(tempty0 + 8 * buf);
     }
-  } else if (warp == V4_MMA_WARP) {
-    // ================================================================= MMA issuer (whole warp converged)
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.c_out >> 3) << 17) | ((TC_BM >> 4) << 24);
-    const uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);   // SBO 1024 B, version 1, SWIZZLE_128B
-    const uint32_t desc_lo_stage = stage_bytes >> 4, desc_lo_a = b_bytes >> 4;
-    const uint32_t desc_lo0 = ((smem_base & 0x3FFFFu) >> 4) | (1u << 16);       // LBO field = 1 (ignored for swizzled K-major)
-    Ring r;
-    uint32_t it = 0;
-    for (long long st = blockIdx.x; st < num_super; st += gridDim.x, ++it) {
-      const uint32_t buf = it & 1, ph = (it >> 1) & 1;
-      unsigned masks[G];
-      const unsigned umask = tile_masks(st, masks);
-      mbar_wait(tempty0 + 8 * buf, ph ^ 1);
-      tc_fence_after();
-      const uint32_t d0 = tmem_base + buf * G * (uint32_t)p.c_out;
-      unsigned started = 0;
-      for (int k = next_bit(umask, -1); k < 32; k = next_bit(umask, k)) {
-        unsigned act = 0;
+  } else if (warp == V5_MMA_WARP || warp == V5_MMA_WARP + 1) {
+    // ================================================================= MMA issuers (one thread per sub-tile)
+    // Issuing a tcgen05.mma costs the issuing thread ~50 cycles whatever its size (traces, profiles/README.md), so for
+    // c_out <= 128 the instruction stream, not the tensor pipe, bounds a stage: each of the G sub-tiles gets its own
+    // issuing warp, and the loop runs in one lane with every per-stage constant hoisted.
+    const int g = warp - V5_MMA_WARP;
+    if (g < G && lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.c_out >> 3) << 17) | ((TC_BM >> 4) << 24);
+      const uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);   // SBO 1024 B, version 1, SWIZZLE_128B
+      const uint32_t desc_lo_stage = stage_bytes >> 4;
+      const uint32_t b_lo0 = ((smem_base & 0x3FFFFu) >> 4) | (1u << 16);          // LBO field = 1 (ignored for swizzled K-major)
+      const uint32_t a_lo0 = b_lo0 + (b_bytes >> 4) + g * (TC_A_BYTES >> 4);
+      const unsigned sub = p.pk >= 32 ? 0xffffffffu : ((1u << p.pk) - 1u);
+      unsigned nk_tab = 0;  // MMAs (16 channels each) of slice j, 4 bits per slice
+      for (int j = 0; j < KB; ++j) {
+        const int kc = p.pk > 1 ? TC_KB : (j < p.kb0 ? min(TC_KB, p.c0 - j * TC_KB) : min(TC_KB, p.c1 - (j - p.kb0) * TC_KB));
+        nk_tab |= (unsigned)(kc >> 4) << (4 * j);
+      }
+      uint32_t slot = 0, phase = 0, it = 0;
+      int n_mma = 0;
+      for (int st = next_super_lane(); st >= 0; st = next_super_lane(), ++it) {
+        const uint32_t buf = it & 1, ph = (it >> 1) & 1;
+        unsigned masks[G];
+        const unsigned umask = tile_masks(st, masks);
+        unsigned mg = masks[0];
 #pragma unroll
-        for (int g = 0; g < G; ++g) act |= ((masks[g] >> k) & 1u) << g;
-        for (int j = 0; j < KB; ++j) {
-          const int kc = j < p.kb0 ? min(TC_KB, p.c0 - j * TC_KB) : min(TC_KB, p.c1 - (j - p.kb0) * TC_KB);
-          const int nk = kc >> 4;
-          mbar_wait(full0 + 8 * r.slot, r.phase);
-          fence_async_proxy();  // cp.async wrote through the generic proxy; the MMA reads through the async proxy
-          tc_fence_after();
-          if (elect_one()) {
-            const uint32_t b_lo = desc_lo0 + r.slot * desc_lo_stage;
-#pragma unroll
-            for (int g = 0; g < G; ++g) {
-              if (!((act >> g) & 1u)) continue;
-              const uint32_t a_lo = b_lo + desc_lo_a + g * (TC_A_BYTES >> 4);
-              const uint32_t d_tmem = d0 + g * (uint32_t)p.c_out;
-              umma_bf16(d_tmem, make_desc(a_lo, desc_hi), make_desc(b_lo, desc_hi), idesc, (started >> g) & 1u);
+        for (int gg = 1; gg < G; ++gg)
+          if (g == gg) mg = masks[gg];
+        mbar_wait(tempty0 + 8 * buf, ph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (buf * G + g) * (uint32_t)p.c_out;
+        uint32_t started = 0;
+        for (int kv = next_bit(umask, -1); kv < 32; kv = next_bit(umask, kv)) {
+          const bool act = ((mg >> (kv * p.pk)) & sub) != 0 && !TSG_DBG(4);
+          unsigned nks = nk_tab;
+          for (int j = 0; j < KB; ++j, nks >>= 4) {
+            const int nk = nks & 15;
+            if (g == 0) TSG_TRACE(5, n_mma);
+            mbar_wait(full0 + 8 * slot, phase);  // producers fenced their writes towards the async proxy before arriving
+            tc_fence_after();
+            if (g == 0) TSG_TRACE(2, n_mma);
+            if (act) {
+              const uint32_t b_lo = b_lo0 + slot * desc_lo_stage, a_lo = a_lo0 + slot * desc_lo_stage;
+              umma_bf16(d_tmem, make_desc(a_lo, desc_hi), make_desc(b_lo, desc_hi), idesc, started);
               if (nk > 1) umma_bf16(d_tmem, make_desc(a_lo + 2, desc_hi), make_desc(b_lo + 2, desc_hi), idesc, 1u);
               if (nk > 2) umma_bf16(d_tmem, make_desc(a_lo + 4, desc_hi), make_desc(b_lo + 4, desc_hi), idesc, 1u);
               if (nk > 3) umma_bf16(d_tmem, make_desc(a_lo + 6, desc_hi), make_desc(b_lo + 6, desc_hi), idesc, 1u);
+              started = 1;
             }
-            umma_commit(empty0 + 8 * r.slot);  // frees the stage once these MMAs have read it
+            umma_commit(empty0 + 8 * slot);  // this warp's share of "stage consumed" (arrives once its MMAs have read it)
+            if (g == 0) TSG_TRACE(3, n_mma);
+            ++n_mma;
+            if (++slot == nst) {
+              slot = 0;
+              phase ^= 1;
+            }
           }
-          __syncwarp();
-          started |= act;
-          r.advance(nst);
         }
+        umma_commit(tfull0 + 8 * buf);  // this sub-tile's accumulator is complete (immediately if there was no work)
       }
-      if (elect_one()) umma_commit(tfull0 + 8 * buf);  // accumulators complete (immediately if there was no work)
-      __syncwarp();
+    } else if (lane == 0) {
+      while (next_super_lane() >= 0) {}  // spare MMA warp (G == 1): keep the scheduler ring moving
     }
-  } else if (warp == V4_W_WARP) {
+    __syncwarp();
+  } else if (warp == V5_W_WARP) {
     // ================================================================= weight loader
     if (lane == 0) {
       Ring r;
-      for (long long st = blockIdx.x; st < num_super; st += gridDim.x) {
+      int n_w = 0;
+      for (int st = next_super_lane(); st >= 0; st = next_super_lane()) {
         unsigned masks[G];
         const unsigned umask = tile_masks(st, masks);
-        for (int k = next_bit(umask, -1); k < 32; k = next_bit(umask, k)) {
-          const uint8_t *wk = p.packed_w + (size_t)k * KB * b_bytes;
+        for (int kv = next_bit(umask, -1); kv < 32; kv = next_bit(umask, kv)) {
+          const uint8_t *wk = p.packed_w + (size_t)kv * KB * b_bytes;
           for (int j = 0; j < KB; ++j) {
             mbar_wait(empty0 + 8 * r.slot, r.phase ^ 1);
-            mbar_arrive_expect_tx(full0 + 8 * r.slot, b_bytes);
-            bulk_g2s(smem_base + r.slot * stage_bytes, wk + (size_t)j * b_bytes, b_bytes, full0 + 8 * r.slot);
+            TSG_TRACE(4, n_w);
+            ++n_w;
+            if (TSG_DBG(2)) {
+              mbar_arrive(full0 + 8 * r.slot);
+            } else {
+              mbar_arrive_expect_tx(full0 + 8 * r.slot, b_bytes);
+              bulk_g2s(smem_base + r.slot * stage_bytes, wk + (size_t)j * b_bytes, b_bytes, full0 + 8 * r.slot);
+            }
             r.advance(nst);
           }
         }
       }
     }
     __syncwarp();
+  } else if (warp == V5_SCHED_WARP) {
+    // ================================================================= scheduler
+    if (lane == 0) {
+      Ring w;
+      int static_next = blockIdx.x;
+      for (;;) {
+        mbar_wait(sempty0 + 8 * w.slot, w.phase ^ 1);
+        int t;
+        if (p.sched) {
+          t = atomicAdd(p.sched, 1);
+        } else {
+          t = static_next;
+          static_next += gridDim.x;
+        }
+        const int st = t < num_super ? num_super - 1 - t : -1;  // heavy (high-mask) tiles first
+        *reinterpret_cast<volatile int *>(&sched_tile[w.slot]) = st;
+        mbar_arrive(sfull0 + 8 * w.slot);  // release: the tile index is visible to the waiters
+        w.advance(V5_SCHED_SLOTS);
+        if (st < 0) break;
+      }
+      if (p.sched) {  // every CTA draws exactly one terminal ticket: the last one re-arms the counters for the next launch
+        __threadfence();
+        if (atomicAdd(p.sched + 1, 1) == (int)gridDim.x - 1) {
+          p.sched[0] = 0;
+          p.sched[1] = 0;
+          __threadfence();
+        }
+      }
+    }
+    __syncwarp();
   } else {
     // ================================================================= producers
-    const int pt = threadIdx.x - 32 * V4_PROD_WARP0;  // 0..255
-    const int chunk = pt & 7, rsub = pt >> 3;         // 8 lanes cover one 128-byte row; 32 rows per pass, 4 passes
+    // V5_GROUPS independent groups of V5_GROUP_WARPS warps; group g owns the global stages s with s % NG == g, so a
+    // hand-shake (empty wait, landing wait, proxy fence, one arrival per warp) is paid once per 8 G copies per thread,
+    // and while one group waits for its rows to land the others are issuing theirs.
+    const int grp = (warp - V5_PROD_WARP0) / V5_GROUP_WARPS;
+    const int NG = (int)nst < V5_GROUPS ? (int)nst : V5_GROUPS;
+    const int tid = threadIdx.x - 32 * (V5_PROD_WARP0 + grp * V5_GROUP_WARPS);  // 0..127 inside the group
+    const int chunk = tid & 7, rsub = tid >> 3;  // 8 lanes cover one 128-byte tile row; 16 rows per pass, 8 passes
     const uint32_t dst_off = b_bytes + (uint32_t)rsub * 128u + (uint32_t)((chunk ^ (rsub & 7)) << 4);
-    const uint32_t col_bytes = (uint32_t)chunk * 16u;
+    const int cpr = p.pk > 1 ? (p.c0 >> 3) : 8;       // 16-byte chunks per source row inside one slice
+    const int sub = p.pk > 1 ? chunk / cpr : 0;       // which of the PK packed offsets this lane copies
+    const uint32_t col_bytes = (uint32_t)(p.pk > 1 ? chunk % cpr : chunk) * 16u;
     const uint32_t rb0 = (uint32_t)p.c0 * 2u, rb1 = (uint32_t)p.c1 * 2u;
     const char *in0 = reinterpret_cast<const char *>(p.in0) + col_bytes;
     const char *in1 = reinterpret_cast<const char *>(p.in1) + col_bytes;
-    Ring r;
-    for (long long st = blockIdx.x; st < num_super; st += gridDim.x) {
+    const int pk = p.pk, K = p.K, kb0 = p.kb0;
+    const long long n_out = p.n_out;
+    const int *nbr = p.nbr;
+    const bool worker = grp < NG;
+    uint32_t slot = (uint32_t)grp, phase = 0;  // ring position of this group's next stage (always NG stages further)
+    int s_mod = 0;                             // global stage counter modulo NG at the start of the super tile
+    int n_issued = 0;
+    for (int st = next_super(); st >= 0; st = next_super()) {
       unsigned masks[G];
       const unsigned umask = tile_masks(st, masks);
-      const long long m0 = st * G * TC_BM + rsub;
-      int cur[G][4], nxt[G][4];
-      auto load_idx = [&](int (&dst)[G][4], int k) {
-        const int *src = p.nbr + (long long)k * p.n_out;
+      const int nstages = __popc(umask) * KB;
+      int t = grp - s_mod;  // first stage of this super tile that belongs to the group
+      if (t < 0) t += NG;
+      s_mod = (s_mod + nstages) % NG;
+      if (!worker || t >= nstages) continue;
+      const long long m0 = (long long)st * G * TC_BM + rsub;
+      int idx[G][V5_Q];  // neighbour row of tile row rsub + 16 q, or -1
+      auto load_idx = [&](int kv) {
+        const int k = kv * pk + sub;
+        const int *src = nbr + (long long)k * n_out + m0;
 #pragma unroll
         for (int g = 0; g < G; ++g) {
-          const bool act = (masks[g] >> k) & 1u;
+          const bool act = k < K && ((masks[g] >> k) & 1u);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const long long o = m0 + g * TC_BM + 32 * q;
-            dst[g][q] = (act && o < p.n_out) ? (p.nbr ? __ldg(src + o) : (int)o) : -1;
+          for (int q = 0; q < V5_Q; ++q) {
+            const int o = g * TC_BM + 16 * q;
+            idx[g][q] = (act && m0 + o < n_out) ? (nbr ? __ldg(src + o) : (int)(m0 + o)) : -1;
           }
         }
       };
-      int k = next_bit(umask, -1);
-      if (k < 32) load_idx(cur, k);
-      while (k < 32) {
-        const int kn = next_bit(umask, k);
-        if (kn < 32) load_idx(nxt, kn);  // prefetch the next offset's neighbour rows while this one is issued
-        for (int j = 0; j < KB; ++j) {
-          const bool second = j >= p.kb0;
-          const uint32_t rb = second ? rb1 : rb0;
-          const uint32_t ch0b = (uint32_t)(second ? j - p.kb0 : j) * 128u;
-          const char *bp = (second ? in1 : in0) + ch0b;
-          const bool chunk_ok = ch0b + col_bytes < rb;   // this 16-byte chunk exists in the (possibly partial) slice
-          mbar_wait(empty0 + 8 * r.slot, r.phase ^ 1);
-          const uint32_t dst = smem_base + r.slot * stage_bytes + dst_off;
-          if (chunk_ok) {
+      int kv = __fns(umask, 0, t / KB + 1);
+      load_idx(kv);
+      for (;;) {
+        const int j = t % KB;
+        const unsigned act = active_tiles(masks, kv);
+        const bool second = j >= kb0;
+        const uint32_t rb = second ? rb1 : rb0;
+        const uint32_t ch0b = pk > 1 ? 0u : (uint32_t)(second ? j - kb0 : j) * 128u;
+        const char *bp = (second ? in1 : in0) + ch0b;
+        const bool chunk_ok = pk > 1 || ch0b + col_bytes < rb;   // this 16-byte chunk exists in the (possibly partial) slice
+        mbar_wait(empty0 + 8 * slot, phase ^ 1);
+        if (tid == 0 && grp == 0) TSG_TRACE(0, n_issued);
+        const uint32_t dst = smem_base + slot * stage_bytes + dst_off;
+        if (chunk_ok && !TSG_DBG(1)) {
 #pragma unroll
-            for (int g = 0; g < G; ++g) {
-              if (!((masks[g] >> k) & 1u)) continue;
+          for (int g = 0; g < G; ++g) {
+            if (!((act >> g) & 1u)) continue;
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const int idx = cur[g][q];
-                const bool ok = idx >= 0;
-                cp_async16(dst + g * TC_A_BYTES + q * 4096u, bp + (size_t)(ok ? idx : 0) * rb, ok ? 16u : 0u);
-              }
+            for (int q = 0; q < V5_Q; ++q) {
+              const int v = idx[g][q];
+              cp_async16(dst + g * TC_A_BYTES + q * 2048u, bp + (unsigned long long)(unsigned)max(v, 0) * rb, v >= 0 ? 16u : 0u);
             }
           }
-          cp_async_arrive(full0 + 8 * r.slot);
-          r.advance(nst);
         }
-#pragma unroll
-        for (int g = 0; g < G; ++g)
-#pragma unroll
-          for (int q = 0; q < 4; ++q) cur[g][q] = nxt[g][q];
-        k = kn;
+        if (tid == 0 && grp == 0) TSG_TRACE(6, n_issued);
+        // the index registers are free again: fetch the neighbour rows of this group's next stage while the copies land
+        t += NG;
+        const bool more = t < nstages;
+        if (more) {
+          const int kn = __fns(umask, 0, t / KB + 1);
+          if (kn != kv) load_idx(kn);
+          kv = kn;
+        }
+        if (tid == 0 && grp == 0) TSG_TRACE(7, n_issued);
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        fence_async_proxy();  // generic-proxy writes -> visible to the async proxy (tensor core reads)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full0 + 8 * slot);
+        if (tid == 0 && grp == 0) TSG_TRACE(1, n_issued);
+        ++n_issued;
+        slot += NG;
+        if (slot >= nst) {
+          slot -= nst;
+          phase ^= 1;
+        }
+        if (!more) break;
       }
     }
-    asm volatile("cp.async.wait_all;" ::: "memory");
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == V4_MMA_WARP) {
+  if (warp == V5_MMA_WARP) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
   }
 }
 
-// W (K, c_in, c_out) fp32 -> per (k, 64-channel slice) [c_out][64] bf16, K-major, 128B-swizzled: the byte image the
-// MMA reads, so a linear bulk copy stages it.  Optional per-output-channel scale (folded BatchNorm).
+// offsets packed per 64-channel slice: narrow single-source layers put 64 / c0 kernel offsets side by side
+__host__ __device__ inline int slice_pack(int c0, int c1) { return (c1 == 0 && (c0 == 16 || c0 == 32)) ? TC_KB / c0 : 1; }
+
+// W (K, c_in, c_out) fp32 -> per (virtual offset, 64-channel slice) [c_out][64] bf16, K-major, 128B-swizzled: the byte
+// image the MMA reads, so a linear bulk copy stages it.  Optional per-output-channel scale (folded BatchNorm).
 __global__ void pack_weights_kernel(const float *__restrict__ w, int K, int c_in, int c_out, int c0, int c1, int kb0,
-                                    int KB, const float *__restrict__ out_scale, __nv_bfloat16 *__restrict__ packed) {
-  const long long total = (long long)K * KB * c_out * TC_KB;
+                                    int KB, int pk, const float *__restrict__ out_scale,
+                                    __nv_bfloat16 *__restrict__ packed) {
+  const int KV = (K + pk - 1) / pk;
+  const long long total = (long long)KV * KB * c_out * TC_KB;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(t % TC_KB);
     const int n = (int)((t / TC_KB) % c_out);
     const int j = (int)((t / ((long long)TC_KB * c_out)) % KB);
-    const int k = (int)(t / ((long long)TC_KB * c_out * KB));
-    const bool second = j >= kb0;
-    const int ch = (second ? j - kb0 : j) * TC_KB + c;          // channel within its source tensor
-    const int g = second ? c0 + ch : ch;                        // row of W[k]
+    const int kv = (int)(t / ((long long)TC_KB * c_out * KB));
     float v = 0.f;
-    if (ch < (second ? c1 : c0) && g < c_in) {
-      v = w[((long long)k * c_in + g) * c_out + n];
-      if (out_scale) v *= out_scale[n];
+    if (pk > 1) {
+      const int k = kv * pk + c / c0, ch = c % c0;
+      if (k < K && ch < c_in) v = w[((long long)k * c_in + ch) * c_out + n];
+    } else {
+      const bool second = j >= kb0;
+      const int ch = (second ? j - kb0 : j) * TC_KB + c;          // channel within its source tensor
+      const int g = second ? c0 + ch : ch;                        // row of W[k]
+      if (ch < (second ? c1 : c0) && g < c_in) v = w[((long long)kv * c_in + g) * c_out + n];
     }
-    const long long blk = ((long long)k * KB + j) * c_out * TC_KB;
+    if (out_scale) v *= out_scale[n];
+    const long long blk = ((long long)kv * KB + j) * c_out * TC_KB;
     const int sw = (((c >> 3) ^ (n & 7)) << 3) | (c & 7);
     packed[blk + (long long)n * TC_KB + sw] = __float2bfloat16_rn(v);
   }
@@ -301,8 +479,9 @@ using namespace tsg;
 extern "C" {
 
 size_t tsg_conv_pack_bytes(int k, int c0, int c1, int c_out) {
-  const int KB = (c0 + TC_KB - 1) / TC_KB + (c1 + TC_KB - 1) / TC_KB;
-  return (size_t)k * KB * c_out * TC_KB * 2;
+  const int pk = slice_pack(c0, c1);
+  const int KB = pk > 1 ? 1 : (c0 + TC_KB - 1) / TC_KB + (c1 + TC_KB - 1) / TC_KB;
+  return (size_t)((k + pk - 1) / pk) * KB * c_out * TC_KB * 2;
 }
 
 int tsg_conv_pack_weights(const float *weight, int k, int c_in, int c_out, int c0, int c1, const float *out_scale,
@@ -311,47 +490,43 @@ int tsg_conv_pack_weights(const float *weight, int k, int c_in, int c_out, int c
     set_error("tsg_conv_pack_weights: need c0,c1,c_out multiples of 16, c_out<=256, c0+c1>=c_in");
     return TSG_ERR_UNSUPPORTED;
   }
-  const int kb0 = (c0 + TC_KB - 1) / TC_KB, KB = kb0 + (c1 + TC_KB - 1) / TC_KB;
-  const long long total = (long long)k * KB * c_out * TC_KB;
-  pack_weights_kernel<<<grid_for(total, 256), 256, 0, stream>>>(weight, k, c_in, c_out, c0, c1, kb0, KB, out_scale,
+  const int pk = slice_pack(c0, c1);
+  const int kb0 = pk > 1 ? 1 : (c0 + TC_KB - 1) / TC_KB, KB = pk > 1 ? 1 : kb0 + (c1 + TC_KB - 1) / TC_KB;
+  const long long total = (long long)((k + pk - 1) / pk) * KB * c_out * TC_KB;
+  pack_weights_kernel<<<grid_for(total, 256), 256, 0, stream>>>(weight, k, c_in, c_out, c0, c1, kb0, KB, pk, out_scale,
                                                                 (__nv_bfloat16 *)packed);
   return check_launch("tsg_conv_pack_weights");
 }
 
-}  // extern "C"
-
-namespace tsg {
-// TMA gather4 producer variant (conv_tc_tma.cu): opt-in with TSG_TC_IMPL=tma, kept for A/B timing
-int conv_fwd_tc_tma(const void *in0, int c0, const void *in1, int c1, int64_t n_in, const void *packed_w, int k,
-                    int c_out, const int32_t *nbr, const uint32_t *tile_mask, int64_t n_out, void *out, int out_dtype,
-                    const float *bias, const void *residual, int relu, int num_sms_hint, tsg_stream_t stream);
-}  // namespace tsg
-
-extern "C" {
+/* profiling aid, not part of the public header: copies the trace of the last TSG_TC_DEBUG&128 launch to `host` (6 x 96 int64) */
+int tsg_debug_conv_trace(long long *host) {
+  TSG_CUDA(cudaDeviceSynchronize());
+  TSG_CUDA(cudaMemcpyFromSymbol(host, g_trace, sizeof(long long) * 8 * TRACE_N));
+  return TSG_OK;
+}
 
 int tsg_conv_fwd_tc(const void *in0, int c0, const void *in1, int c1, int64_t n_in, const void *packed_w, int k,
                     int c_out, const int32_t *nbr, const uint32_t *tile_mask, const int32_t *perm, int64_t n_out,
                     void *out, int out_dtype, const float *bias, const void *residual, int relu, int num_sms_hint,
-                    tsg_stream_t stream) {
+                    int32_t *sched, tsg_stream_t stream) {
   if (c0 % 16 || c1 % 16 || c_out % 16 || c_out > 256 || c_out <= 0 || c0 <= 0 || k <= 0 || k > 32 ||
       (out_dtype != TSG_BF16 && out_dtype != TSG_F32)) {
     set_error("tsg_conv_fwd_tc: need c0,c1,c_out multiples of 16, c_out<=256, K<=32, out bf16/f32");
     return TSG_ERR_UNSUPPORTED;
   }
   if (n_out <= 0) return TSG_OK;
-  static const char *impl = getenv("TSG_TC_IMPL");
-  if (impl && strcmp(impl, "tma") == 0 && !perm) {
-    const int rc = conv_fwd_tc_tma(in0, c0, in1, c1, n_in, packed_w, k, c_out, nbr, tile_mask, n_out, out, out_dtype,
-                                   bias, residual, relu, num_sms_hint, stream);
-    if (rc >= 0) return rc;  // < 0: no tensor map could be encoded, use the default producer
+  if (n_out >= (1ll << 31) - 4 * TC_BM || n_in * (int64_t)(c0 > c1 ? c0 : c1) * 2 >= (1ll << 40)) {
+    set_error("tsg_conv_fwd_tc: tensor too large for 32-bit tile arithmetic");
+    return TSG_ERR_UNSUPPORTED;
   }
   TcParams p;
   p.in0 = (const __nv_bfloat16 *)in0;
   p.in1 = (const __nv_bfloat16 *)in1;
   p.c0 = c0;
   p.c1 = c1;
-  p.kb0 = (c0 + TC_KB - 1) / TC_KB;
-  p.kb1 = (c1 + TC_KB - 1) / TC_KB;
+  p.pk = slice_pack(c0, c1);
+  p.kb0 = p.pk > 1 ? 1 : (c0 + TC_KB - 1) / TC_KB;
+  p.kb1 = p.pk > 1 ? 0 : (c1 + TC_KB - 1) / TC_KB;
   p.packed_w = (const uint8_t *)packed_w;
   p.K = k;
   p.c_out = c_out;
@@ -364,18 +539,21 @@ int tsg_conv_fwd_tc(const void *in0, int c0, const void *in1, int c1, int64_t n_
   p.bias = bias;
   p.residual = (const __nv_bfloat16 *)residual;
   p.relu = relu;
+  p.sched = sched;
+  static const char *dbg_env = getenv("TSG_TC_DEBUG");  // profiling knock-outs (wrong results): 1 no gathers, 2 no weight
+  p.dbg = dbg_env ? atoi(dbg_env) : 0;                  // copies, 4 no MMAs, 8 no epilogue stores
   const int sms = num_sms_hint > 0 ? num_sms_hint : num_sms();
   const long long num_tiles = (n_out + TC_BM - 1) / TC_BM;
   // G sub-tiles share every weight slice; bounded by TMEM (2 buffers x G x c_out fp32 columns <= 512) and by the
   // number of super tiles needed to keep every SM busy
-  int G = c_out <= 64 ? 4 : (c_out <= 128 ? 2 : 1);
+  int G = c_out <= 128 ? 2 : 1;  // (G = 4 spills the producers' index registers at 736 threads per CTA)
   while (G > 1 && (num_tiles + G - 1) / G < 2LL * sms) G >>= 1;
   uint32_t cols = 32;
   while (cols < 2u * (uint32_t)G * (uint32_t)c_out) cols <<= 1;
   p.tmem_cols = cols;
   const size_t b_bytes = (size_t)c_out * 128, stage_bytes = b_bytes + (size_t)G * TC_A_BYTES, budget = 222 * 1024;
   int stages = (int)(budget / stage_bytes);
-  if (stages > V4_MAX_STAGES) stages = V4_MAX_STAGES;
+  if (stages > V5_MAX_STAGES) stages = V5_MAX_STAGES;
   if (stages < 2) {
     set_error("tsg_conv_fwd_tc: not enough shared memory for the pipeline");
     return TSG_ERR_UNSUPPORTED;
@@ -387,14 +565,12 @@ int tsg_conv_fwd_tc(const void *in0, int c0, const void *in1, int c1, int64_t n_
   if (!configured) {
     TSG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     TSG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-    TSG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     configured = true;
   }
   const long long num_super = (num_tiles + G - 1) / G;
   const unsigned grid = (unsigned)(num_super < sms ? num_super : sms);
-  if (G == 4) conv_tc_kernel<4><<<grid, V4_THREADS, smem, stream>>>(p);
-  else if (G == 2) conv_tc_kernel<2><<<grid, V4_THREADS, smem, stream>>>(p);
-  else conv_tc_kernel<1><<<grid, V4_THREADS, smem, stream>>>(p);
+  if (G == 2) conv_tc_kernel<2><<<grid, V5_THREADS, smem, stream>>>(p);
+  else conv_tc_kernel<1><<<grid, V5_THREADS, smem, stream>>>(p);
   return check_launch("tsg_conv_fwd_tc");
 }
 

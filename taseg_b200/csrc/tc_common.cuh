@@ -7,9 +7,7 @@ namespace tsg {
 constexpr int TC_BM = 128;
 constexpr int TC_KB = 64;                       // channels per unit (128 B of bf16)
 constexpr int TC_A_BYTES = TC_BM * TC_KB * 2;   // 16 KB
-constexpr int TC_MAX_A = 12, TC_MAX_B = 4;     // ring depths (slots)
-constexpr int TC_EPI_WARPS = 4, TC_PROD_WARPS = 4;
-constexpr int TC_THREADS = 32 * (TC_EPI_WARPS + 1 + TC_PROD_WARPS);
+constexpr int TC_EPI_WARPS = 4;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -82,6 +80,17 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,"
+      "%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): rows of 128 B, 8-row groups
 // 1024 B apart (SBO), version 1, layout type 2.  `addr` may be advanced by 32 B per K=16 step inside the row.
@@ -92,6 +101,7 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t addr) {
 struct TcParams {
   const __nv_bfloat16 *in0, *in1;
   int c0, c1, kb0, kb1;
+  int pk;  // kernel offsets packed side by side in one 64-channel slice (1, 2 or 4; > 1 only for single-source c0 <= 32)
   const uint8_t *packed_w;
   int K, c_out, na, nb;
   const int *nbr;
@@ -104,6 +114,8 @@ struct TcParams {
   const __nv_bfloat16 *residual;
   int relu;
   uint32_t tmem_cols;
+  int dbg;     // profiling knock-out bits (TSG_TC_DEBUG), 0 in production
+  int *sched;  // {next ticket, finished CTAs}, zero between launches; NULL = static round-robin tile assignment
 };
 
 struct Ring {  // slot + phase of a circular mbarrier pipeline

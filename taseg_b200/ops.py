@@ -6,6 +6,7 @@ data-dependent size must become a tensor shape (`.item()` on a device counter), 
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Optional, Sequence, Tuple
 
 import numpy as np
@@ -410,6 +411,19 @@ def cast_pad_bf16(feats: torch.Tensor, c_pad: int) -> torch.Tensor:
     return out
 
 
+_SCHED = {}
+
+
+def _sched_ws(device) -> torch.Tensor:
+    """Two zeroed int32 per (device, stream) for the convolution's dynamic tile scheduler (the kernel re-zeroes them)."""
+    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    t = _SCHED.get(key)
+    if t is None:
+        t = _SCHED[key] = torch.zeros(2, dtype=torch.int32, device=device)
+    return t
+
+
+DYNAMIC_TILES = os.environ.get("TSG_DYNAMIC_TILES", "1") != "0"   # A/B switch: in-kernel dynamic tile scheduler
 PROFILE = None   # set to a list to record (tag, start_event, end_event, pairs, c_in, c_out) per tensor-core launch
 
 
@@ -433,7 +447,8 @@ def conv_forward_tc(in0: torch.Tensor, in1: Optional[torch.Tensor], packed_w: to
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
     call("tsg_conv_fwd_tc", ptr(in0), c0, ptr(in1), c1, in0.shape[0], ptr(packed_w), k, c_out, ptr(nbr), ptr(tile_mask),
-         ptr(perm), int(n_out), ptr(out), L.DTYPES[out_dtype], ptr(bias), ptr(residual), int(relu), int(num_sms), stream())
+         ptr(perm), int(n_out), ptr(out), L.DTYPES[out_dtype], ptr(bias), ptr(residual), int(relu), int(num_sms),
+         ptr(_sched_ws(in0.device)) if DYNAMIC_TILES else None, stream())
     if PROFILE is not None:
         e1.record()
         PROFILE.append((k, e0, e1, pairs, c0 + c1, c_out, n_out))
