@@ -96,7 +96,8 @@ int tsg_kmap_from_pairs(const int32_t *nbmaps, const int32_t *nbsizes_host, int 
                         int64_t n_rows_out, int32_t *nbr, tsg_stream_t stream);
 
 /* ---------------------------------------------------------------- sort / unique (a5, a12, a16)
- * Stable LSD radix sort of 64-bit keys with a 32-bit payload (payload = 0..n-1 when vals_in is NULL).
+ * Stable LSD radix sort (9-bit digits, one-sweep with decoupled look-back) of 64-bit keys with a 32-bit payload
+ * (payload = 0..n-1 when vals_in is NULL); n < 2^30.
  * Results land in keys_out/vals_out.  ws: tsg_sort_ws_bytes(n). */
 size_t tsg_sort_ws_bytes(int64_t n);
 int tsg_sort_pairs(const uint64_t *keys_in, const uint32_t *vals_in, int64_t n, int begin_bit, int end_bit,
@@ -110,7 +111,7 @@ int tsg_sort_pairs(const uint64_t *keys_in, const uint32_t *vals_in, int64_t n, 
  * input order, inverse (N) = voxel row of every input point; *m_dev = number of unique voxels.
  * field_bits_host: NULL, or HOST int32[4] = bit widths of x,y,z,b when the caller knows 0 <= coordinate < 2^bits
  * (true after the loader's min-shift): sort keys are then packed densely and the radix sort runs
- * ceil(sum/8) passes instead of 8; a coordinate outside the promise raises bit 0 of *status. */
+ * ceil(sum/9) passes instead of 8; a coordinate outside the promise raises bit 0 of *status. */
 size_t tsg_unique_ws_bytes(int64_t n);
 int tsg_unique_coords(const int32_t *in_coords, int64_t n, int trunc_stride, const int32_t *field_bits_host,
                       int32_t *out_coords, int32_t *first_idx, int32_t *inverse, int32_t *m_dev, int32_t *status,
@@ -234,8 +235,9 @@ int tsg_conv_fwd_tc(const void *in0, int c0, const void *in1, int c1, int64_t n_
                     int c_out, const int32_t *nbr, const uint32_t *tile_mask, const int32_t *perm, int64_t n_out,
                     void *out, int out_dtype, const float *bias, const void *residual, int relu, int num_sms,
                     int32_t *sched, tsg_stream_t stream);
-/* Tile-row order for tsg_conv_fwd_tc: stable sort of the n_out output rows by their K-bit neighbour mask
- * (bit k set iff nbr[k, o] >= 0).  Outputs: perm (n_out) int32 = output row of tile row r, nbr_sorted (K, n_out) with
+/* Tile-row order for tsg_conv_fwd_tc: stable sort of the n_out output rows by a K-bit key built from their neighbour
+ * mask (offset k present iff nbr[k, o] >= 0; for K = 27 the rarest offsets — cube corners, then edges — are the most
+ * significant key bits, otherwise bit k = offset k).  Outputs: perm (n_out) int32 = output row of tile row r, nbr_sorted (K, n_out) with
  * nbr_sorted[k, r] = nbr[k, perm[r]], tile_mask (ceil(n_out/128)) of the sorted table.  ws: tsg_kmap_sort_ws_bytes. */
 size_t tsg_kmap_sort_ws_bytes(int64_t n_out);
 int tsg_kmap_sort_rows(const int32_t *nbr, int k, int64_t n_out, int32_t *perm, int32_t *nbr_sorted,

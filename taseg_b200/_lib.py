@@ -89,10 +89,11 @@ def check(status: int, what: str = "") -> None:
     raise RuntimeError(f"{what}: status {status}: {msg}")
 
 
-# kernels launched per C-ABI call (for the benchmark's gpu_launches claim); sort = 3 kernels x 8 passes
+# kernels launched per C-ABI call (for the benchmark's gpu_launches claim; conservative: sorts launch 1 histogram kernel
+# + one kernel per 9-bit pass, counted here at their minimum for the key widths of the benchmark)
 KERNELS_PER_CALL = {"tsg_table_build": 2, "tsg_coord_table_build": 2, "tsg_kmap_pairs": 2, "tsg_kmap_transpose": 2,
-                    "tsg_sort_pairs": 24, "tsg_unique_coords": 28, "tsg_unique_hash": 28, "tsg_aggregate_quantize": 4,
-                    "tsg_compact_rows": 3, "tsg_kmap_sort_rows": 15}
+                    "tsg_sort_pairs": 4, "tsg_unique_coords": 7, "tsg_unique_hash": 11, "tsg_aggregate_quantize": 4,
+                    "tsg_compact_rows": 3, "tsg_kmap_sort_rows": 5}
 launch_count = 0
 
 

@@ -268,7 +268,12 @@ def _tc_case(seed, n, c0, c1, c_out, ks, relu, residual, out_dtype, dense_span):
     nbr_s, mask_s, perm = km.sorted()
     assert np.array_equal(np.sort(npy(perm)), np.arange(n)), "perm is not a permutation"
     assert torch.equal(nbr_s, km.nbr[:, perm.long()])
-    keys = ((km.nbr >= 0).long() << torch.arange(k, device="cuda").view(-1, 1)).sum(0)
+    pos = list(range(k))    # bit position of offset j in the sort key: rare offsets are the most significant (sort.cu)
+    if k == 27:
+        order = [0, 2, 6, 8, 18, 20, 24, 26, 1, 3, 5, 7, 19, 21, 23, 25, 4, 22, 9, 11, 15, 17, 10, 12, 14, 16, 13]
+        for r, j in enumerate(order):
+            pos[j] = 26 - r
+    keys = ((km.nbr >= 0).long() << torch.tensor(pos, device="cuda").view(-1, 1)).sum(0)
     ks_sorted = keys[perm.long()]
     assert bool((ks_sorted[1:] >= ks_sorted[:-1]).all()), "tile rows are not ordered by neighbour mask"
     same = ks_sorted[1:] == ks_sorted[:-1]
