@@ -183,8 +183,7 @@ def main():
 
     def step():
         out = frontend.aggregate_voxelize(pts, mfb, VOXEL, cur_idx)
-        logits = engine(out["coords"], out["feats"], field_bits=out["field_bits"])
-        return ops.gather_rows(logits.contiguous(), out["cur_rows"])
+        return engine(out["coords"], out["feats"], field_bits=out["field_bits"], out_rows=out["cur_rows"])
 
     def step_e2e():
         pts.copy_(host_pts, non_blocking=True)

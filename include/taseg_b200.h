@@ -186,6 +186,14 @@ int tsg_point_query(const void *table, int64_t slots, const float *pcoords, int6
                     tsg_stream_t stream);
 int tsg_trilinear_query(const void *table, int64_t slots, const float *pcoords, int64_t n, int stride, int nearest,
                         int32_t *idx8, float *w8, tsg_stream_t stream);
+/* Fused multi-scale devoxelisation: out[j, :c_out] = sum_s sum_k w_{s,k}(p) * feats_s[idx_{s,k}(p), :c_out] with
+ * p = pcoords[rows[j]] (rows == NULL: p = pcoords[j]) — tsg_trilinear_query + tsg_devoxelize_fwd of up to four scales,
+ * their sum and the final row gather in one pass (voxel_to_point x3 + classifier tail of minkunet_ms.py:392-420 once the
+ * Linear has been applied per scale at voxel level).  tables/slots/strides/feats: HOST arrays of n_scales entries
+ * (device tables from tsg_coord_table_build, fp32 device features (n_s, c), c % 4 == 0); out (m, c_out) fp32. */
+int tsg_devoxelize_multi(int n_scales, const void *const *tables, const int64_t *slots, const int32_t *strides,
+                         const float *const *feats, int c, const float *pcoords, const int32_t *rows, int64_t m,
+                         float *out, int c_out, tsg_stream_t stream);
 /* initial_voxelize front end (minkunet/utils.py:11-16): fc = (C*init_res)/after_res in fp32 (mul then div),
  * out_f (N,4) fp32 = [fc, b], out_i (N,4) int32 = floor. */
 int tsg_rescale_coords(const float *pcoords, int64_t n, float init_res, float after_res, float *out_f,

@@ -109,6 +109,40 @@ __device__ inline void table_insert(Slot *tab, unsigned long long mask, unsigned
   }
 }
 
+// Home slot of a packed COORDINATE key: the line (8 slots = 128 B) is chosen by hashing everything but the three low z
+// bits, the slot inside the line by those bits.  Voxels that are neighbours in z then sit in the same 128-byte line, so
+// the three dz probes of a kernel map (and the probes of a warp's 32 consecutive, mostly z-adjacent rows) hit one or
+// two L2 sectors instead of three random ones.  Any collision falls back to the usual linear probing.
+__device__ __forceinline__ unsigned long long coord_home(unsigned long long key, unsigned long long mask) {
+#ifdef TSG_COORD_LOCALITY
+  return ((mix64(key >> 3) << 3) | (key & 7ull)) & mask;
+#else
+  return mix64(key) & mask;
+#endif
+}
+
+__device__ inline void table_insert_coord(Slot *tab, unsigned long long mask, unsigned long long key, int val) {
+  unsigned long long s = coord_home(key, mask);
+  while (true) {
+    unsigned long long prev = atomicCAS(&tab[s].key, EMPTY_KEY, key);
+    if (prev == EMPTY_KEY || prev == key) {
+      atomicMin(&tab[s].val, val);
+      return;
+    }
+    s = (s + 1) & mask;
+  }
+}
+
+__device__ inline int table_find_coord(const Slot *__restrict__ tab, unsigned long long mask, unsigned long long key) {
+  unsigned long long s = coord_home(key, mask);
+  while (true) {
+    const ulonglong2 raw = __ldg(reinterpret_cast<const ulonglong2 *>(tab + s));
+    if (raw.x == key) return (int)(unsigned)(raw.y & 0xffffffffull);
+    if (raw.x == EMPTY_KEY) return -1;
+    s = (s + 1) & mask;
+  }
+}
+
 __device__ inline int table_find(const Slot *__restrict__ tab, unsigned long long mask, unsigned long long key) {
   unsigned long long s = mix64(key) & mask;
   while (true) {

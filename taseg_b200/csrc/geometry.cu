@@ -2,6 +2,7 @@
 // All of this is HBM/L2-bound integer work: coalesced int4 coordinate loads, 16-byte table slots read with one
 // 128-bit load per probe, outputs written k-major so that the convolution reads 128 consecutive rows per offset.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -61,7 +62,7 @@ __global__ void table_insert_coords_kernel(const int4 *__restrict__ coords, int6
       if (status) atomicOr(status, 1);
       continue;
     }
-    table_insert(tab, mask, pack_coord(c.x, c.y, c.z, c.w), (int)i);
+    table_insert_coord(tab, mask, pack_coord(c.x, c.y, c.z, c.w), (int)i);
   }
 }
 
@@ -77,18 +78,22 @@ struct Offsets {
   int v[32 * 3];
 };
 
-// One CTA = 1024 consecutive output voxels (256 threads x 4 rows), looping over the K offsets.  For a fixed
-// offset a warp probes 32 consecutive voxels (their coordinates differ mostly in z), writes nbr k-major with
-// full 128-byte stores and counts hits with a ballot; per-offset CTA totals go to blockcnt[k][cta].
+// One CTA = 1024 consecutive output voxels (256 threads x 4 rows) x `ksplit` kernel offsets (grid.y covers the rest; small
+// maps split the offsets over more CTAs so that every SM has probes in flight).  For a fixed offset a warp probes 32
+// consecutive voxels, four independent probes per thread; nbr is written k-major with full 128-byte STREAMING stores
+// (the 4 K N bytes of the map must not evict the table from L2: with plain stores the stride-1 map of the benchmark
+// batch, 76 MB next to a 32 MB table in a 126 MB L2, ran anywhere between 240 and 840 us); hits are counted with a
+// ballot, per-offset CTA totals go to blockcnt[k][cta].
 __global__ void __launch_bounds__(256) kmap_build_kernel(const Slot *__restrict__ tab, unsigned long long mask,
                                                          const int4 *__restrict__ out_coords, int64_t n_out,
-                                                         Offsets offs, int K, int *__restrict__ nbr,
+                                                         Offsets offs, int K, int ksplit, int *__restrict__ nbr,
                                                          int *__restrict__ nbsizes, int *__restrict__ blockcnt,
                                                          int64_t nblk) {
   __shared__ int s_cnt[32];
   if (threadIdx.x < 32) s_cnt[threadIdx.x] = 0;
   __syncthreads();
   const int64_t base = (int64_t)blockIdx.x * KM_ROWS;
+  const int k0 = blockIdx.y * ksplit, k1 = min(K, k0 + ksplit);
   int4 c[4];
   bool ok[4];
 #pragma unroll
@@ -97,7 +102,7 @@ __global__ void __launch_bounds__(256) kmap_build_kernel(const Slot *__restrict_
     ok[r] = o < n_out;
     c[r] = ok[r] ? __ldg(out_coords + o) : make_int4(0, 0, 0, 0);
   }
-  for (int k = 0; k < K; ++k) {
+  for (int k = k0; k < k1; ++k) {
     const int dx = offs.v[3 * k], dy = offs.v[3 * k + 1], dz = offs.v[3 * k + 2];
     int hits = 0;
 #pragma unroll
@@ -105,18 +110,18 @@ __global__ void __launch_bounds__(256) kmap_build_kernel(const Slot *__restrict_
       int found = -1;
       if (ok[r]) {
         const int x = c[r].x + dx, y = c[r].y + dy, z = c[r].z + dz;
-        if (coord_in_range(x, y, z, c[r].w)) found = table_find(tab, mask, pack_coord(x, y, z, c[r].w));
-        nbr[(int64_t)k * n_out + base + r * 256 + threadIdx.x] = found;
+        if (coord_in_range(x, y, z, c[r].w)) found = table_find_coord(tab, mask, pack_coord(x, y, z, c[r].w));
+        __stcs(nbr + (int64_t)k * n_out + base + r * 256 + threadIdx.x, found);
       }
       hits += __popc(__ballot_sync(0xffffffffu, found >= 0));
     }
-    if ((threadIdx.x & 31) == 0 && hits) atomicAdd(&s_cnt[k], hits);
+    if ((threadIdx.x & 31) == 0 && hits) atomicAdd(&s_cnt[k - k0], hits);
   }
   __syncthreads();
-  if (threadIdx.x < K) {
+  if (threadIdx.x < k1 - k0) {
     const int v = s_cnt[threadIdx.x];
-    blockcnt[(int64_t)threadIdx.x * nblk + blockIdx.x] = v;
-    if (v) atomicAdd(&nbsizes[threadIdx.x], v);
+    blockcnt[(int64_t)(k0 + threadIdx.x) * nblk + blockIdx.x] = v;
+    if (v) atomicAdd(&nbsizes[k0 + threadIdx.x], v);
   }
 }
 
@@ -281,9 +286,12 @@ int tsg_kmap_build(const void *table, int64_t slots, const int32_t *out_coords, 
   Offsets offs;
   for (int i = 0; i < 3 * k; ++i) offs.v[i] = offsets_host[i];
   const int64_t nblk = tsg_kmap_blocks(n_out);
-  kmap_build_kernel<<<(unsigned)nblk, 256, 0, stream>>>((const Slot *)table, (unsigned long long)(slots - 1),
-                                                        (const int4 *)out_coords, n_out, offs, k, nbr, nbsizes,
-                                                        blockcnt, nblk);
+  // enough CTAs to cover the chip a few times: split the offsets when the map has few row blocks
+  int ksplit = k;
+  while (ksplit > 1 && nblk * ((k + ksplit - 1) / ksplit) < 4LL * num_sms()) ksplit = (ksplit + 2) / 3;
+  kmap_build_kernel<<<dim3((unsigned)nblk, (unsigned)((k + ksplit - 1) / ksplit)), 256, 0, stream>>>(
+      (const Slot *)table, (unsigned long long)(slots - 1), (const int4 *)out_coords, n_out, offs, k, ksplit, nbr, nbsizes,
+      blockcnt, nblk);
   return check_launch("tsg_kmap_build");
 }
 

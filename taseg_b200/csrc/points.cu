@@ -312,7 +312,7 @@ __global__ void point_query_kernel(const Slot *__restrict__ tab, unsigned long l
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float4 p = __ldg(pc + i);
     const int x = floor_to_stride(p.x, s), y = floor_to_stride(p.y, s), z = floor_to_stride(p.z, s), b = (int)p.w;
-    idx[i] = coord_in_range(x, y, z, b) ? table_find(tab, mask, pack_coord(x, y, z, b)) : -1;
+    idx[i] = coord_in_range(x, y, z, b) ? table_find_coord(tab, mask, pack_coord(x, y, z, b)) : -1;
   }
 }
 
@@ -342,7 +342,7 @@ __global__ void trilinear_query_kernel(const Slot *__restrict__ tab, unsigned lo
     for (int k = 0; k < 8; ++k) {
       const int ix = k >> 2, iy = (k >> 1) & 1, iz = k & 1;
       const int x = bx + ix * s, y = by + iy * s, z = bz + iz * s;
-      id[k] = coord_in_range(x, y, z, b) ? table_find(tab, mask, pack_coord(x, y, z, b)) : -1;
+      id[k] = coord_in_range(x, y, z, b) ? table_find_coord(tab, mask, pack_coord(x, y, z, b)) : -1;
       float wk = __fmul_rn(__fmul_rn(ix ? xh : xl, iy ? yh : yl), iz ? zh : zl);
       if (s != 1) wk = __fdiv_rn(wk, (float)(s * s * s));
       if (id[k] < 0) wk = 0.f;
@@ -357,6 +357,83 @@ __global__ void trilinear_query_kernel(const Slot *__restrict__ tab, unsigned lo
       if (nearest && k > 0) { wk = 0.f; v = -1; }
       idx8[i * 8 + k] = v;
       w8[i * 8 + k] = wk;
+    }
+  }
+}
+
+// Fused multi-scale devoxelisation (the tail of MinkUNet / MinkUNetMs once the classifier has been applied per scale at
+// voxel level): out[j,:] = sum_s sum_k w_{s,k}(p) * feats_s[idx_{s,k}(p), :], p = pcoords[rows[j]].  The 8-corner query,
+// calc_ti_weights and the gather of every scale happen in registers: no (N,8) index / weight tensors, no per-scale
+// outputs, no adds, no final row gather.  8 lanes per point: lane j probes corner j, then owns channels 4j..4j+3.
+struct DevoxScales {
+  const Slot *tab[4];
+  unsigned long long mask[4];
+  const float *feats[4];
+  int stride[4];
+  int count;
+};
+__global__ void __launch_bounds__(256) devoxelize_multi_kernel(DevoxScales sc, const float4 *__restrict__ pc,
+                                                               const int *__restrict__ rows, int64_t m, int c,
+                                                               float *__restrict__ out, int c_out) {
+  const int sub = threadIdx.x & 7;
+  const unsigned gmask = 0xffu << (threadIdx.x & 24);  // the 8 lanes of this point
+  const int gl0 = threadIdx.x & 24;
+  const int64_t step = (int64_t)gridDim.x * (blockDim.x >> 3);
+  const int64_t m_pad = (m + 3) & ~(int64_t)3;         // whole warps stay converged for the shuffles
+  for (int64_t j = blockIdx.x * (int64_t)(blockDim.x >> 3) + (threadIdx.x >> 3); j < m_pad; j += step) {
+    const bool live = j < m;
+    const int64_t pi = live ? (rows ? (int64_t)__ldg(rows + j) : j) : 0;
+    const float4 p = __ldg(pc + pi);
+    const float pv[3] = {p.x, p.y, p.z};
+    const int b = (int)p.w;
+    const int ix = sub >> 2, iy = (sub >> 1) & 1, iz = sub & 1;
+    for (int ch = 4 * sub; ch < c; ch += 32) {   // one pass for c <= 32
+      float4 total = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int si = 0; si < 4; ++si) {
+        if (si >= sc.count) break;
+        const int s = sc.stride[si];
+        const float fs = (float)s;
+        float pf[3], lo[3], hi[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          pf[a] = (s != 1) ? __fmul_rn(floorf(__fdiv_rn(pv[a], fs)), fs) : floorf(pv[a]);
+          lo[a] = __fsub_rn(__fadd_rn(pf[a], fs), pv[a]);
+          hi[a] = __fsub_rn(pv[a], pf[a]);
+        }
+        float wk = __fmul_rn(__fmul_rn(ix ? hi[0] : lo[0], iy ? hi[1] : lo[1]), iz ? hi[2] : lo[2]);
+        if (s != 1) wk = __fdiv_rn(wk, (float)(s * s * s));
+        int id = -1;
+        if (wk != 0.f && live) {   // a zero-weight corner contributes nothing whether it exists or not
+          const int x = floor_to_stride(pv[0], s) + ix * s, y = floor_to_stride(pv[1], s) + iy * s,
+                    z = floor_to_stride(pv[2], s) + iz * s;
+          if (coord_in_range(x, y, z, b)) id = table_find_coord(sc.tab[si], sc.mask[si], pack_coord(x, y, z, b));
+        }
+        if (id < 0) wk = 0.f;
+        float sum = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sum = __fadd_rn(sum, __shfl_sync(gmask, wk, gl0 + k));
+        wk = __fdiv_rn(wk, __fadd_rn(sum, 1e-8f));
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float *f = sc.feats[si];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int v = __shfl_sync(gmask, id, gl0 + k);
+          const float w = __shfl_sync(gmask, wk, gl0 + k);
+          if (v >= 0) {
+            const float4 r = __ldg(reinterpret_cast<const float4 *>(f + (int64_t)v * c + ch));
+            acc.x += w * r.x; acc.y += w * r.y; acc.z += w * r.z; acc.w += w * r.w;
+          }
+        }
+        total.x += acc.x; total.y += acc.y; total.z += acc.z; total.w += acc.w;
+      }
+      if (live) {
+        float *o = out + j * c_out + ch;
+        if (ch + 0 < c_out) o[0] = total.x;
+        if (ch + 1 < c_out) o[1] = total.y;
+        if (ch + 2 < c_out) o[2] = total.z;
+        if (ch + 3 < c_out) o[3] = total.w;
+      }
     }
   }
 }
@@ -544,6 +621,31 @@ int tsg_trilinear_query(const void *table, int64_t slots, const float *pcoords, 
   trilinear_query_kernel<<<grid_for(n, 128), 128, 0, stream>>>((const Slot *)table, (unsigned long long)(slots - 1),
                                                                (const float4 *)pcoords, n, stride, nearest, idx8, w8);
   return check_launch("tsg_trilinear_query");
+}
+
+int tsg_devoxelize_multi(int n_scales, const void *const *tables, const int64_t *slots, const int32_t *strides,
+                         const float *const *feats, int c, const float *pcoords, const int32_t *rows, int64_t m,
+                         float *out, int c_out, tsg_stream_t stream) {
+  if (n_scales < 1 || n_scales > 4 || c % 4 || c_out > c || c_out <= 0) {
+    set_error("tsg_devoxelize_multi: need 1..4 scales, c %% 4 == 0, 0 < c_out <= c");
+    return TSG_ERR_INVALID;
+  }
+  if (m <= 0) return TSG_OK;
+  DevoxScales sc;
+  sc.count = n_scales;
+  for (int i = 0; i < n_scales; ++i) {
+    if (slots[i] <= 0 || (slots[i] & (slots[i] - 1))) {
+      set_error("tsg_devoxelize_multi: slots must be a power of two");
+      return TSG_ERR_INVALID;
+    }
+    sc.tab[i] = (const Slot *)tables[i];
+    sc.mask[i] = (unsigned long long)(slots[i] - 1);
+    sc.feats[i] = feats[i];
+    sc.stride[i] = strides[i];
+  }
+  devoxelize_multi_kernel<<<grid_for((m + 3) / 4 * 4 * 8, 256), 256, 0, stream>>>(sc, (const float4 *)pcoords, rows, m, c, out,
+                                                                                 c_out);
+  return check_launch("tsg_devoxelize_multi");
 }
 
 int tsg_rescale_coords(const float *pcoords, int64_t n, float init_res, float after_res, float *out_f, int32_t *out_i,

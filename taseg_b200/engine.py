@@ -164,9 +164,12 @@ class Engine:
 
     # ------------------------------------------------------------------------------------------------
     @torch.no_grad()
-    def __call__(self, coords: torch.Tensor, feats: torch.Tensor, return_geometry: bool = False, field_bits=None):
+    def __call__(self, coords: torch.Tensor, feats: torch.Tensor, return_geometry: bool = False, field_bits=None,
+                 out_rows: Optional[torch.Tensor] = None):
         """coords (N,4) int32 [x,y,z,b], feats (N,>=in_dim) fp32 -> logits (N, num_class) fp32, one row per input row.
-        field_bits: optional (bx,by,bz,bb) promise 0 <= coordinate < 2^bits (shorter radix sorts in the pyramid)."""
+        field_bits: optional (bx,by,bz,bb) promise 0 <= coordinate < 2^bits (shorter radix sorts in the pyramid).
+        out_rows: optional (M,) int32 — return logits[out_rows] only (the eval gather of minkunet_ms.py:441-456 fused
+        into the last kernel)."""
         feats = feats[:, :self.in_dim].float().contiguous()
         zc = coords.float().contiguous()
         if self.voxelize_input:      # initial_voxelize (minkunet/utils.py:11-36)
@@ -183,10 +186,10 @@ class Engine:
         for conv in self.stem:
             x = conv(x, None, conv_map(L[0].km3), L[0].n)
         x0 = x
-        q1 = ops.trilinear_query(L[0].table, zc, 1)
-        q16 = ops.trilinear_query(L[4].table, zc, 16)
-        q4 = ops.trilinear_query(L[2].table, zc, 4)
         if self.spv:
+            q1 = ops.trilinear_query(L[0].table, zc, 1)
+            q16 = ops.trilinear_query(L[4].table, zc, 16)
+            q4 = ops.trilinear_query(L[2].table, zc, 4)
             z0 = ops.devoxelize_forward(x0, *q1)
             p2v1 = (inv0, cnt0)
             x = ops.voxelize_forward(z0, *p2v1)
@@ -226,8 +229,12 @@ class Engine:
             l16 = self.heads[0](x4, None, None, L[4].n, out_dtype=torch.float32)
             l4 = self.heads[1](y2, None, None, L[2].n, out_dtype=torch.float32)
             l1 = self.heads[2](y4, None, None, L[0].n, out_dtype=torch.float32)
-            logits = ops.devoxelize_forward(l16, *q16) + ops.devoxelize_forward(l4, *q4) + ops.devoxelize_forward(l1, *q1)
+            logits = ops.devoxelize_multi([L[4].table, L[2].table, L[0].table], [16, 4, 1], [l16, l4, l1], zc,
+                                          self.num_class, rows=out_rows)
+            return (logits, geo) if return_geometry else logits
         logits = logits[:, :self.num_class]
+        if out_rows is not None:
+            logits = ops.gather_rows(logits.contiguous(), out_rows)
         return (logits, geo) if return_geometry else logits
 
     @torch.no_grad()

@@ -284,6 +284,25 @@ def devoxelize_backward(top_grad: torch.Tensor, idx8: torch.Tensor, w8: torch.Te
     return out
 
 
+def devoxelize_multi(tables: Sequence[Table], strides: Sequence[int], feats: Sequence[torch.Tensor], pcoords: torch.Tensor,
+                     c_out: int, rows: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[j] = sum over scales of trilinear_devoxelize(feats_s) at point pcoords[rows[j]] (rows None: every point)."""
+    ns = len(tables)
+    pc = pcoords.float().contiguous()
+    feats = [f.contiguous() for f in feats]
+    c = feats[0].shape[1]
+    assert all(f.dtype == torch.float32 and f.shape[1] == c for f in feats)
+    rows = _i32(rows).contiguous() if rows is not None else None
+    m = rows.shape[0] if rows is not None else pc.shape[0]
+    out = torch.empty((m, c_out), dtype=torch.float32, device=pc.device)
+    tabs = (ctypes.c_void_p * ns)(*[t.buf.data_ptr() for t in tables])
+    slots = (ctypes.c_int64 * ns)(*[t.slots for t in tables])
+    strd = (ctypes.c_int32 * ns)(*[int(v) for v in strides])
+    fts = (ctypes.c_void_p * ns)(*[f.data_ptr() for f in feats])
+    call("tsg_devoxelize_multi", ns, tabs, slots, strd, fts, c, ptr(pc), ptr(rows), m, ptr(out), int(c_out), stream())
+    return out
+
+
 def point_query(table: Table, pcoords: torch.Tensor, stride: int) -> torch.Tensor:
     pc = pcoords.float().contiguous()
     out = torch.empty((pc.shape[0],), dtype=torch.int32, device=pc.device)

@@ -27,8 +27,7 @@ def main():
 
     def step():
         out = frontend.aggregate_voxelize(pts, mfb, bench.VOXEL, cur_idx)
-        logits = engine(out["coords"], out["feats"], field_bits=out["field_bits"])
-        return ops.gather_rows(logits.contiguous(), out["cur_rows"])
+        return engine(out["coords"], out["feats"], field_bits=out["field_bits"], out_rows=out["cur_rows"])
 
     for _ in range(int(os.environ.get("WARM", "2"))):
         step()
