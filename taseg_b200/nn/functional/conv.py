@@ -67,7 +67,16 @@ class ConvolutionFunction(Function):
         # pairs (in i, out o, k): dX[i] += dY[o] W[k]^T ; dW[k] += X[i]^T dY[o]
         tab_in_of_out = kmap.nbr_t if transposed else kmap.nbr       # rows = outputs of the forward, values = inputs
         tab_out_of_in = kmap.nbr if transposed else kmap.nbr_t       # rows = inputs of the forward, values = outputs
-        grad_input = ops.conv_dgrad(grad_output, weight, tab_out_of_in, input.shape[0]).to(input.dtype)
+        c_in, c_out = weight.shape[1], weight.shape[2]
+        if ctx.needs_input_grad[0] and _tc_ok(input, c_out, c_in):
+            # dgrad = the same tensor-core kernel over the transposed table with W[k]^T (bf16 operands, fp32 accumulate)
+            packed_t = ops.pack_weights(weight.transpose(1, 2).contiguous(), c_out)
+            grad_input = ops.conv_forward_tc(grad_output.contiguous().to(torch.bfloat16), None, packed_t, k, c_in,
+                                             tab_out_of_in, kmap.tile_mask(not transposed), input.shape[0])
+        elif ctx.needs_input_grad[0]:
+            grad_input = ops.conv_dgrad(grad_output, weight, tab_out_of_in, input.shape[0]).to(input.dtype)
+        else:
+            grad_input = None
         grad_weight = ops.conv_wgrad(input, grad_output, tab_in_of_out, k).to(weight.dtype)
         return grad_input, grad_weight, None, None
 
@@ -78,7 +87,7 @@ def conv3d(input: SparseTensor, weight: torch.Tensor, kernel_size: Union[int, Li
     kernel_size, stride, dilation = make_ntuple(kernel_size, 3), make_ntuple(stride, 3), make_ntuple(dilation, 3)
     feats = input.feats
     if torch.is_autocast_enabled():        # reference: custom_fwd(cast_inputs=torch.half) (conv.py:19)
-        dt = torch.get_autocast_gpu_dtype()
+        dt = torch.get_autocast_dtype('cuda')
         feats, weight = feats.to(dt), weight.to(dt)
 
     if kernel_size == (1, 1, 1) and stride == (1, 1, 1) and dilation == (1, 1, 1):

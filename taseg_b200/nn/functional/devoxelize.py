@@ -46,5 +46,5 @@ class DevoxelizeFunction(Function):
 
 def spdevoxelize(feats: torch.Tensor, coords: torch.Tensor, weights: torch.Tensor) -> torch.Tensor:
     if torch.is_autocast_enabled():
-        feats = feats.to(torch.get_autocast_gpu_dtype())   # devoxelize.py:54
+        feats = feats.to(torch.get_autocast_dtype('cuda'))   # devoxelize.py:54
     return DevoxelizeFunction.apply(feats, coords, weights)

@@ -23,5 +23,5 @@ class VoxelizeFunction(Function):
 
 def spvoxelize(feats: torch.Tensor, coords: torch.Tensor, counts: torch.Tensor) -> torch.Tensor:
     if torch.is_autocast_enabled():
-        feats = feats.to(torch.get_autocast_gpu_dtype())   # the reference casts to half under --amp (voxelize.py:13)
+        feats = feats.to(torch.get_autocast_dtype('cuda'))   # the reference casts to half under --amp (voxelize.py:13)
     return VoxelizeFunction.apply(feats, coords, counts)

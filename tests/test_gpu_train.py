@@ -1,0 +1,91 @@
+"""Training step of the hot path: autograd through the CUDA kernels, bf16 autocast, gradient reducer."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _batch(seed=0, n=6000, span=48, n_cls=5):
+    import taseg_b200 as ts
+    rng = np.random.default_rng(seed)
+    xyz = rng.normal(0, span / 6, (n, 3))
+    xyz[:, 2] *= 0.2
+    c = np.unique(np.round(xyz).astype(np.int32), axis=0)
+    c -= c.min(0)
+    coords = np.concatenate([c, np.zeros((len(c), 1), np.int32)], 1)
+    feats = rng.normal(size=(len(c), 5)).astype(np.float32)
+    labels = 1 + (c[:, 0] > c[:, 0].mean()).astype(np.int64) * 2 + (c[:, 1] > c[:, 1].mean())   # learnable from position
+    dev = "cuda"
+    return {"lidar_ms": ts.SparseTensor(torch.from_numpy(feats).to(dev), torch.from_numpy(coords).to(dev)),
+            "targets_ms": ts.SparseTensor(torch.from_numpy(labels).to(dev), torch.from_numpy(coords).to(dev))}, len(c)
+
+
+def _model(n_cls=5, planes=16):
+    from taseg_b200.segmentor import MinkUNetMs, ModelCfg
+    torch.manual_seed(0)
+    cfg = ModelCfg(IN_FEATURE_DIM=5, BLOCK="ResBlock", NUM_LAYER=[1, 1, 1, 1, 1, 1, 1, 1], cr=1.0,
+                   PLANES=[planes, planes, 2 * planes, 2 * planes, 4 * planes, 4 * planes, 2 * planes, planes, planes],
+                   pres=1.0, vres=1.0, IF_DIST=False, IGNORE_LABEL=0, DROPOUT_P=0.0)
+    return MinkUNetMs(cfg, n_cls).cuda()
+
+
+def _fresh(batch):
+    import taseg_b200 as ts
+    x, t = batch["lidar_ms"], batch["targets_ms"]
+    return {"lidar_ms": ts.SparseTensor(x.F.clone(), x.C), "targets_ms": ts.SparseTensor(t.F, t.C)}
+
+
+def test_training_steps_reduce_the_loss():
+    from taseg_b200 import parallel
+    batch, _ = _batch()
+    model = _model()
+    opt = torch.optim.SGD(model.parameters(), lr=0.05, momentum=0.9)
+    reducer = parallel.GradientReducer(model.parameters())      # world size 1: no exchange
+    losses = [parallel.train_step(model, _fresh(batch), opt, reducer, amp_dtype=torch.bfloat16) for _ in range(10)]
+    assert all(np.isfinite(losses)), losses
+    assert losses[-1] < 0.9 * losses[0], losses
+    assert reducer.bytes_per_step() == 4 * sum(p.numel() for p in model.parameters())
+
+
+def test_bf16_gradients_agree_with_fp32():
+    batch, _ = _batch(seed=1)
+    grads = {}
+    for name, amp in (("fp32", None), ("bf16", torch.bfloat16)):
+        model = _model()
+        model.train()
+        with torch.autocast("cuda", dtype=amp or torch.bfloat16, enabled=amp is not None):
+            loss = model(_fresh(batch))[0]["loss"]
+        loss.backward()
+        grads[name] = {k: p.grad.float().flatten() for k, p in model.named_parameters() if p.grad is not None}
+    assert set(grads["fp32"]) == set(grads["bf16"])
+    cos = {k: float(torch.nn.functional.cosine_similarity(grads["fp32"][k], grads["bf16"][k], dim=0)) for k in grads["fp32"]
+           if grads["fp32"][k].norm() > 0}
+    worst = min(cos, key=cos.get)
+    # stated bf16 bound: bf16 activations and bf16 dgrad (fp32 accumulate) through ~25 layers on a 3 k-voxel batch
+    assert cos[worst] > 0.8 and float(np.mean(list(cos.values()))) > 0.97, (worst, cos[worst], np.mean(list(cos.values())))
+
+
+def test_fp32_gradient_against_finite_differences():
+    batch, _ = _batch(seed=2, n=1500, span=24)
+    model = _model(planes=8)
+    model.train()
+    for m in model.modules():                      # freeze BN statistics so that the loss is a smooth function of one weight
+        if isinstance(m, torch.nn.BatchNorm1d):
+            m.eval()
+    loss = model(_fresh(batch))[0]["loss"]
+    loss.backward()
+    w = model.stem[3].kernel                        # (27, 8, 8)
+    picks = [(13, 0, 0), (4, 3, 5), (22, 7, 1)]
+    eps = 2e-2
+    for k, i, j in picks:
+        with torch.no_grad():
+            orig = float(w[k, i, j])
+            w[k, i, j] = orig + eps
+            lp = float(model(_fresh(batch))[0]["loss"])
+            w[k, i, j] = orig - eps
+            lm = float(model(_fresh(batch))[0]["loss"])
+            w[k, i, j] = orig
+        fd = (lp - lm) / (2 * eps)
+        an = float(w.grad[k, i, j])
+        assert abs(fd - an) <= 5e-2 * max(abs(fd), abs(an)) + 2e-4, ((k, i, j), fd, an)
