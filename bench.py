@@ -224,15 +224,18 @@ def main():
     clocks = sampler.summary(w0, w2)
 
     # roofline of the dominant kernel (conv_tc_kernel): algorithmic FLOPs / CUDA-event time of its launches in one step
-    ops.PROFILE = []
-    torch.cuda.synchronize()
-    es, ee = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    es.record()
-    step()
-    ee.record()
-    torch.cuda.synchronize()
-    prof, ops.PROFILE = ops.PROFILE, None
-    conv_ms = sum(e0.elapsed_time(e1) for _, e0, e1, *_ in prof)
+    # (events on the launching stream around every launch; minimum over 3 instrumented steps, the instrumentation itself
+    # — pair counts, extra events — is outside the bracketed launches)
+    runs = []
+    for _ in range(3):
+        ops.PROFILE = []
+        torch.cuda.synchronize()
+        step()
+        torch.cuda.synchronize()
+        runs.append(ops.PROFILE)
+        ops.PROFILE = None
+    prof = runs[0]
+    conv_ms = sum(min(r[i][1].elapsed_time(r[i][2]) for r in runs) for i in range(len(prof)))
     flops = sum(2.0 * float(p.item()) * cin * cout for _, _, _, p, cin, cout, _ in prof)
     pk = peaks()
     achieved = flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
@@ -244,7 +247,7 @@ def main():
                 "achieved": achieved, "peak": pk["bf16"], "unit": "TFLOP/s", "frac": achieved / pk["bf16"],
                 "peak_source": pk["source"] + " bf16_tflops_sustained", "traffic": traffic,
                 "algorithmic_gflop_per_step": flops / 1e9, "kernel_ms_per_step": conv_ms,
-                "kernel_share_of_step": conv_ms / es.elapsed_time(ee)}
+                "kernel_share_of_step": conv_ms / (ms / args.steps)}
 
     if rank == 0:
         scans = BATCH * world * args.steps

@@ -232,6 +232,9 @@ int tsg_conv_wgrad(const float *in, int64_t n_in, int c_in, const float *grad_ou
  * perm == NULL: tile row r is output row r.  Otherwise nbr / tile_mask describe tile rows in the order produced by
  * tsg_kmap_sort_rows and row r is written to out[perm[r]] (residual read from residual[perm[r]]): rows with the same
  * neighbour pattern share a tile, so most (tile, offset) pairs are empty and skipped.
+ * nbr_stride: elements between consecutive offsets of nbr (>= n_out).  The producers fetch eight neighbour indices per
+ * thread with two 16-byte loads and never test row bounds, so nbr_stride must be a multiple of 256 with -1 in the padding
+ * rows [n_out, nbr_stride) — what tsg_kmap_sort_rows writes for out_stride = tsg_kmap_sort_stride(n_out).
  * sched: NULL (tiles are dealt to the CTAs round-robin) or two int32 that are ZERO on entry: the kernel hands tiles out
  * dynamically through them, heaviest first, and leaves them zero again; launches that may overlap need their own pair.
  * out dtype TSG_BF16 or TSG_F32. */
@@ -240,15 +243,16 @@ int tsg_conv_pack_weights(const float *weight, int k, int c_in, int c_out, int c
                           const float *out_scale, void *packed, tsg_stream_t stream);
 int tsg_kmap_tile_mask(const int32_t *nbr, int k, int64_t n_out, uint32_t *tile_mask, tsg_stream_t stream);
 int tsg_conv_fwd_tc(const void *in0, int c0, const void *in1, int c1, int64_t n_in, const void *packed_w, int k,
-                    int c_out, const int32_t *nbr, const uint32_t *tile_mask, const int32_t *perm, int64_t n_out,
+                    int c_out, const int32_t *nbr, int64_t nbr_stride, const uint32_t *tile_mask, const int32_t *perm, int64_t n_out,
                     void *out, int out_dtype, const float *bias, const void *residual, int relu, int num_sms,
                     int32_t *sched, tsg_stream_t stream);
 /* Tile-row order for tsg_conv_fwd_tc: stable sort of the n_out output rows by a K-bit key built from their neighbour
  * mask (offset k present iff nbr[k, o] >= 0; for K = 27 the rarest offsets — cube corners, then edges — are the most
- * significant key bits, otherwise bit k = offset k).  Outputs: perm (n_out) int32 = output row of tile row r, nbr_sorted (K, n_out) with
- * nbr_sorted[k, r] = nbr[k, perm[r]], tile_mask (ceil(n_out/128)) of the sorted table.  ws: tsg_kmap_sort_ws_bytes. */
+ * significant key bits, otherwise bit k = offset k).  Outputs: perm (n_out) int32 = output row of tile row r, nbr_sorted (K, out_stride) with
+ * nbr_sorted[k, r] = nbr[k, perm[r]] (-1 in the padding rows r >= n_out), tile_mask (ceil(n_out/128)) of the sorted table.  ws: tsg_kmap_sort_ws_bytes. */
 size_t tsg_kmap_sort_ws_bytes(int64_t n_out);
-int tsg_kmap_sort_rows(const int32_t *nbr, int k, int64_t n_out, int32_t *perm, int32_t *nbr_sorted,
+int64_t tsg_kmap_sort_stride(int64_t n_out); /* row stride of nbr_sorted the convolution wants: n_out rounded up to 256 */
+int tsg_kmap_sort_rows(const int32_t *nbr, int k, int64_t n_out, int32_t *perm, int32_t *nbr_sorted, int64_t out_stride,
                        uint32_t *tile_mask, void *ws, size_t ws_bytes, tsg_stream_t stream);
 
 /* fp32 -> bf16 with zero padding of the channel dimension to c_pad (first-layer input, 4/5 -> 16 channels). */

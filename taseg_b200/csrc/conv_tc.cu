@@ -46,7 +46,7 @@ constexpr int V5_GROUPS = 4;                                      // producer gr
 constexpr int V5_GROUP_WARPS = 4;
 constexpr int V5_PROD_WARPS = V5_GROUPS * V5_GROUP_WARPS;         // 16
 constexpr int V5_THREADS = 32 * (V5_PROD_WARP0 + V5_PROD_WARPS);  // 768
-constexpr int V5_Q = TC_BM / (V5_GROUP_WARPS * 4);                // 8 passes of 16 rows per tile (8 lanes cover one row)
+constexpr int V5_Q = TC_BM / (V5_GROUP_WARPS * 4);                // 8 consecutive tile rows per producer thread
 constexpr int V5_MAX_STAGES = 8;
 constexpr int V5_SCHED_SLOTS = 3;
 constexpr int V5_CONSUMER_WARPS = V5_PROD_WARPS + TC_EPI_WARPS + 3;  // producers + epilogue + 2 MMA + weights
@@ -345,8 +345,10 @@ __global__ void __launch_bounds__(V5_THREADS, 1) conv_tc_kernel(const TcParams p
     const int grp = (warp - V5_PROD_WARP0) / V5_GROUP_WARPS;
     const int NG = (int)nst < V5_GROUPS ? (int)nst : V5_GROUPS;
     const int tid = threadIdx.x - 32 * (V5_PROD_WARP0 + grp * V5_GROUP_WARPS);  // 0..127 inside the group
-    const int chunk = tid & 7, rsub = tid >> 3;  // 8 lanes cover one 128-byte tile row; 16 rows per pass, 8 passes
-    const uint32_t dst_off = b_bytes + (uint32_t)rsub * 128u + (uint32_t)((chunk ^ (rsub & 7)) << 4);
+    const int chunk = tid & 7, rsub = tid >> 3;  // 8 lanes cover one 128-byte tile row; thread owns rows 8 rsub .. 8 rsub + 7
+    uint32_t dst_off[V5_Q];                      // row 8 rsub + q sits at chunk position chunk ^ q of its 128-byte line
+#pragma unroll
+    for (int q = 0; q < V5_Q; ++q) dst_off[q] = b_bytes + (uint32_t)(rsub * V5_Q + q) * 128u + (uint32_t)((chunk ^ q) << 4);
     const int cpr = p.pk > 1 ? (p.c0 >> 3) : 8;       // 16-byte chunks per source row inside one slice
     const int sub = p.pk > 1 ? chunk / cpr : 0;       // which of the PK packed offsets this lane copies
     const uint32_t col_bytes = (uint32_t)(p.pk > 1 ? chunk % cpr : chunk) * 16u;
@@ -354,7 +356,7 @@ __global__ void __launch_bounds__(V5_THREADS, 1) conv_tc_kernel(const TcParams p
     const char *in0 = reinterpret_cast<const char *>(p.in0) + col_bytes;
     const char *in1 = reinterpret_cast<const char *>(p.in1) + col_bytes;
     const int pk = p.pk, K = p.K, kb0 = p.kb0;
-    const long long n_out = p.n_out;
+    const long long n_out = p.n_out, nbr_stride = p.nbr_stride;
     const int *nbr = p.nbr;
     const bool worker = grp < NG;
     uint32_t slot = (uint32_t)grp, phase = 0;  // ring position of this group's next stage (always NG stages further)
@@ -368,25 +370,34 @@ __global__ void __launch_bounds__(V5_THREADS, 1) conv_tc_kernel(const TcParams p
       if (t < 0) t += NG;
       s_mod = (s_mod + nstages) % NG;
       if (!worker || t >= nstages) continue;
-      const long long m0 = (long long)st * G * TC_BM + rsub;
-      int idx[G][V5_Q];  // neighbour row of tile row rsub + 16 q, or -1
+      const long long m0 = (long long)st * G * TC_BM + rsub * V5_Q;  // first of this thread's 8 consecutive tile rows
+      int idx[G][V5_Q];  // neighbour row of tile row 8 rsub + q, or -1
+      // eight consecutive indices = two 16-byte loads; rows past n_out read the -1 padding of the table
       auto load_idx = [&](int kv) {
         const int k = kv * pk + sub;
-        const int *src = nbr + (long long)k * n_out + m0;
+        const int4 *src = reinterpret_cast<const int4 *>(nbr + (long long)k * nbr_stride + m0);
 #pragma unroll
         for (int g = 0; g < G; ++g) {
-          const bool act = k < K && ((masks[g] >> k) & 1u);
+          if (k < K && ((masks[g] >> k) & 1u)) {
+            if (nbr) {
+              const int4 a = __ldg(src + g * (TC_BM / 4)), b = __ldg(src + g * (TC_BM / 4) + 1);
+              idx[g][0] = a.x; idx[g][1] = a.y; idx[g][2] = a.z; idx[g][3] = a.w;
+              idx[g][4] = b.x; idx[g][5] = b.y; idx[g][6] = b.z; idx[g][7] = b.w;
+            } else {  // identity map (1x1x1 convolutions, point MLPs)
 #pragma unroll
-          for (int q = 0; q < V5_Q; ++q) {
-            const int o = g * TC_BM + 16 * q;
-            idx[g][q] = (act && m0 + o < n_out) ? (nbr ? __ldg(src + o) : (int)(m0 + o)) : -1;
+              for (int q = 0; q < V5_Q; ++q) idx[g][q] = m0 + g * TC_BM + q < n_out ? (int)(m0 + g * TC_BM + q) : -1;
+            }
+          } else {
+#pragma unroll
+            for (int q = 0; q < V5_Q; ++q) idx[g][q] = -1;
           }
         }
       };
-      int kv = __fns(umask, 0, t / KB + 1);
+      int rank = t / KB, j = t - rank * KB;   // stage t = (rank-th active virtual offset, slice j)
+      int kv = next_bit(umask, -1);
+      for (int i = 0; i < rank; ++i) kv = next_bit(umask, kv);
       load_idx(kv);
       for (;;) {
-        const int j = t % KB;
         const unsigned act = active_tiles(masks, kv);
         const bool second = j >= kb0;
         const uint32_t rb = second ? rb1 : rb0;
@@ -395,7 +406,7 @@ __global__ void __launch_bounds__(V5_THREADS, 1) conv_tc_kernel(const TcParams p
         const bool chunk_ok = pk > 1 || ch0b + col_bytes < rb;   // this 16-byte chunk exists in the (possibly partial) slice
         mbar_wait(empty0 + 8 * slot, phase ^ 1);
         if (tid == 0 && grp == 0) TSG_TRACE(0, n_issued);
-        const uint32_t dst = smem_base + slot * stage_bytes + dst_off;
+        const uint32_t dst = smem_base + slot * stage_bytes;
         if (chunk_ok && !TSG_DBG(1)) {
 #pragma unroll
           for (int g = 0; g < G; ++g) {
@@ -403,7 +414,7 @@ __global__ void __launch_bounds__(V5_THREADS, 1) conv_tc_kernel(const TcParams p
 #pragma unroll
             for (int q = 0; q < V5_Q; ++q) {
               const int v = idx[g][q];
-              cp_async16(dst + g * TC_A_BYTES + q * 2048u, bp + (unsigned long long)(unsigned)max(v, 0) * rb, v >= 0 ? 16u : 0u);
+              cp_async16(dst + g * TC_A_BYTES + dst_off[q], bp + (unsigned long long)(unsigned)max(v, 0) * rb, v >= 0 ? 16u : 0u);
             }
           }
         }
@@ -412,9 +423,14 @@ __global__ void __launch_bounds__(V5_THREADS, 1) conv_tc_kernel(const TcParams p
         t += NG;
         const bool more = t < nstages;
         if (more) {
-          const int kn = __fns(umask, 0, t / KB + 1);
-          if (kn != kv) load_idx(kn);
-          kv = kn;
+          j += NG;
+          bool moved = false;
+          while (j >= KB) {   // at most NG steps
+            j -= KB;
+            kv = next_bit(umask, kv);
+            moved = true;
+          }
+          if (moved) load_idx(kv);
         }
         if (tid == 0 && grp == 0) TSG_TRACE(7, n_issued);
         asm volatile("cp.async.wait_all;" ::: "memory");
@@ -506,15 +522,19 @@ int tsg_debug_conv_trace(long long *host) {
 }
 
 int tsg_conv_fwd_tc(const void *in0, int c0, const void *in1, int c1, int64_t n_in, const void *packed_w, int k,
-                    int c_out, const int32_t *nbr, const uint32_t *tile_mask, const int32_t *perm, int64_t n_out,
-                    void *out, int out_dtype, const float *bias, const void *residual, int relu, int num_sms_hint,
-                    int32_t *sched, tsg_stream_t stream) {
+                    int c_out, const int32_t *nbr, int64_t nbr_stride, const uint32_t *tile_mask, const int32_t *perm,
+                    int64_t n_out, void *out, int out_dtype, const float *bias, const void *residual, int relu,
+                    int num_sms_hint, int32_t *sched, tsg_stream_t stream) {
   if (c0 % 16 || c1 % 16 || c_out % 16 || c_out > 256 || c_out <= 0 || c0 <= 0 || k <= 0 || k > 32 ||
       (out_dtype != TSG_BF16 && out_dtype != TSG_F32)) {
     set_error("tsg_conv_fwd_tc: need c0,c1,c_out multiples of 16, c_out<=256, K<=32, out bf16/f32");
     return TSG_ERR_UNSUPPORTED;
   }
   if (n_out <= 0) return TSG_OK;
+  if (nbr && (nbr_stride % 256 || nbr_stride < (n_out + 255) / 256 * 256)) {
+    set_error("tsg_conv_fwd_tc: nbr_stride must be a multiple of 256 covering n_out (padding rows hold -1)");
+    return TSG_ERR_INVALID;
+  }
   if (n_out >= (1ll << 31) - 4 * TC_BM || n_in * (int64_t)(c0 > c1 ? c0 : c1) * 2 >= (1ll << 40)) {
     set_error("tsg_conv_fwd_tc: tensor too large for 32-bit tile arithmetic");
     return TSG_ERR_UNSUPPORTED;
@@ -531,6 +551,7 @@ int tsg_conv_fwd_tc(const void *in0, int c0, const void *in1, int c1, int64_t n_
   p.K = k;
   p.c_out = c_out;
   p.nbr = nbr;
+  p.nbr_stride = nbr_stride;
   p.tile_mask = tile_mask;
   p.perm = perm;
   p.n_out = n_out;

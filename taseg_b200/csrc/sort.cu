@@ -233,12 +233,34 @@ __global__ void row_mask_keys_kernel(const int *__restrict__ nbr, int K, int64_t
     keys[o] = m;
   }
 }
-// nbr_sorted[k, r] = nbr[k, perm[r]]
+// nbr_sorted[k, r] = nbr[k, perm[r]] for r < n_out and -1 in the padding rows [n_out, out_stride)
 __global__ void permute_nbr_kernel(const int *__restrict__ nbr, const int *__restrict__ perm, int K, int64_t n_out,
-                                   int *__restrict__ nbr_sorted) {
-  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n_out; r += (int64_t)gridDim.x * blockDim.x) {
-    const int o = __ldg(perm + r);
-    for (int k = 0; k < K; ++k) nbr_sorted[(int64_t)k * n_out + r] = __ldg(nbr + (int64_t)k * n_out + o);
+                                   int64_t out_stride, int *__restrict__ nbr_sorted) {
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < out_stride; r += (int64_t)gridDim.x * blockDim.x) {
+    if (r < n_out) {
+      const int o = __ldg(perm + r);
+      for (int k = 0; k < K; ++k) nbr_sorted[(int64_t)k * out_stride + r] = __ldg(nbr + (int64_t)k * n_out + o);
+    } else {
+      for (int k = 0; k < K; ++k) nbr_sorted[(int64_t)k * out_stride + r] = -1;
+    }
+  }
+}
+// tile_mask[t] = which offsets occur in tile rows [128 t, 128 t + 128): OR of the SORTED keys, key bits mapped back to offsets
+__global__ void __launch_bounds__(128) tile_mask_from_keys_kernel(const unsigned long long *__restrict__ keys_sorted,
+                                                                  int64_t n_out, KeyBits kb, int K,
+                                                                  unsigned *__restrict__ tile_mask) {
+  __shared__ unsigned long long s_or[4];
+  const int64_t r = (int64_t)blockIdx.x * 128 + threadIdx.x;
+  unsigned long long m = r < n_out ? keys_sorted[r] : 0ull;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) m |= __shfl_xor_sync(0xffffffffu, m, o);
+  if ((threadIdx.x & 31) == 0) s_or[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    m = s_or[0] | s_or[1] | s_or[2] | s_or[3];
+    unsigned out = 0;
+    for (int k = 0; k < K; ++k) out |= (unsigned)((m >> kb.pos[k]) & 1ull) << k;
+    tile_mask[blockIdx.x] = out;
   }
 }
 
@@ -427,8 +449,14 @@ size_t tsg_kmap_sort_ws_bytes(int64_t n_out) {
   return 2 * align256((size_t)n * 8) + sort_ws_layout(n, nullptr, nullptr);
 }
 
-int tsg_kmap_sort_rows(const int32_t *nbr, int k, int64_t n_out, int32_t *perm, int32_t *nbr_sorted,
+int64_t tsg_kmap_sort_stride(int64_t n_out) { return (n_out + 255) / 256 * 256; }
+
+int tsg_kmap_sort_rows(const int32_t *nbr, int k, int64_t n_out, int32_t *perm, int32_t *nbr_sorted, int64_t out_stride,
                        uint32_t *tile_mask, void *ws, size_t ws_bytes, tsg_stream_t stream) {
+  if (out_stride < n_out) {
+    set_error("tsg_kmap_sort_rows: out_stride < n_out");
+    return TSG_ERR_INVALID;
+  }
   if (k <= 0 || k > 32) {
     set_error("tsg_kmap_sort_rows: need 1 <= K <= 32");
     return TSG_ERR_INVALID;
@@ -446,8 +474,9 @@ int tsg_kmap_sort_rows(const int32_t *nbr, int k, int64_t n_out, int32_t *perm, 
   const int rc = sort_pairs(keys, nullptr, n_out, 0, k, keys_sorted, (unsigned *)perm, sort_ws,
                             ws_bytes - 2 * align256((size_t)n_out * 8), stream);
   if (rc != TSG_OK) return rc;
-  permute_nbr_kernel<<<grid_for(n_out, 256), 256, 0, stream>>>(nbr, perm, k, n_out, nbr_sorted);
-  return tsg_kmap_tile_mask(nbr_sorted, k, n_out, tile_mask, stream);
+  permute_nbr_kernel<<<grid_for(out_stride, 256), 256, 0, stream>>>(nbr, perm, k, n_out, out_stride, nbr_sorted);
+  tile_mask_from_keys_kernel<<<(unsigned)((n_out + 127) / 128), 128, 0, stream>>>(keys_sorted, n_out, key_bits_for(k), k, tile_mask);
+  return check_launch("tsg_kmap_sort_rows");
 }
 
 size_t tsg_unique_ws_bytes(int64_t n) { return unique_ws_layout(n > 0 ? n : 1, nullptr, nullptr); }

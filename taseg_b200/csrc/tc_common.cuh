@@ -105,6 +105,7 @@ struct TcParams {
   const uint8_t *packed_w;
   int K, c_out, na, nb;
   const int *nbr;
+  long long nbr_stride;  // elements between offsets of nbr; multiple of 256, padding rows hold -1
   const unsigned *tile_mask;
   const int *perm;  // tile row r -> output row (NULL = identity); nbr / tile_mask are indexed by tile row
   long long n_out;

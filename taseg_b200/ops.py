@@ -146,11 +146,13 @@ class KernelMap:
             rows = self.n_in if transposed else self.n_out
             dev = nbr.device
             perm = torch.empty((rows,), dtype=torch.int32, device=dev)
-            nbr_s = torch.empty_like(nbr)
+            stride = int(L.lib().tsg_kmap_sort_stride(rows))       # padded row stride (-1 beyond `rows`)
+            nbr_s = torch.empty((self.k, stride), dtype=torch.int32, device=dev)
             mask = torch.empty(((rows + 127) // 128,), dtype=torch.int32, device=dev)
             ws_bytes = int(L.lib().tsg_kmap_sort_ws_bytes(rows))
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-            call("tsg_kmap_sort_rows", ptr(nbr), self.k, rows, ptr(perm), ptr(nbr_s), ptr(mask), ptr(ws), ws_bytes, stream())
+            call("tsg_kmap_sort_rows", ptr(nbr), self.k, rows, ptr(perm), ptr(nbr_s), stride, ptr(mask), ptr(ws), ws_bytes,
+                 stream())
             setattr(self, attr, (nbr_s, mask, perm))
         return getattr(self, attr)
 
@@ -461,11 +463,18 @@ def conv_forward_tc(in0: torch.Tensor, in1: Optional[torch.Tensor], packed_w: to
     if residual is not None:
         assert residual.dtype == torch.bfloat16 and residual.is_contiguous() and residual.shape == (n_out, c_out)
     out = torch.empty((n_out, c_out), dtype=out_dtype, device=in0.device)
+    nbr_stride = 0
+    if nbr is not None:
+        want = (n_out + 255) // 256 * 256
+        if nbr.shape[1] < want:     # plain (K, n_out) table: the kernel wants a 256-padded stride with -1 in the padding
+            nbr = torch.nn.functional.pad(nbr, (0, want - nbr.shape[1]), value=-1)
+        assert nbr.is_contiguous()
+        nbr_stride = nbr.shape[1]
     if PROFILE is not None:
         pairs = (nbr >= 0).sum() if nbr is not None else torch.tensor(n_out * k, device=in0.device)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    call("tsg_conv_fwd_tc", ptr(in0), c0, ptr(in1), c1, in0.shape[0], ptr(packed_w), k, c_out, ptr(nbr), ptr(tile_mask),
+    call("tsg_conv_fwd_tc", ptr(in0), c0, ptr(in1), c1, in0.shape[0], ptr(packed_w), k, c_out, ptr(nbr), nbr_stride, ptr(tile_mask),
          ptr(perm), int(n_out), ptr(out), L.DTYPES[out_dtype], ptr(bias), ptr(residual), int(relu), int(num_sms),
          ptr(_sched_ws(in0.device)) if DYNAMIC_TILES else None, stream())
     if PROFILE is not None:

@@ -267,7 +267,8 @@ def _tc_case(seed, n, c0, c1, c_out, ks, relu, residual, out_dtype, dense_span):
     # mask-sorted tile rows: a permutation of the same table, and bit-identical output rows (same MMAs per row)
     nbr_s, mask_s, perm = km.sorted()
     assert np.array_equal(np.sort(npy(perm)), np.arange(n)), "perm is not a permutation"
-    assert torch.equal(nbr_s, km.nbr[:, perm.long()])
+    assert nbr_s.shape[1] % 256 == 0 and bool((nbr_s[:, n:] == -1).all())   # padded stride, -1 in the padding rows
+    assert torch.equal(nbr_s[:, :n], km.nbr[:, perm.long()])
     pos = list(range(k))    # bit position of offset j in the sort key: rare offsets are the most significant (sort.cu)
     if k == 27:
         order = [0, 2, 6, 8, 18, 20, 24, 26, 1, 3, 5, 7, 19, 21, 23, 25, 4, 22, 9, 11, 15, 17, 10, 12, 14, 16, 13]
