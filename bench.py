@@ -185,9 +185,44 @@ def main():
         out = frontend.aggregate_voxelize(pts, mfb, VOXEL, cur_idx)
         return engine(out["coords"], out["feats"], field_bits=out["field_bits"], out_rows=out["cur_rows"])
 
+    # End to end through the public API with HOST buffers: every step copies its raw points pinned-host -> device and
+    # its logits device -> pinned-host.  Copies run on their own stream and are double buffered, so the transfer of
+    # step i+1's points and of step i-1's logits overlaps the kernels of step i (every byte still moves every step).
+    copy_stream = torch.cuda.Stream()
+    dev_pts = [torch.empty_like(pts), torch.empty_like(pts)]
+    dev_out = [torch.empty((n_cur, 20), dtype=torch.float32, device="cuda") for _ in range(2)]
+    h2d_done = [torch.cuda.Event(), torch.cuda.Event()]
+    out_ready = [torch.cuda.Event(), torch.cuda.Event()]
+    d2h_done = [torch.cuda.Event(), torch.cuda.Event()]
+    e2e_state = {"i": 0, "primed": False}
+
+    def enqueue_h2d(slot):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(out_ready[slot])      # the step that last read this buffer has finished with it
+            dev_pts[slot].copy_(host_pts, non_blocking=True)
+            h2d_done[slot].record(copy_stream)
+
     def step_e2e():
-        pts.copy_(host_pts, non_blocking=True)
-        host_out.copy_(step(), non_blocking=True)
+        i = e2e_state["i"]
+        slot = i & 1
+        if not e2e_state["primed"]:
+            enqueue_h2d(slot)
+            e2e_state["primed"] = True
+        enqueue_h2d(slot ^ 1)                             # next step's input travels while this step computes
+        main = torch.cuda.current_stream()
+        main.wait_event(h2d_done[slot])
+        main.wait_event(d2h_done[slot])                   # dev_out[slot] was drained two steps ago
+        out = frontend.aggregate_voxelize(dev_pts[slot], mfb, VOXEL, cur_idx)
+        dev_out[slot].copy_(engine(out["coords"], out["feats"], field_bits=out["field_bits"], out_rows=out["cur_rows"]))
+        out_ready[slot].record(main)
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(out_ready[slot])
+            host_out.copy_(dev_out[slot], non_blocking=True)
+            d2h_done[slot].record(copy_stream)
+        e2e_state["i"] = i + 1
+
+    def e2e_drain():
+        torch.cuda.current_stream().wait_stream(copy_stream)
 
     def barrier():
         if world > 1:
@@ -201,6 +236,8 @@ def main():
         e0.record()
         for _ in range(k):
             fn()
+        if fn is step_e2e:
+            e2e_drain()       # the last logits must have reached the host inside the timed region
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
