@@ -4,9 +4,11 @@
 // One persistent CTA per SM walks "super tiles" of G x 128 tile rows (G in {1,2}), handed out by an in-kernel dynamic
 // scheduler (heaviest tiles first).  The unit of the shared-memory pipeline is a STAGE = one 64-channel K slice: the
 // pre-swizzled weight slice (c_out x 128 B) plus the G gathered 128 x 64 A tiles that multiply it, behind ONE full /
-// ONE empty mbarrier.  For c_in > 32 a slice is (kernel offset k, 64-channel block j); for c_in <= 32 a slice packs
-// PK = 64 / c_in kernel offsets side by side ("virtual offset" kv = k / PK), so narrow layers still issue K=64 MMAs and
-// every producer lane moves useful bytes.  Warp roles (768 threads):
+// ONE empty mbarrier.  The K dimension is a flat stream of 16-byte chunks (8 channels): all chunks of offset 0 (first
+// source tensor, then the second), then offset 1, ...; a slice is the next 8 chunks of that stream, so every slice is
+// full whatever the channel count: 96 channels -> 3 slices per 2 offsets (not 2 per offset), 96 + 32 concatenated ->
+// 2 slices per offset (not 3), 32 channels -> 2 offsets per slice, 16 -> 4.  The pattern repeats every P = 8 / gcd(C/8, 8)
+// offsets ("virtual offset" kv = k / P) with Q = (C/8) / gcd slices.  Warp roles (768 threads):
 //   warps 0-3   epilogue   tcgen05.ld the G 128 x c_out fp32 accumulators (one TMEM lane quadrant per warp),
 //                          + bias + residual, ReLU, store bf16/fp32 rows (to row perm[r] when tiles are mask-sorted)
 //   warps 4-5   MMA        one issuing thread per sub-tile: tcgen05.mma (M=128, N=c_out, K=16) per 16 input channels,
@@ -62,18 +64,9 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t lo, uint32_t hi) {
   return d;
 }
 
-// tile mask over real offsets -> mask over virtual offsets (PK real offsets per virtual one)
-__device__ __forceinline__ unsigned virt_mask(unsigned m, int pk, int kv_count) {
-  if (pk == 1) return m;
-  const unsigned sub = (1u << pk) - 1u;
-  unsigned vm = 0;
-  for (int kv = 0; kv < kv_count; ++kv) vm |= ((m >> (kv * pk)) & sub) ? (1u << kv) : 0u;
-  return vm;
-}
-
 // Profiling aid (TSG_TC_DEBUG bit 128): CTA 0 records clock64() at the pipeline hand-offs of its first TRACE_N stages.
 constexpr int TRACE_N = 96;
-__device__ long long g_trace[8][TRACE_N];  // 0 producer group 0 got empty, 1 it arrived on full, 2 MMA got full, 3 MMA committed,
+__device__ long long g_trace[13][TRACE_N];  // 0 producer group 0 got empty, 1 it arrived on full, 2 MMA got full, 3 MMA committed,
                                            // 4 weights got empty, 5 MMA starts waiting for full
 #ifdef TSG_TC_TRACE  // profiling build (TSG_TC_TRACE=1 python -m taseg_b200.build): knock-outs and traces cost nothing otherwise
 #define TSG_DBG(bit) (p.dbg & (bit))
@@ -95,14 +88,16 @@ __global__ void __launch_bounds__(V5_THREADS, 1) conv_tc_kernel(const TcParams p
 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int KB = p.kb0 + p.kb1;
+  const int P = p.pk, Q = p.kq;                                      // offsets per virtual offset, slices per virtual offset
+  const unsigned subP = (1u << P) - 1u;
+  const unsigned long long slice_need = p.slice_need;                // 4 bits per slice: which of the P offsets it touches
   const uint32_t b_bytes = (uint32_t)p.c_out * 128u;                 // multiple of 2048
   const uint32_t stage_bytes = b_bytes + (uint32_t)G * TC_A_BYTES;   // [W slice][A tile 0]..[A tile G-1]
   const uint32_t nst = (uint32_t)p.na;                               // stages
   const int num_tiles = (int)((p.n_out + TC_BM - 1) / TC_BM);
   const int num_super = (num_tiles + G - 1) / G;
   const unsigned kmask = p.K >= 32 ? 0xffffffffu : ((1u << p.K) - 1u);
-  const int KV = (p.K + p.pk - 1) / p.pk;                            // virtual offsets
+  const int KV = (p.K + P - 1) / P;                                  // virtual offsets
   const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[V5_MAX_STAGES]);
   const uint32_t tfull0 = smem_u32(&bars[2 * V5_MAX_STAGES]), tempty0 = tfull0 + 16;
   const uint32_t sfull0 = tfull0 + 32, sempty0 = sfull0 + 8 * V5_SCHED_SLOTS;
@@ -110,7 +105,7 @@ __global__ void __launch_bounds__(V5_THREADS, 1) conv_tc_kernel(const TcParams p
   if (threadIdx.x == 0) {
     for (uint32_t s = 0; s < nst; ++s) {
       mbar_init(full0 + 8 * s, V5_GROUP_WARPS + 1);  // one arrival per warp of the owning producer group + the weight thread
-      mbar_init(empty0 + 8 * s, G);  // one tcgen05.commit per MMA warp
+      mbar_init(empty0 + 8 * s, G);                  // one tcgen05.commit per MMA warp
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull0 + 8 * b, G);
@@ -150,7 +145,7 @@ __global__ void __launch_bounds__(V5_THREADS, 1) conv_tc_kernel(const TcParams p
     sr.advance(V5_SCHED_SLOTS);
     return st;
   };
-  // real-offset masks of the G tiles of a super tile; returns the union over tiles of their VIRTUAL masks
+  // real-offset masks of the G tiles of a super tile; returns their union
   auto tile_masks = [&](int st, unsigned (&masks)[G]) -> unsigned {
     unsigned um = 0;
 #pragma unroll
@@ -159,16 +154,19 @@ __global__ void __launch_bounds__(V5_THREADS, 1) conv_tc_kernel(const TcParams p
       masks[g] = tile < num_tiles ? ((p.tile_mask ? __ldg(p.tile_mask + tile) : 0xffffffffu) & kmask) : 0u;
       um |= masks[g];
     }
-    return virt_mask(um, p.pk, KV);
+    return um;
   };
-  // which of the G tiles take part in virtual offset kv
-  auto active_tiles = [&](const unsigned (&masks)[G], int kv) -> unsigned {
-    const unsigned sub = p.pk >= 32 ? 0xffffffffu : ((1u << p.pk) - 1u);
-    unsigned act = 0;
-#pragma unroll
-    for (int g = 0; g < G; ++g) act |= (((masks[g] >> (kv * p.pk)) & sub) ? 1u : 0u) << g;
-    return act;
+  // virtual offsets with at least one real offset present in `m`
+  auto virt_mask = [&](unsigned m) -> unsigned {
+    if (P == 1) return m;
+    unsigned vm = 0;
+    for (int kv = 0; kv < KV; ++kv) vm |= ((m >> (kv * P)) & subP) ? (1u << kv) : 0u;
+    return vm;
   };
+  // The stages of a super tile, in the order every role walks them: for each virtual offset kv present in the union
+  // mask `um`, the slices j whose offsets (bits `need`) intersect it.  All roles enumerate with the same two tests.
+  auto group_bits = [&](unsigned m, int kv) -> unsigned { return (m >> (kv * P)) & subP; };
+  auto need_of = [&](int j) -> unsigned { return (unsigned)(slice_need >> (4 * j)) & 15u; };
 
   if (warp < TC_EPI_WARPS) {
     // ================================================================= epilogue
@@ -185,6 +183,7 @@ __global__ void __launch_bounds__(V5_THREADS, 1) conv_tc_kernel(const TcParams p
       }
       mbar_wait_sleep(tfull0 + 8 * buf, ph);
       tc_fence_after();
+      if (threadIdx.x == 0) TSG_TRACE(10, it);
 #pragma unroll
       for (int g = 0; g < G; ++g) {
         if (st * G + g >= num_tiles) break;
@@ -216,12 +215,13 @@ __global__ void __launch_bounds__(V5_THREADS, 1) conv_tc_kernel(const TcParams p
       }
       tc_fence_before();
       mbar_arrive(tempty0 + 8 * buf);
+      if (threadIdx.x == 0) TSG_TRACE(11, it);
     }
   } else if (warp == V5_MMA_WARP || warp == V5_MMA_WARP + 1) {
     // ================================================================= MMA issuers (one thread per sub-tile)
-    // Issuing a tcgen05.mma costs the issuing thread ~50 cycles whatever its size (traces, profiles/README.md), so for
-    // c_out <= 128 the instruction stream, not the tensor pipe, bounds a stage: each of the G sub-tiles gets its own
-    // issuing warp, and the loop runs in one lane with every per-stage constant hoisted.
+    // Issuing a tcgen05.mma costs the issuing thread ~56 cycles and a tcgen05.commit ~180 whatever the MMA's size
+    // (tools/micro/mma_issue.cu, profiles/README.md), so for c_out <= 128 the instruction stream, not the tensor pipe,
+    // bounds a stage: each of the G sub-tiles gets its own issuing warp, and the loop runs in one lane.
     const int g = warp - V5_MMA_WARP;
     if (g < G && lane == 0) {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.c_out >> 3) << 17) | ((TC_BM >> 4) << 24);
@@ -229,41 +229,39 @@ __global__ void __launch_bounds__(V5_THREADS, 1) conv_tc_kernel(const TcParams p
       const uint32_t desc_lo_stage = stage_bytes >> 4;
       const uint32_t b_lo0 = ((smem_base & 0x3FFFFu) >> 4) | (1u << 16);          // LBO field = 1 (ignored for swizzled K-major)
       const uint32_t a_lo0 = b_lo0 + (b_bytes >> 4) + g * (TC_A_BYTES >> 4);
-      const unsigned sub = p.pk >= 32 ? 0xffffffffu : ((1u << p.pk) - 1u);
-      unsigned nk_tab = 0;  // MMAs (16 channels each) of slice j, 4 bits per slice
-      for (int j = 0; j < KB; ++j) {
-        const int kc = p.pk > 1 ? TC_KB : (j < p.kb0 ? min(TC_KB, p.c0 - j * TC_KB) : min(TC_KB, p.c1 - (j - p.kb0) * TC_KB));
-        nk_tab |= (unsigned)(kc >> 4) << (4 * j);
-      }
       uint32_t slot = 0, phase = 0, it = 0;
       int n_mma = 0;
       for (int st = next_super_lane(); st >= 0; st = next_super_lane(), ++it) {
         const uint32_t buf = it & 1, ph = (it >> 1) & 1;
         unsigned masks[G];
-        const unsigned umask = tile_masks(st, masks);
+        const unsigned um = tile_masks(st, masks);
+        const unsigned umask = virt_mask(um);
         unsigned mg = masks[0];
 #pragma unroll
         for (int gg = 1; gg < G; ++gg)
           if (g == gg) mg = masks[gg];
         mbar_wait(tempty0 + 8 * buf, ph ^ 1);
         tc_fence_after();
+        if (g == 0) TSG_TRACE(8, it);
+        const int n_mma_tile0 = n_mma;
         const uint32_t d_tmem = tmem_base + (buf * G + g) * (uint32_t)p.c_out;
         uint32_t started = 0;
         for (int kv = next_bit(umask, -1); kv < 32; kv = next_bit(umask, kv)) {
-          const bool act = ((mg >> (kv * p.pk)) & sub) != 0 && !TSG_DBG(4);
-          unsigned nks = nk_tab;
-          for (int j = 0; j < KB; ++j, nks >>= 4) {
-            const int nk = nks & 15;
+          const unsigned gu = group_bits(um, kv), gm = group_bits(mg, kv);
+          for (int j = 0; j < Q; ++j) {
+            const unsigned need = need_of(j);
+            if (!(gu & need)) continue;                 // no tile of the super tile needs this slice: no stage
+            const bool act = (gm & need) != 0 && !TSG_DBG(4);
             if (g == 0) TSG_TRACE(5, n_mma);
             mbar_wait(full0 + 8 * slot, phase);  // producers fenced their writes towards the async proxy before arriving
             tc_fence_after();
             if (g == 0) TSG_TRACE(2, n_mma);
-            if (act) {
+            if (act) {  // every slice is a full 64-channel block: four K = 16 MMAs
               const uint32_t b_lo = b_lo0 + slot * desc_lo_stage, a_lo = a_lo0 + slot * desc_lo_stage;
               umma_bf16(d_tmem, make_desc(a_lo, desc_hi), make_desc(b_lo, desc_hi), idesc, started);
-              if (nk > 1) umma_bf16(d_tmem, make_desc(a_lo + 2, desc_hi), make_desc(b_lo + 2, desc_hi), idesc, 1u);
-              if (nk > 2) umma_bf16(d_tmem, make_desc(a_lo + 4, desc_hi), make_desc(b_lo + 4, desc_hi), idesc, 1u);
-              if (nk > 3) umma_bf16(d_tmem, make_desc(a_lo + 6, desc_hi), make_desc(b_lo + 6, desc_hi), idesc, 1u);
+              umma_bf16(d_tmem, make_desc(a_lo + 2, desc_hi), make_desc(b_lo + 2, desc_hi), idesc, 1u);
+              umma_bf16(d_tmem, make_desc(a_lo + 4, desc_hi), make_desc(b_lo + 4, desc_hi), idesc, 1u);
+              umma_bf16(d_tmem, make_desc(a_lo + 6, desc_hi), make_desc(b_lo + 6, desc_hi), idesc, 1u);
               started = 1;
             }
             umma_commit(empty0 + 8 * slot);  // this warp's share of "stage consumed" (arrives once its MMAs have read it)
@@ -276,6 +274,10 @@ __global__ void __launch_bounds__(V5_THREADS, 1) conv_tc_kernel(const TcParams p
           }
         }
         umma_commit(tfull0 + 8 * buf);  // this sub-tile's accumulator is complete (immediately if there was no work)
+        if (g == 0) TSG_TRACE(9, it);
+#ifdef TSG_TC_TRACE
+        if (g == 0 && (p.dbg & 128) && blockIdx.x == 0 && it < TRACE_N) g_trace[12][it] = n_mma - n_mma_tile0;
+#endif
       }
     } else if (lane == 0) {
       while (next_super_lane() >= 0) {}  // spare MMA warp (G == 1): keep the scheduler ring moving
@@ -288,10 +290,13 @@ __global__ void __launch_bounds__(V5_THREADS, 1) conv_tc_kernel(const TcParams p
       int n_w = 0;
       for (int st = next_super_lane(); st >= 0; st = next_super_lane()) {
         unsigned masks[G];
-        const unsigned umask = tile_masks(st, masks);
+        const unsigned um = tile_masks(st, masks);
+        const unsigned umask = virt_mask(um);
         for (int kv = next_bit(umask, -1); kv < 32; kv = next_bit(umask, kv)) {
-          const uint8_t *wk = p.packed_w + (size_t)kv * KB * b_bytes;
-          for (int j = 0; j < KB; ++j) {
+          const unsigned gu = group_bits(um, kv);
+          const uint8_t *wk = p.packed_w + (size_t)kv * Q * b_bytes;
+          for (int j = 0; j < Q; ++j) {
+            if (!(gu & need_of(j))) continue;
             mbar_wait(empty0 + 8 * r.slot, r.phase ^ 1);
             TSG_TRACE(4, n_w);
             ++n_w;
@@ -321,7 +326,7 @@ __global__ void __launch_bounds__(V5_THREADS, 1) conv_tc_kernel(const TcParams p
           t = static_next;
           static_next += gridDim.x;
         }
-        const int st = t < num_super ? num_super - 1 - t : -1;  // heavy (high-mask) tiles first
+        const int st = t < num_super ? num_super - 1 - t : -1;  // heavy (high-key) tiles first
         *reinterpret_cast<volatile int *>(&sched_tile[w.slot]) = st;
         mbar_arrive(sfull0 + 8 * w.slot);  // release: the tile index is visible to the waiters
         w.advance(V5_SCHED_SLOTS);
@@ -349,36 +354,65 @@ __global__ void __launch_bounds__(V5_THREADS, 1) conv_tc_kernel(const TcParams p
     uint32_t dst_off[V5_Q];                      // row 8 rsub + q sits at chunk position chunk ^ q of its 128-byte line
 #pragma unroll
     for (int q = 0; q < V5_Q; ++q) dst_off[q] = b_bytes + (uint32_t)(rsub * V5_Q + q) * 128u + (uint32_t)((chunk ^ q) << 4);
-    const int cpr = p.pk > 1 ? (p.c0 >> 3) : 8;       // 16-byte chunks per source row inside one slice
-    const int sub = p.pk > 1 ? chunk / cpr : 0;       // which of the PK packed offsets this lane copies
-    const uint32_t col_bytes = (uint32_t)(p.pk > 1 ? chunk % cpr : chunk) * 16u;
+    const int cpo = p.cpo, c0c = p.c0 >> 3;      // chunks per offset, chunks of the first source tensor
     const uint32_t rb0 = (uint32_t)p.c0 * 2u, rb1 = (uint32_t)p.c1 * 2u;
-    const char *in0 = reinterpret_cast<const char *>(p.in0) + col_bytes;
-    const char *in1 = reinterpret_cast<const char *>(p.in1) + col_bytes;
-    const int pk = p.pk, K = p.K, kb0 = p.kb0;
+    const char *in0 = reinterpret_cast<const char *>(p.in0);
+    const char *in1 = reinterpret_cast<const char *>(p.in1);
+    const int K = p.K;
     const long long n_out = p.n_out, nbr_stride = p.nbr_stride;
     const int *nbr = p.nbr;
     const bool worker = grp < NG;
     uint32_t slot = (uint32_t)grp, phase = 0;  // ring position of this group's next stage (always NG stages further)
-    int s_mod = 0;                             // global stage counter modulo NG at the start of the super tile
+    int cnt = NG - 1;                          // global stage number modulo NG of the iterator's current stage (none yet)
     int n_issued = 0;
     for (int st = next_super(); st >= 0; st = next_super()) {
+      if (!worker) continue;
       unsigned masks[G];
-      const unsigned umask = tile_masks(st, masks);
-      const int nstages = __popc(umask) * KB;
-      int t = grp - s_mod;  // first stage of this super tile that belongs to the group
-      if (t < 0) t += NG;
-      s_mod = (s_mod + nstages) % NG;
-      if (!worker || t >= nstages) continue;
+      const unsigned um = tile_masks(st, masks);
+      const unsigned umask = virt_mask(um);
+      // iterator over the stages of this super tile; every group walks all of them and keeps `cnt` in step
+      int kv = next_bit(umask, -1), j = -1;
+      unsigned gu = kv < 32 ? group_bits(um, kv) : 0u;
+      auto next_stage = [&]() -> bool {  // advance to the next stage of the super tile; false at its end
+        while (kv < 32) {
+          while (++j < Q)
+            if (gu & need_of(j)) {
+              cnt = cnt + 1 == NG ? 0 : cnt + 1;
+              return true;
+            }
+          kv = next_bit(umask, kv);
+          j = -1;
+          gu = kv < 32 ? group_bits(um, kv) : 0u;
+        }
+        return false;
+      };
+      auto next_mine = [&]() -> bool {   // advance to this group's next stage
+        while (next_stage())
+          if (cnt == grp) return true;
+        return false;
+      };
       const long long m0 = (long long)st * G * TC_BM + rsub * V5_Q;  // first of this thread's 8 consecutive tile rows
       int idx[G][V5_Q];  // neighbour row of tile row 8 rsub + q, or -1
+      int k_loaded = -1;
+      // this lane's chunk of slice j of virtual offset kv: offset k, source tensor, byte offset inside the source row
+      int k_cur = 0;
+      const char *src_cur = in0;
+      uint32_t rb_cur = rb0;
+      auto locate = [&]() {
+        const int f = 8 * j + chunk, ksub = f / cpo, cc = f - ksub * cpo;
+        k_cur = kv * P + ksub;
+        const bool second = cc >= c0c;
+        src_cur = (second ? in1 : in0) + (second ? cc - c0c : cc) * 16;
+        rb_cur = second ? rb1 : rb0;
+      };
       // eight consecutive indices = two 16-byte loads; rows past n_out read the -1 padding of the table
-      auto load_idx = [&](int kv) {
-        const int k = kv * pk + sub;
-        const int4 *src = reinterpret_cast<const int4 *>(nbr + (long long)k * nbr_stride + m0);
+      auto load_idx = [&]() {
+        if (k_cur == k_loaded) return;
+        k_loaded = k_cur;
+        const int4 *src = reinterpret_cast<const int4 *>(nbr + (long long)k_cur * nbr_stride + m0);
 #pragma unroll
         for (int g = 0; g < G; ++g) {
-          if (k < K && ((masks[g] >> k) & 1u)) {
+          if (k_cur < K && ((masks[g] >> k_cur) & 1u)) {
             if (nbr) {
               const int4 a = __ldg(src + g * (TC_BM / 4)), b = __ldg(src + g * (TC_BM / 4) + 1);
               idx[g][0] = a.x; idx[g][1] = a.y; idx[g][2] = a.z; idx[g][3] = a.w;
@@ -393,21 +427,22 @@ __global__ void __launch_bounds__(V5_THREADS, 1) conv_tc_kernel(const TcParams p
           }
         }
       };
-      int rank = t / KB, j = t - rank * KB;   // stage t = (rank-th active virtual offset, slice j)
-      int kv = next_bit(umask, -1);
-      for (int i = 0; i < rank; ++i) kv = next_bit(umask, kv);
-      load_idx(kv);
-      for (;;) {
-        const unsigned act = active_tiles(masks, kv);
-        const bool second = j >= kb0;
-        const uint32_t rb = second ? rb1 : rb0;
-        const uint32_t ch0b = pk > 1 ? 0u : (uint32_t)(second ? j - kb0 : j) * 128u;
-        const char *bp = (second ? in1 : in0) + ch0b;
-        const bool chunk_ok = pk > 1 || ch0b + col_bytes < rb;   // this 16-byte chunk exists in the (possibly partial) slice
+      bool have = next_mine();
+      if (have) {
+        locate();
+        load_idx();
+      }
+      while (have) {
+        const unsigned need = need_of(j);
+        unsigned act = 0;
+#pragma unroll
+        for (int g = 0; g < G; ++g) act |= ((group_bits(masks[g], kv) & need) ? 1u : 0u) << g;
+        const char *bp = src_cur;
+        const uint32_t rb = rb_cur;
         mbar_wait(empty0 + 8 * slot, phase ^ 1);
         if (tid == 0 && grp == 0) TSG_TRACE(0, n_issued);
         const uint32_t dst = smem_base + slot * stage_bytes;
-        if (chunk_ok && !TSG_DBG(1)) {
+        if (!TSG_DBG(1)) {
 #pragma unroll
           for (int g = 0; g < G; ++g) {
             if (!((act >> g) & 1u)) continue;
@@ -420,17 +455,10 @@ __global__ void __launch_bounds__(V5_THREADS, 1) conv_tc_kernel(const TcParams p
         }
         if (tid == 0 && grp == 0) TSG_TRACE(6, n_issued);
         // the index registers are free again: fetch the neighbour rows of this group's next stage while the copies land
-        t += NG;
-        const bool more = t < nstages;
-        if (more) {
-          j += NG;
-          bool moved = false;
-          while (j >= KB) {   // at most NG steps
-            j -= KB;
-            kv = next_bit(umask, kv);
-            moved = true;
-          }
-          if (moved) load_idx(kv);
+        have = next_mine();
+        if (have) {
+          locate();
+          load_idx();
         }
         if (tid == 0 && grp == 0) TSG_TRACE(7, n_issued);
         asm volatile("cp.async.wait_all;" ::: "memory");
@@ -444,7 +472,6 @@ __global__ void __launch_bounds__(V5_THREADS, 1) conv_tc_kernel(const TcParams p
           slot -= nst;
           phase ^= 1;
         }
-        if (!more) break;
       }
     }
   }
@@ -456,34 +483,48 @@ __global__ void __launch_bounds__(V5_THREADS, 1) conv_tc_kernel(const TcParams p
   }
 }
 
-// offsets packed per 64-channel slice: narrow single-source layers put 64 / c0 kernel offsets side by side
-__host__ __device__ inline int slice_pack(int c0, int c1) { return (c1 == 0 && (c0 == 16 || c0 == 32)) ? TC_KB / c0 : 1; }
+// K-slice packing of a layer with C = c0 + c1 input channels (both multiples of 16): the flat chunk stream repeats every
+// P offsets with Q slices; need[j] = which of the P offsets slice j touches.
+struct SlicePlan {
+  int P, Q, cpo;
+  unsigned long long need;
+};
+static SlicePlan slice_plan(int c0, int c1) {
+  SlicePlan sp;
+  sp.cpo = (c0 + c1) / 8;
+  int g = 8;
+  while (sp.cpo % g) g >>= 1;   // gcd(cpo, 8)
+  sp.P = 8 / g;
+  sp.Q = sp.cpo / g;
+  sp.need = 0;
+  for (int j = 0; j < sp.Q && j < 16; ++j) {
+    const int lo = (8 * j) / sp.cpo, hi = (8 * j + 7) / sp.cpo;
+    unsigned long long bits = 0;
+    for (int k = lo; k <= hi; ++k) bits |= 1ull << k;
+    sp.need |= bits << (4 * j);
+  }
+  return sp;
+}
 
-// W (K, c_in, c_out) fp32 -> per (virtual offset, 64-channel slice) [c_out][64] bf16, K-major, 128B-swizzled: the byte
-// image the MMA reads, so a linear bulk copy stages it.  Optional per-output-channel scale (folded BatchNorm).
-__global__ void pack_weights_kernel(const float *__restrict__ w, int K, int c_in, int c_out, int c0, int c1, int kb0,
-                                    int KB, int pk, const float *__restrict__ out_scale,
-                                    __nv_bfloat16 *__restrict__ packed) {
-  const int KV = (K + pk - 1) / pk;
-  const long long total = (long long)KV * KB * c_out * TC_KB;
+// W (K, c_in, c_out) fp32 -> per (virtual offset kv, slice j) a [c_out][64] bf16 block, K-major, 128B-swizzled: the byte
+// image the MMA reads, so a linear bulk copy stages it.  Column 8 c + e of block (kv, j) is channel 8 cc + e of offset
+// kv P + ksub with 8 j + c = ksub cpo + cc.  Optional per-output-channel scale (folded BatchNorm).
+__global__ void pack_weights_kernel(const float *__restrict__ w, int K, int c_in, int c_out, int P, int Q, int cpo,
+                                    const float *__restrict__ out_scale, __nv_bfloat16 *__restrict__ packed) {
+  const int KV = (K + P - 1) / P;
+  const long long total = (long long)KV * Q * c_out * TC_KB;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(t % TC_KB);
+    const int col = (int)(t % TC_KB);
     const int n = (int)((t / TC_KB) % c_out);
-    const int j = (int)((t / ((long long)TC_KB * c_out)) % KB);
-    const int kv = (int)(t / ((long long)TC_KB * c_out * KB));
+    const int j = (int)((t / ((long long)TC_KB * c_out)) % Q);
+    const int kv = (int)(t / ((long long)TC_KB * c_out * Q));
+    const int f = 8 * j + (col >> 3), ksub = f / cpo, cc = f - ksub * cpo;
+    const int k = kv * P + ksub, ch = cc * 8 + (col & 7);
     float v = 0.f;
-    if (pk > 1) {
-      const int k = kv * pk + c / c0, ch = c % c0;
-      if (k < K && ch < c_in) v = w[((long long)k * c_in + ch) * c_out + n];
-    } else {
-      const bool second = j >= kb0;
-      const int ch = (second ? j - kb0 : j) * TC_KB + c;          // channel within its source tensor
-      const int g = second ? c0 + ch : ch;                        // row of W[k]
-      if (ch < (second ? c1 : c0) && g < c_in) v = w[((long long)kv * c_in + g) * c_out + n];
-    }
+    if (k < K && ch < c_in) v = w[((long long)k * c_in + ch) * c_out + n];
     if (out_scale) v *= out_scale[n];
-    const long long blk = ((long long)kv * KB + j) * c_out * TC_KB;
-    const int sw = (((c >> 3) ^ (n & 7)) << 3) | (c & 7);
+    const long long blk = ((long long)kv * Q + j) * c_out * TC_KB;
+    const int sw = (((col >> 3) ^ (n & 7)) << 3) | (col & 7);
     packed[blk + (long long)n * TC_KB + sw] = __float2bfloat16_rn(v);
   }
 }
@@ -495,9 +536,8 @@ using namespace tsg;
 extern "C" {
 
 size_t tsg_conv_pack_bytes(int k, int c0, int c1, int c_out) {
-  const int pk = slice_pack(c0, c1);
-  const int KB = pk > 1 ? 1 : (c0 + TC_KB - 1) / TC_KB + (c1 + TC_KB - 1) / TC_KB;
-  return (size_t)((k + pk - 1) / pk) * KB * c_out * TC_KB * 2;
+  const SlicePlan sp = slice_plan(c0, c1);
+  return (size_t)((k + sp.P - 1) / sp.P) * sp.Q * c_out * TC_KB * 2;
 }
 
 int tsg_conv_pack_weights(const float *weight, int k, int c_in, int c_out, int c0, int c1, const float *out_scale,
@@ -506,18 +546,21 @@ int tsg_conv_pack_weights(const float *weight, int k, int c_in, int c_out, int c
     set_error("tsg_conv_pack_weights: need c0,c1,c_out multiples of 16, c_out<=256, c0+c1>=c_in");
     return TSG_ERR_UNSUPPORTED;
   }
-  const int pk = slice_pack(c0, c1);
-  const int kb0 = pk > 1 ? 1 : (c0 + TC_KB - 1) / TC_KB, KB = pk > 1 ? 1 : kb0 + (c1 + TC_KB - 1) / TC_KB;
-  const long long total = (long long)((k + pk - 1) / pk) * KB * c_out * TC_KB;
-  pack_weights_kernel<<<grid_for(total, 256), 256, 0, stream>>>(weight, k, c_in, c_out, c0, c1, kb0, KB, pk, out_scale,
+  const SlicePlan sp = slice_plan(c0, c1);
+  if (sp.Q > 16) {
+    set_error("tsg_conv_pack_weights: unsupported channel count (more than 16 slices per offset group)");
+    return TSG_ERR_UNSUPPORTED;
+  }
+  const long long total = (long long)((k + sp.P - 1) / sp.P) * sp.Q * c_out * TC_KB;
+  pack_weights_kernel<<<grid_for(total, 256), 256, 0, stream>>>(weight, k, c_in, c_out, sp.P, sp.Q, sp.cpo, out_scale,
                                                                 (__nv_bfloat16 *)packed);
   return check_launch("tsg_conv_pack_weights");
 }
 
-/* profiling aid, not part of the public header: copies the trace of the last TSG_TC_DEBUG&128 launch to `host` (6 x 96 int64) */
+/* profiling aid, not part of the public header: copies the trace of the last TSG_TC_DEBUG&128 launch to `host` (13 x 96 int64) */
 int tsg_debug_conv_trace(long long *host) {
   TSG_CUDA(cudaDeviceSynchronize());
-  TSG_CUDA(cudaMemcpyFromSymbol(host, g_trace, sizeof(long long) * 8 * TRACE_N));
+  TSG_CUDA(cudaMemcpyFromSymbol(host, g_trace, sizeof(long long) * 13 * TRACE_N));
   return TSG_OK;
 }
 
@@ -535,8 +578,13 @@ int tsg_conv_fwd_tc(const void *in0, int c0, const void *in1, int c1, int64_t n_
     set_error("tsg_conv_fwd_tc: nbr_stride must be a multiple of 256 covering n_out (padding rows hold -1)");
     return TSG_ERR_INVALID;
   }
-  if (n_out >= (1ll << 31) - 4 * TC_BM || n_in * (int64_t)(c0 > c1 ? c0 : c1) * 2 >= (1ll << 40)) {
-    set_error("tsg_conv_fwd_tc: tensor too large for 32-bit tile arithmetic");
+  if (n_out >= (1ll << 31) - 4 * TC_BM || n_in >= (1ll << 31)) {
+    set_error("tsg_conv_fwd_tc: tensor too large for 32-bit row arithmetic");
+    return TSG_ERR_UNSUPPORTED;
+  }
+  const SlicePlan sp = slice_plan(c0, c1);
+  if (sp.Q > 16) {
+    set_error("tsg_conv_fwd_tc: unsupported channel count (more than 16 slices per offset group)");
     return TSG_ERR_UNSUPPORTED;
   }
   TcParams p;
@@ -544,9 +592,10 @@ int tsg_conv_fwd_tc(const void *in0, int c0, const void *in1, int c1, int64_t n_
   p.in1 = (const __nv_bfloat16 *)in1;
   p.c0 = c0;
   p.c1 = c1;
-  p.pk = slice_pack(c0, c1);
-  p.kb0 = p.pk > 1 ? 1 : (c0 + TC_KB - 1) / TC_KB;
-  p.kb1 = p.pk > 1 ? 0 : (c1 + TC_KB - 1) / TC_KB;
+  p.pk = sp.P;
+  p.kq = sp.Q;
+  p.cpo = sp.cpo;
+  p.slice_need = sp.need;
   p.packed_w = (const uint8_t *)packed_w;
   p.K = k;
   p.c_out = c_out;
@@ -561,13 +610,13 @@ int tsg_conv_fwd_tc(const void *in0, int c0, const void *in1, int c1, int64_t n_
   p.residual = (const __nv_bfloat16 *)residual;
   p.relu = relu;
   p.sched = sched;
-  static const char *dbg_env = getenv("TSG_TC_DEBUG");  // profiling knock-outs (wrong results): 1 no gathers, 2 no weight
-  p.dbg = dbg_env ? atoi(dbg_env) : 0;                  // copies, 4 no MMAs, 8 no epilogue stores
+  static const char *dbg_env = getenv("TSG_TC_DEBUG");  // profiling knock-outs (trace build only, wrong results): 1 no gathers,
+  p.dbg = dbg_env ? atoi(dbg_env) : 0;                  // 2 no weight copies, 4 no MMAs, 8 no epilogue stores, 128 trace
   const int sms = num_sms_hint > 0 ? num_sms_hint : num_sms();
   const long long num_tiles = (n_out + TC_BM - 1) / TC_BM;
   // G sub-tiles share every weight slice; bounded by TMEM (2 buffers x G x c_out fp32 columns <= 512) and by the
   // number of super tiles needed to keep every SM busy
-  int G = c_out <= 128 ? 2 : 1;  // (G = 4 spills the producers' index registers at 736 threads per CTA)
+  int G = c_out <= 128 ? 2 : 1;  // (G = 4 spills the producers' index registers at 768 threads per CTA)
   while (G > 1 && (num_tiles + G - 1) / G < 2LL * sms) G >>= 1;
   uint32_t cols = 32;
   while (cols < 2u * (uint32_t)G * (uint32_t)c_out) cols <<= 1;

@@ -100,8 +100,9 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t addr) {
 
 struct TcParams {
   const __nv_bfloat16 *in0, *in1;
-  int c0, c1, kb0, kb1;
-  int pk;  // kernel offsets packed side by side in one 64-channel slice (1, 2 or 4; > 1 only for single-source c0 <= 32)
+  int c0, c1;
+  int pk, kq, cpo;                // K-slice packing: offsets per virtual offset (P), slices per virtual offset (Q), chunks per offset
+  unsigned long long slice_need;  // 4 bits per slice j < Q: which of the P offsets of a virtual offset slice j touches
   const uint8_t *packed_w;
   int K, c_out, na, nb;
   const int *nbr;

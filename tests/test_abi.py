@@ -33,7 +33,9 @@ def test_host_only_entry_points(lib):
     assert lib.tsg_sort_ws_bytes(1000) > 1000 * 12
     assert lib.tsg_unique_ws_bytes(1000) > lib.tsg_sort_ws_bytes(1000)
     assert lib.tsg_conv_pack_bytes(27, 64, 0, 64) == 27 * 64 * 64 * 2
-    assert lib.tsg_conv_pack_bytes(27, 96, 32, 96) == 27 * 3 * 96 * 64 * 2
+    assert lib.tsg_conv_pack_bytes(27, 96, 32, 96) == 27 * 2 * 96 * 64 * 2      # 128 flat channels: 2 slices per offset
+    assert lib.tsg_conv_pack_bytes(27, 96, 0, 96) == 14 * 3 * 96 * 64 * 2       # 96 channels: 3 slices per 2 offsets
+    assert lib.tsg_conv_pack_bytes(27, 32, 0, 32) == 14 * 1 * 32 * 64 * 2       # 32 channels: 2 offsets per slice
 
 
 def test_no_cpu_fallback():

@@ -33,8 +33,19 @@ for spec in os.environ.get("CASES", "0:96:96").split(","):
         import ctypes
         import numpy as np
         from taseg_b200 import _lib
-        buf = np.zeros((8, 96), np.int64)
+        buf = np.zeros((13, 96), np.int64)
         _lib.lib().tsg_debug_conv_trace(buf.ctypes.data_as(ctypes.c_void_p))
+        if os.environ.get("TRACE_TILES"):
+            tb = buf[8:12]
+            t0 = tb[tb > 0].min()
+            print(" tile stages  M.start    M.end  E.start    E.end | mainloop  epilogue  cycles/stage")
+            for i in range(96):
+                if buf[8, i] == 0:
+                    break
+                ms, me, es, ee, ns = (int(buf[r, i]) for r in (8, 9, 10, 11, 12))
+                print("%5d %6d %8d %8d %8d %8d | %8d %8d %8.0f" % (i, ns, ms - t0, me - t0, es - t0, ee - t0, me - ms, ee - es,
+                                                                  (me - ms) / max(ns, 1)))
+            continue
         t0 = buf[buf > 0].min()
         names = ["P0.empty", "P0.arrive", "M.full", "M.commit", "W.empty", "M.wait", "P0.copied", "P0.idxnext"]
         print("stage " + " ".join("%9s" % n for n in names))
