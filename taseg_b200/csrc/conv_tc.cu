@@ -40,34 +40,53 @@
 
 namespace tsg {
 
-constexpr int V5_MMA_WARP = TC_EPI_WARPS;        // 4, 5 (one per sub-tile)
-constexpr int V5_W_WARP = TC_EPI_WARPS + 2;      // 6
-constexpr int V5_SCHED_WARP = TC_EPI_WARPS + 3;  // 7
-constexpr int V5_PROD_WARP0 = TC_EPI_WARPS + 4;  // 8
-constexpr int V5_GROUPS = 4;                                      // producer groups; each owns every NG-th stage
-constexpr int V5_GROUP_WARPS = 4;
-constexpr int V5_PROD_WARPS = V5_GROUPS * V5_GROUP_WARPS;         // 16
-constexpr int V5_THREADS = 32 * (V5_PROD_WARP0 + V5_PROD_WARPS);  // 768
-constexpr int V5_Q = TC_BM / (V5_GROUP_WARPS * 4);                // 8 consecutive tile rows per producer thread
-constexpr int V5_MAX_STAGES = 8;
-constexpr int V5_SCHED_SLOTS = 3;
-constexpr int V5_CONSUMER_WARPS = V5_PROD_WARPS + TC_EPI_WARPS + 3;  // producers + epilogue + 2 MMA + weights
+constexpr int V8_EPI_WARPS = 8;                  // 0-3 and 4-7: two sets over the four TMEM lane quadrants (warp % 4)
+constexpr int V8_MMA_WARP = V8_EPI_WARPS;        // 8, 9 (one issuer per sub-tile)
+constexpr int V8_W_WARP = V8_EPI_WARPS + 2;      // 10
+constexpr int V8_SCHED_WARP = V8_EPI_WARPS + 3;  // 11
+constexpr int V8_PROD_WARP0 = V8_EPI_WARPS + 4;  // 12
+constexpr int V8_GROUPS = 4;                                      // producer groups; each owns every NG-th stage
+constexpr int V8_GROUP_WARPS = 4;
+constexpr int V8_PROD_WARPS = V8_GROUPS * V8_GROUP_WARPS;         // 16
+constexpr int V8_THREADS = 32 * (V8_PROD_WARP0 + V8_PROD_WARPS);  // 896
+constexpr int V8_Q = TC_BM / (V8_GROUP_WARPS * 4);                // 8 consecutive tile rows per producer thread
+constexpr int V8_MAX_STAGES = 8;
+constexpr int V8_PLAN_SLOTS = 4;
+constexpr int V8_PLAN_MAX = 512;                                  // stages of one super tile: <= 32 virtual offsets x 16 slices
+constexpr int V8_CONSUMER_WARPS = V8_PROD_WARPS + V8_EPI_WARPS + 3;  // producers + epilogue + 2 MMA + weights
+// Epilogue staging: per epilogue warp 32 rows x (64 B of output + 16 B pad).  The pad makes both access patterns
+// conflict-free: a thread walking its own row in 16-byte steps (pitch 80 B = 20 banks) and a warp reading
+// consecutive 16-byte chunks of consecutive rows.
+constexpr int V8_STG_PITCH = 80;
+constexpr int V8_STG_BYTES = 32 * V8_STG_PITCH;  // 2560
+constexpr int V8_DYN_SMEM = 221 * 1024;          // dynamic shared memory requested per CTA
 
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-  return pred != 0;
-}
+// What the planner publishes per super tile: the tile, the offset masks of its G tiles and the list of pipeline stages
+// (stage = bits 0-4 virtual offset kv, 5-8 slice j, 9-10 which sub-tiles multiply this slice).
+struct __align__(16) Plan {
+  int tile, n;
+  unsigned mask[2];
+  unsigned short stage[V8_PLAN_MAX];
+};
+
 __device__ __forceinline__ uint64_t make_desc(uint32_t lo, uint32_t hi) {
   uint64_t d;
   asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
   return d;
 }
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 
 // Profiling aid (TSG_TC_DEBUG bit 128): CTA 0 records clock64() at the pipeline hand-offs of its first TRACE_N stages.
 constexpr int TRACE_N = 96;
 __device__ long long g_trace[13][TRACE_N];  // 0 producer group 0 got empty, 1 it arrived on full, 2 MMA got full, 3 MMA committed,
-                                           // 4 weights got empty, 5 MMA starts waiting for full
+                                           // 4 weights got empty, 5 MMA starts waiting for full, 6 copies issued, 7 next indices requested
 #ifdef TSG_TC_TRACE  // profiling build (TSG_TC_TRACE=1 python -m taseg_b200.build): knock-outs and traces cost nothing otherwise
 #define TSG_DBG(bit) (p.dbg & (bit))
 #define TSG_TRACE(role, idx)                                                              \
@@ -79,12 +98,104 @@ __device__ long long g_trace[13][TRACE_N];  // 0 producer group 0 got empty, 1 i
 #define TSG_TRACE(role, idx) do { } while (0)
 #endif
 
+// ---- epilogue building blocks: NCOLS accumulator columns of 32 tile rows (one per lane) through the warp's staging buffer
+template <int NCOLS>
+__device__ __forceinline__ void epi_prefetch_res(uint32_t stg, const char *res_c0, long long pitch, int rows_g, int lane) {
+  constexpr int CPR = NCOLS / 8;  // 16-byte chunks of bf16 per row
+#pragma unroll
+  for (int it = 0; it < CPR; ++it) {
+    const int r = it * (32 / CPR) + lane / CPR, q = lane % CPR;
+    const int orow = __shfl_sync(0xffffffffu, rows_g, r);
+    cp_async16(stg + r * V8_STG_PITCH + q * 16, res_c0 + (long long)max(orow, 0) * pitch + q * 16, orow >= 0 ? 16u : 0u);
+  }
+}
+
+template <int NCOLS, bool F32>
+__device__ __forceinline__ void epi_block(const TcParams &p, uint32_t taddr, bool have_acc, const float *bias_c, uint32_t stg,
+                                          int lane, int rows_g, int c0, bool res_staged, bool no_store) {
+  const uint32_t my_row = stg + lane * V8_STG_PITCH;
+  // (A) every thread finishes NCOLS columns of its own row: accumulator + bias (+ residual), ReLU, convert, into staging
+#pragma unroll
+  for (int cc = 0; cc < NCOLS; cc += 16) {
+    uint32_t v[16];
+    if (have_acc) {
+      tmem_ld16(taddr + cc, v);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = 0u;
+    }
+    float f[16];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 b = *reinterpret_cast<const float4 *>(bias_c + cc + 4 * j);
+      f[4 * j] = __uint_as_float(v[4 * j]) + b.x;
+      f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b.y;
+      f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b.z;
+      f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b.w;
+    }
+    if (p.residual) {
+      uint4 r0, r1;
+      if (res_staged) {
+        r0 = lds128(my_row + cc * 2);
+        r1 = lds128(my_row + cc * 2 + 16);
+      } else if (rows_g >= 0) {  // fp32 output with a residual (not on the engine's path): direct loads
+        const uint4 *rp = reinterpret_cast<const uint4 *>(p.residual + (long long)rows_g * p.c_out + c0 + cc);
+        r0 = __ldg(rp);
+        r1 = __ldg(rp + 1);
+      } else {
+        r0 = r1 = make_uint4(0u, 0u, 0u, 0u);
+      }
+      const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        f[2 * j] += __uint_as_float(rw[j] << 16);
+        f[2 * j + 1] += __uint_as_float(rw[j] & 0xffff0000u);
+      }
+    }
+    if (p.relu) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+    }
+    if (F32) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        sts128(my_row + cc * 4 + 16 * j, make_uint4(__float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]),
+                                                    __float_as_uint(f[4 * j + 2]), __float_as_uint(f[4 * j + 3])));
+    } else {
+      uint32_t w[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+        w[j] = *reinterpret_cast<const uint32_t *>(&h);
+      }
+      sts128(my_row + cc * 2, make_uint4(w[0], w[1], w[2], w[3]));
+      sts128(my_row + cc * 2 + 16, make_uint4(w[4], w[5], w[6], w[7]));
+    }
+  }
+  __syncwarp();
+  // (B) the warp streams the block out: consecutive lanes on consecutive 16-byte chunks of a row
+  constexpr int ESZ = F32 ? 4 : 2;
+  constexpr int CPR = NCOLS * ESZ / 16;
+  char *out_c0 = reinterpret_cast<char *>(p.out) + (long long)c0 * ESZ;
+  const long long pitch = (long long)p.c_out * ESZ;
+#pragma unroll
+  for (int it = 0; it < CPR; ++it) {
+    const int r = it * (32 / CPR) + lane / CPR, q = lane % CPR;
+    const int orow = __shfl_sync(0xffffffffu, rows_g, r);
+    const uint4 val = lds128(stg + r * V8_STG_PITCH + q * 16);
+    if (orow >= 0 && !no_store) *reinterpret_cast<uint4 *>(out_c0 + (long long)orow * pitch + q * 16) = val;
+  }
+  __syncwarp();
+}
+
 template <int G>
-__global__ void __launch_bounds__(V5_THREADS, 1) conv_tc_kernel(const TcParams p) {
+__global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[2 * V5_MAX_STAGES + 4 + 2 * V5_SCHED_SLOTS];
-  __shared__ int sched_tile[V5_SCHED_SLOTS];
+  __shared__ __align__(8) uint64_t bars[2 * V8_MAX_STAGES + 4 + 2 * V8_PLAN_SLOTS];
+  __shared__ Plan plans[V8_PLAN_SLOTS];
   __shared__ uint32_t tmem_base_slot;
+  __shared__ __align__(16) float bias_s[256];
+  __shared__ uint32_t lut[128];  // per (slice j, 16-byte chunk c of the slice): which offset / source tensor / source chunk
 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -94,30 +205,45 @@ __global__ void __launch_bounds__(V5_THREADS, 1) conv_tc_kernel(const TcParams p
   const uint32_t b_bytes = (uint32_t)p.c_out * 128u;                 // multiple of 2048
   const uint32_t stage_bytes = b_bytes + (uint32_t)G * TC_A_BYTES;   // [W slice][A tile 0]..[A tile G-1]
   const uint32_t nst = (uint32_t)p.na;                               // stages
+  const uint32_t stg0 = smem_base + nst * stage_bytes;               // epilogue staging, then the producers' index buffers
+  const uint32_t idx0 = stg0 + V8_EPI_WARPS * V8_STG_BYTES;
+  const uint32_t idx_warp_bytes = (uint32_t)p.ksmax * G * 128u;      // per producer warp: [offset of the slice][sub-tile][32 rows]
   const int num_tiles = (int)((p.n_out + TC_BM - 1) / TC_BM);
   const int num_super = (num_tiles + G - 1) / G;
   const unsigned kmask = p.K >= 32 ? 0xffffffffu : ((1u << p.K) - 1u);
   const int KV = (p.K + P - 1) / P;                                  // virtual offsets
-  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[V5_MAX_STAGES]);
-  const uint32_t tfull0 = smem_u32(&bars[2 * V5_MAX_STAGES]), tempty0 = tfull0 + 16;
-  const uint32_t sfull0 = tfull0 + 32, sempty0 = sfull0 + 8 * V5_SCHED_SLOTS;
+  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[V8_MAX_STAGES]);
+  const uint32_t tfull0 = smem_u32(&bars[2 * V8_MAX_STAGES]), tempty0 = tfull0 + 16;
+  const uint32_t sfull0 = tfull0 + 32, sempty0 = sfull0 + 8 * V8_PLAN_SLOTS;
 
   if (threadIdx.x == 0) {
     for (uint32_t s = 0; s < nst; ++s) {
-      mbar_init(full0 + 8 * s, V5_GROUP_WARPS + 1);  // one arrival per warp of the owning producer group + the weight thread
-      mbar_init(empty0 + 8 * s, G);                  // one tcgen05.commit per MMA warp
+      mbar_init(full0 + 8 * s, V8_GROUP_WARPS + 1);  // one arrival per warp of the owning producer group + the weight thread
+      mbar_init(empty0 + 8 * s, G);                  // one tcgen05.commit per sub-tile (from the issuer that owns the stage)
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull0 + 8 * b, G);
-      mbar_init(tempty0 + 8 * b, TC_EPI_WARPS * 32);
+      mbar_init(tempty0 + 8 * b, V8_EPI_WARPS * 32);
     }
-    for (int s = 0; s < V5_SCHED_SLOTS; ++s) {
+    for (int s = 0; s < V8_PLAN_SLOTS; ++s) {
       mbar_init(sfull0 + 8 * s, 1);
-      mbar_init(sempty0 + 8 * s, V5_CONSUMER_WARPS);
+      mbar_init(sempty0 + 8 * s, V8_CONSUMER_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == V5_MMA_WARP) {  // TMEM allocation by the MMA warp
+  if (threadIdx.x < 256) bias_s[threadIdx.x] = (p.bias && (int)threadIdx.x < p.c_out) ? __ldg(p.bias + threadIdx.x) : 0.f;
+  if (threadIdx.x >= 256 && threadIdx.x < 256 + 128) {
+    const int t = threadIdx.x - 256, j = t >> 3, c = t & 7;
+    uint32_t e = 0;
+    if (j < Q) {
+      const int cpo = p.cpo, c0c = p.c0 >> 3;
+      const int f = 8 * j + c, ksub = f / cpo, cc = f - ksub * cpo, lo = (8 * j) / cpo;
+      const bool second = cc >= c0c;
+      e = (uint32_t)(ksub - lo) | ((uint32_t)ksub << 2) | ((second ? 1u : 0u) << 4) | ((uint32_t)(second ? cc - c0c : cc) << 5);
+    }
+    lut[t] = e;
+  }
+  if (warp == V8_MMA_WARP) {  // TMEM allocation by the MMA warp
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
                  "r"(p.tmem_cols)
                  : "memory");
@@ -128,131 +254,118 @@ __global__ void __launch_bounds__(V5_THREADS, 1) conv_tc_kernel(const TcParams p
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
 
-  // next super tile from the scheduler ring (every consumer warp calls this once per super tile, converged)
-  Ring sr;
-  auto next_super = [&]() -> int {
-    mbar_wait(sfull0 + 8 * sr.slot, sr.phase);
-    const int st = *reinterpret_cast<volatile int *>(&sched_tile[sr.slot]);
-    __syncwarp();
-    if (lane == 0) mbar_arrive(sempty0 + 8 * sr.slot);
-    sr.advance(V5_SCHED_SLOTS);
-    return st;
-  };
-  auto next_super_lane = [&]() -> int {  // same, for roles that run in one lane
-    mbar_wait(sfull0 + 8 * sr.slot, sr.phase);
-    const int st = *reinterpret_cast<volatile int *>(&sched_tile[sr.slot]);
-    mbar_arrive(sempty0 + 8 * sr.slot);
-    sr.advance(V5_SCHED_SLOTS);
-    return st;
-  };
-  // real-offset masks of the G tiles of a super tile; returns their union
-  auto tile_masks = [&](int st, unsigned (&masks)[G]) -> unsigned {
-    unsigned um = 0;
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-      const int tile = st * G + g;
-      masks[g] = tile < num_tiles ? ((p.tile_mask ? __ldg(p.tile_mask + tile) : 0xffffffffu) & kmask) : 0u;
-      um |= masks[g];
-    }
-    return um;
-  };
-  // virtual offsets with at least one real offset present in `m`
-  auto virt_mask = [&](unsigned m) -> unsigned {
-    if (P == 1) return m;
-    unsigned vm = 0;
-    for (int kv = 0; kv < KV; ++kv) vm |= ((m >> (kv * P)) & subP) ? (1u << kv) : 0u;
-    return vm;
-  };
-  // The stages of a super tile, in the order every role walks them: for each virtual offset kv present in the union
-  // mask `um`, the slices j whose offsets (bits `need`) intersect it.  All roles enumerate with the same two tests.
   auto group_bits = [&](unsigned m, int kv) -> unsigned { return (m >> (kv * P)) & subP; };
   auto need_of = [&](int j) -> unsigned { return (unsigned)(slice_need >> (4 * j)) & 15u; };
+  // Plan ring, consumer side: wait for the next plan; release it when the role is done with the super tile.
+  Ring pr;
+  auto plan_wait = [&]() -> const volatile Plan * {
+    mbar_wait(sfull0 + 8 * pr.slot, pr.phase);
+    return &plans[pr.slot];
+  };
+  auto plan_release_lane = [&]() {  // from the one running lane of a single-lane role
+    mbar_arrive(sempty0 + 8 * pr.slot);
+    pr.advance(V8_PLAN_SLOTS);
+  };
+  auto plan_release_warp = [&]() {  // converged warp
+    __syncwarp();
+    if (lane == 0) mbar_arrive(sempty0 + 8 * pr.slot);
+    pr.advance(V8_PLAN_SLOTS);
+  };
 
-  if (warp < TC_EPI_WARPS) {
+  if (warp < V8_EPI_WARPS) {
     // ================================================================= epilogue
+    // Accumulator rows live one per TMEM lane = one per thread, but a thread storing its own row touches 32 different
+    // cache lines per warp instruction.  So each warp transposes through its staging buffer, 64 B of output per row at
+    // a time (epi_block): the residual block is fetched into the buffer with coalesced cp.async, every thread finishes
+    // its row there, and the warp streams the buffer out with consecutive lanes on consecutive chunks of a row.
+    // Two sets of four warps (one warp per TMEM lane quadrant): with G = 2 set e drains sub-tile e, with G = 1 the sets
+    // take alternate column blocks — the epilogue of a super tile must not outlast the main loop of the next one.
+    const int quad = warp & 3, eset = warp >> 2;
+    const uint32_t stg = stg0 + warp * V8_STG_BYTES;
+    const int c_out = p.c_out;
+    const bool f32 = p.out_f32 != 0;
+    const bool res_staged = p.residual != nullptr && !f32;
+    const bool no_store = TSG_DBG(8) != 0;
+    const char *resp = reinterpret_cast<const char *>(p.residual);
+    const long long res_pitch = (long long)c_out * 2;
+    const int g = G == 2 ? eset : 0;
+    const int bw = f32 ? 16 : 32;                           // full block width in columns (64 B of output per row)
+    const int cstep = G == 2 ? bw : 2 * bw;                 // this warp's blocks start at cfirst, cfirst + cstep, ...
+    const int cfirst = G == 2 ? 0 : eset * bw;
+    auto blk_cols = [&](int c0) -> int { return c_out - c0 >= bw ? bw : 16; };  // the last block may be 16 columns wide
+    auto prefetch_res = [&](int rows_g, int c0, int ncols) {
+      const char *src = resp + (long long)c0 * 2;
+      if (ncols == 32) epi_prefetch_res<32>(stg, src, res_pitch, rows_g, lane);
+      else epi_prefetch_res<16>(stg, src, res_pitch, rows_g, lane);
+    };
     uint32_t it = 0;
-    for (int st = next_super(); st >= 0; st = next_super(), ++it) {
+    for (;; ++it) {
+      const volatile Plan *pl = plan_wait();
+      const int st = pl->tile;
+      const unsigned mask_g = pl->mask[g];
+      plan_release_warp();
+      if (st < 0) break;
       const uint32_t buf = it & 1, ph = (it >> 1) & 1;
-      unsigned masks[G];
-      long long rows[G];
-      tile_masks(st, masks);
-#pragma unroll
-      for (int g = 0; g < G; ++g) {  // destination rows are fetched before the (long) wait for the accumulators
-        const long long r = (long long)(st * G + g) * TC_BM + warp * 32 + lane;
-        rows[g] = r < p.n_out ? (p.perm ? (long long)__ldg(p.perm + r) : r) : -1;
-      }
+      const long long r = (long long)(st * G + g) * TC_BM + quad * 32 + lane;  // destination row: fetched before the long wait
+      const int rows_g = r < p.n_out ? (p.perm ? __ldg(p.perm + r) : (int)r) : -1;
+      const bool live = st * G + g < num_tiles && cfirst < c_out;
+      if (res_staged && live) prefetch_res(rows_g, cfirst, blk_cols(cfirst));  // lands while the main loop still runs
       mbar_wait_sleep(tfull0 + 8 * buf, ph);
       tc_fence_after();
       if (threadIdx.x == 0) TSG_TRACE(10, it);
-#pragma unroll
-      for (int g = 0; g < G; ++g) {
-        if (st * G + g >= num_tiles) break;
-        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (buf * G + g) * (uint32_t)p.c_out;
-        int c = 0;
-        for (; c + 32 <= p.c_out; c += 32) {
-          uint32_t v[32];
-          if (masks[g]) {
-            tmem_ld32(taddr + c, v);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = 0u;
+      if (live) {
+        const bool have_acc = mask_g != 0u;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (buf * G + g) * (uint32_t)c_out;
+        for (int c0 = cfirst; c0 < c_out; c0 += cstep) {
+          const int ncols = blk_cols(c0);
+          if (res_staged) {
+            if (c0 != cfirst) prefetch_res(rows_g, c0, ncols);
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            __syncwarp();
           }
-          if (rows[g] >= 0 && !TSG_DBG(8)) {
-            epilogue_store16(p, rows[g], c, *reinterpret_cast<const uint32_t(*)[16]>(&v[0]));
-            epilogue_store16(p, rows[g], c + 16, *reinterpret_cast<const uint32_t(*)[16]>(&v[16]));
-          }
-        }
-        if (c < p.c_out) {  // c_out is a multiple of 16
-          uint32_t v[16];
-          if (masks[g]) {
-            tmem_ld16(taddr + c, v);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = 0u;
-          }
-          if (rows[g] >= 0) epilogue_store16(p, rows[g], c, v);
+          if (f32) epi_block<16, true>(p, taddr + c0, have_acc, bias_s + c0, stg, lane, rows_g, c0, res_staged, no_store);
+          else if (ncols == 32) epi_block<32, false>(p, taddr + c0, have_acc, bias_s + c0, stg, lane, rows_g, c0, res_staged, no_store);
+          else epi_block<16, false>(p, taddr + c0, have_acc, bias_s + c0, stg, lane, rows_g, c0, res_staged, no_store);
         }
       }
       tc_fence_before();
       mbar_arrive(tempty0 + 8 * buf);
       if (threadIdx.x == 0) TSG_TRACE(11, it);
     }
-  } else if (warp == V5_MMA_WARP || warp == V5_MMA_WARP + 1) {
+  } else if (warp == V8_MMA_WARP || warp == V8_MMA_WARP + 1) {
     // ================================================================= MMA issuers (one thread per sub-tile)
-    // Issuing a tcgen05.mma costs the issuing thread ~56 cycles and a tcgen05.commit ~180 whatever the MMA's size
-    // (tools/micro/mma_issue.cu, profiles/README.md), so for c_out <= 128 the instruction stream, not the tensor pipe,
-    // bounds a stage: each of the G sub-tiles gets its own issuing warp, and the loop runs in one lane.
-    const int g = warp - V5_MMA_WARP;
-    if (g < G && lane == 0) {
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.c_out >> 3) << 17) | ((TC_BM >> 4) << 24);
-      const uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);   // SBO 1024 B, version 1, SWIZZLE_128B
-      const uint32_t desc_lo_stage = stage_bytes >> 4;
-      const uint32_t b_lo0 = ((smem_base & 0x3FFFFu) >> 4) | (1u << 16);          // LBO field = 1 (ignored for swizzled K-major)
-      const uint32_t a_lo0 = b_lo0 + (b_bytes >> 4) + g * (TC_A_BYTES >> 4);
-      uint32_t slot = 0, phase = 0, it = 0;
-      int n_mma = 0;
-      for (int st = next_super_lane(); st >= 0; st = next_super_lane(), ++it) {
-        const uint32_t buf = it & 1, ph = (it >> 1) & 1;
-        unsigned masks[G];
-        const unsigned um = tile_masks(st, masks);
-        const unsigned umask = virt_mask(um);
-        unsigned mg = masks[0];
-#pragma unroll
-        for (int gg = 1; gg < G; ++gg)
-          if (g == gg) mg = masks[gg];
-        mbar_wait(tempty0 + 8 * buf, ph ^ 1);
-        tc_fence_after();
-        if (g == 0) TSG_TRACE(8, it);
-        const int n_mma_tile0 = n_mma;
-        const uint32_t d_tmem = tmem_base + (buf * G + g) * (uint32_t)p.c_out;
-        uint32_t started = 0;
-        for (int kv = next_bit(umask, -1); kv < 32; kv = next_bit(umask, kv)) {
-          const unsigned gu = group_bits(um, kv), gm = group_bits(mg, kv);
-          for (int j = 0; j < Q; ++j) {
-            const unsigned need = need_of(j);
-            if (!(gu & need)) continue;                 // no tile of the super tile needs this slice: no stage
-            const bool act = (gm & need) != 0 && !TSG_DBG(4);
+    // Issuing a tcgen05.mma costs the issuing thread ~60 cycles and a tcgen05.commit ~150 whatever the MMA's size
+    // (tools/micro/mma_issue.cu, profiles/README.md): each of the G sub-tiles gets its own issuing warp, and the loop
+    // runs in one lane.
+    const int g = warp - V8_MMA_WARP;
+    if (lane == 0) {
+      if (g < G) {
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.c_out >> 3) << 17) | ((TC_BM >> 4) << 24);
+        const uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);   // SBO 1024 B, version 1, SWIZZLE_128B
+        const uint32_t desc_lo_stage = stage_bytes >> 4;
+        const uint32_t b_lo0 = ((smem_base & 0x3FFFFu) >> 4) | (1u << 16);          // LBO field = 1 (ignored for swizzled K-major)
+        const uint32_t a_lo0 = b_lo0 + (b_bytes >> 4) + g * (TC_A_BYTES >> 4);
+        uint32_t slot = 0, phase = 0, it = 0;
+        int n_mma = 0;
+        for (;; ++it) {
+          const volatile Plan *pl = plan_wait();
+          if (pl->tile < 0) {
+            plan_release_lane();
+            break;
+          }
+          const int n = pl->n;
+          const uint32_t buf = it & 1, ph = (it >> 1) & 1;
+          mbar_wait(tempty0 + 8 * buf, ph ^ 1);
+          tc_fence_after();
+          if (g == 0) TSG_TRACE(8, it);
+          const uint32_t d_tmem = tmem_base + (buf * G + g) * (uint32_t)p.c_out;
+          uint32_t started = 0;
+          unsigned d_next = n > 0 ? pl->stage[0] : 0u;
+          for (int i = 0; i < n; ++i) {
+            const bool act = ((d_next >> (9 + g)) & 1u) && !TSG_DBG(4);
+            if (i + 1 < n) d_next = pl->stage[i + 1];  // off the critical path: read before the wait
             if (g == 0) TSG_TRACE(5, n_mma);
+            TSG_STATE(pl->tile, n, i, n_mma);
             mbar_wait(full0 + 8 * slot, phase);  // producers fenced their writes towards the async proxy before arriving
             tc_fence_after();
             if (g == 0) TSG_TRACE(2, n_mma);
@@ -272,200 +385,300 @@ __global__ void __launch_bounds__(V5_THREADS, 1) conv_tc_kernel(const TcParams p
               phase ^= 1;
             }
           }
-        }
-        umma_commit(tfull0 + 8 * buf);  // this sub-tile's accumulator is complete (immediately if there was no work)
-        if (g == 0) TSG_TRACE(9, it);
+          umma_commit(tfull0 + 8 * buf);  // this sub-tile's accumulator is complete (immediately if there was no work)
+          if (g == 0) TSG_TRACE(9, it);
 #ifdef TSG_TC_TRACE
-        if (g == 0 && (p.dbg & 128) && blockIdx.x == 0 && it < TRACE_N) g_trace[12][it] = n_mma - n_mma_tile0;
+          if (g == 0 && (p.dbg & 128) && blockIdx.x == 0 && it < TRACE_N) g_trace[12][it] = n;
 #endif
+          plan_release_lane();
+        }
+      } else {
+        for (;;) {  // spare MMA warp (G == 1): keep the plan ring moving
+          const int st = plan_wait()->tile;
+          plan_release_lane();
+          if (st < 0) break;
+        }
       }
-    } else if (lane == 0) {
-      while (next_super_lane() >= 0) {}  // spare MMA warp (G == 1): keep the scheduler ring moving
     }
     __syncwarp();
-  } else if (warp == V5_W_WARP) {
+  } else if (warp == V8_W_WARP) {
     // ================================================================= weight loader
     if (lane == 0) {
       Ring r;
       int n_w = 0;
-      for (int st = next_super_lane(); st >= 0; st = next_super_lane()) {
-        unsigned masks[G];
-        const unsigned um = tile_masks(st, masks);
-        const unsigned umask = virt_mask(um);
-        for (int kv = next_bit(umask, -1); kv < 32; kv = next_bit(umask, kv)) {
-          const unsigned gu = group_bits(um, kv);
-          const uint8_t *wk = p.packed_w + (size_t)kv * Q * b_bytes;
-          for (int j = 0; j < Q; ++j) {
-            if (!(gu & need_of(j))) continue;
-            mbar_wait(empty0 + 8 * r.slot, r.phase ^ 1);
-            TSG_TRACE(4, n_w);
-            ++n_w;
-            if (TSG_DBG(2)) {
-              mbar_arrive(full0 + 8 * r.slot);
-            } else {
-              mbar_arrive_expect_tx(full0 + 8 * r.slot, b_bytes);
-              bulk_g2s(smem_base + r.slot * stage_bytes, wk + (size_t)j * b_bytes, b_bytes, full0 + 8 * r.slot);
-            }
-            r.advance(nst);
-          }
+      for (;;) {
+        const volatile Plan *pl = plan_wait();
+        if (pl->tile < 0) {
+          plan_release_lane();
+          break;
         }
+        const int n = pl->n;
+        for (int i = 0; i < n; ++i) {
+          const unsigned d = pl->stage[i];
+          const uint8_t *src = p.packed_w + (size_t)((d & 31u) * Q + ((d >> 5) & 15u)) * b_bytes;
+          TSG_STATE(pl->tile, n, i, n_w);
+          mbar_wait(empty0 + 8 * r.slot, r.phase ^ 1);
+          TSG_TRACE(4, n_w);
+          ++n_w;
+          if (TSG_DBG(2)) {
+            mbar_arrive(full0 + 8 * r.slot);
+          } else {
+            mbar_arrive_expect_tx(full0 + 8 * r.slot, b_bytes);
+            bulk_g2s(smem_base + r.slot * stage_bytes, src, b_bytes, full0 + 8 * r.slot);
+          }
+          r.advance(nst);
+        }
+        plan_release_lane();
       }
     }
     __syncwarp();
-  } else if (warp == V5_SCHED_WARP) {
-    // ================================================================= scheduler
-    if (lane == 0) {
-      Ring w;
-      int static_next = blockIdx.x;
-      for (;;) {
-        mbar_wait(sempty0 + 8 * w.slot, w.phase ^ 1);
-        int t;
+  } else if (warp == V8_SCHED_WARP) {
+    // ================================================================= planner
+    // Draws super-tile tickets from a global counter (heaviest tiles first) and expands each into its stage list, one
+    // virtual offset per lane, so that no other role walks masks or touches global memory to learn what to do next.
+    // (v7/v8 let every warp enumerate the stages itself: ~2000 cycles of branchy scalar code per producer group stage,
+    // the bottleneck of the whole kernel — profiles/README.md.)
+    Ring w;
+    int static_next = blockIdx.x;
+    for (;;) {
+      mbar_wait(sempty0 + 8 * w.slot, w.phase ^ 1);
+      int t = 0;
+      if (lane == 0) {
         if (p.sched) {
           t = atomicAdd(p.sched, 1);
         } else {
           t = static_next;
           static_next += gridDim.x;
         }
-        const int st = t < num_super ? num_super - 1 - t : -1;  // heavy (high-key) tiles first
-        *reinterpret_cast<volatile int *>(&sched_tile[w.slot]) = st;
-        mbar_arrive(sfull0 + 8 * w.slot);  // release: the tile index is visible to the waiters
-        w.advance(V5_SCHED_SLOTS);
-        if (st < 0) break;
       }
-      if (p.sched) {  // every CTA draws exactly one terminal ticket: the last one re-arms the counters for the next launch
+      t = __shfl_sync(0xffffffffu, t, 0);
+      const int st = t < num_super ? num_super - 1 - t : -1;  // heavy (high-key) tiles first
+      unsigned mm = 0;
+      if (st >= 0 && lane < G) {
+        const int tile = st * G + lane;
+        mm = tile < num_tiles ? ((p.tile_mask ? __ldg(p.tile_mask + tile) : 0xffffffffu) & kmask) : 0u;
+      }
+      const unsigned m0 = __shfl_sync(0xffffffffu, mm, 0), m1 = G > 1 ? __shfl_sync(0xffffffffu, mm, 1) : 0u;
+      const unsigned g0 = lane < KV ? group_bits(m0, lane) : 0u, g1 = lane < KV ? group_bits(m1, lane) : 0u;
+      const unsigned gu = g0 | g1;
+      unsigned sl = 0;  // slices of virtual offset `lane` that some tile of the super tile needs
+      for (int j = 0; j < Q; ++j) sl |= (gu & need_of(j)) ? (1u << j) : 0u;
+      int incl = __popc(sl);
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+      }
+      int pos = incl - __popc(sl);
+      Plan *pl = &plans[w.slot];
+      for (unsigned rest = sl; rest; rest &= rest - 1) {
+        const int j = __ffs(rest) - 1;
+        const unsigned need = need_of(j);
+        pl->stage[pos++] = (unsigned short)(lane | (j << 5) | ((g0 & need) ? 1u << 9 : 0u) | ((g1 & need) ? 1u << 10 : 0u));
+      }
+      const int n_total = __shfl_sync(0xffffffffu, incl, 31);
+      TSG_STATE(st, n_total, t, (int)w.slot);
+      if (lane == 0) {
+        pl->tile = st;
+        pl->n = n_total;
+        pl->mask[0] = m0;
+        pl->mask[1] = m1;
+      }
+      __threadfence_block();  // every lane's stage entries are performed before lane 0 publishes the plan
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sfull0 + 8 * w.slot);  // release: the plan is visible to the waiters
+      w.advance(V8_PLAN_SLOTS);
+      if (st < 0) break;
+    }
+    if (lane == 0 && p.sched) {  // every CTA draws exactly one terminal ticket: the last one re-arms the counters for the next launch
+      __threadfence();
+      if (atomicAdd(p.sched + 1, 1) == (int)gridDim.x - 1) {
+        p.sched[0] = 0;
+        p.sched[1] = 0;
         __threadfence();
-        if (atomicAdd(p.sched + 1, 1) == (int)gridDim.x - 1) {
-          p.sched[0] = 0;
-          p.sched[1] = 0;
-          __threadfence();
-        }
       }
     }
     __syncwarp();
   } else {
     // ================================================================= producers
-    // V5_GROUPS independent groups of V5_GROUP_WARPS warps; group g owns the global stages s with s % NG == g, so a
+    // V8_GROUPS independent groups of V8_GROUP_WARPS warps; group g owns the global stages s with s % NG == g, so a
     // hand-shake (empty wait, landing wait, proxy fence, one arrival per warp) is paid once per 8 G copies per thread,
-    // and while one group waits for its rows to land the others are issuing theirs.
-    const int grp = (warp - V5_PROD_WARP0) / V5_GROUP_WARPS;
-    const int NG = (int)nst < V5_GROUPS ? (int)nst : V5_GROUPS;
-    const int tid = threadIdx.x - 32 * (V5_PROD_WARP0 + grp * V5_GROUP_WARPS);  // 0..127 inside the group
-    const int chunk = tid & 7, rsub = tid >> 3;  // 8 lanes cover one 128-byte tile row; thread owns rows 8 rsub .. 8 rsub + 7
-    uint32_t dst_off[V5_Q];                      // row 8 rsub + q sits at chunk position chunk ^ q of its 128-byte line
+    // and while one group waits for its rows to land the others are issuing theirs.  A warp covers 32 consecutive tile
+    // rows (four 8-lane row groups x 8 rows).  While the rows of stage n land, the warp requests the 128-byte index
+    // lines of ITS next stage with cp.async into a private shared-memory buffer; they are complete at the same
+    // cp.async.wait_all and are read back with two LDS.128 per sub-tile.
+    const int pw = warp - V8_PROD_WARP0;
+    const int grp = pw / V8_GROUP_WARPS, wg = pw % V8_GROUP_WARPS;
+    const int NG = (int)nst < V8_GROUPS ? (int)nst : V8_GROUPS;
+    const int chunk = lane & 7, rsl = lane >> 3;  // 8 lanes cover one 128-byte tile row; row group rsl of the warp
+    const int rsub = wg * 4 + rsl;                // thread owns tile rows 8 rsub .. 8 rsub + 7
+    uint32_t dst_off[V8_Q];                       // row 8 rsub + q sits at chunk position chunk ^ q of its 128-byte line
 #pragma unroll
-    for (int q = 0; q < V5_Q; ++q) dst_off[q] = b_bytes + (uint32_t)(rsub * V5_Q + q) * 128u + (uint32_t)((chunk ^ q) << 4);
-    const int cpo = p.cpo, c0c = p.c0 >> 3;      // chunks per offset, chunks of the first source tensor
+    for (int q = 0; q < V8_Q; ++q) dst_off[q] = b_bytes + (uint32_t)(rsub * V8_Q + q) * 128u + (uint32_t)((chunk ^ q) << 4);
+    const uint32_t ibuf = idx0 + (uint32_t)pw * idx_warp_bytes;
     const uint32_t rb0 = (uint32_t)p.c0 * 2u, rb1 = (uint32_t)p.c1 * 2u;
     const char *in0 = reinterpret_cast<const char *>(p.in0);
     const char *in1 = reinterpret_cast<const char *>(p.in1);
-    const int K = p.K;
     const long long n_out = p.n_out, nbr_stride = p.nbr_stride;
     const int *nbr = p.nbr;
-    const bool worker = grp < NG;
-    uint32_t slot = (uint32_t)grp, phase = 0;  // ring position of this group's next stage (always NG stages further)
-    int cnt = NG - 1;                          // global stage number modulo NG of the iterator's current stage (none yet)
-    int n_issued = 0;
-    for (int st = next_super(); st >= 0; st = next_super()) {
-      if (!worker) continue;
-      unsigned masks[G];
-      const unsigned um = tile_masks(st, masks);
-      const unsigned umask = virt_mask(um);
-      // iterator over the stages of this super tile; every group walks all of them and keeps `cnt` in step
-      int kv = next_bit(umask, -1), j = -1;
-      unsigned gu = kv < 32 ? group_bits(um, kv) : 0u;
-      auto next_stage = [&]() -> bool {  // advance to the next stage of the super tile; false at its end
-        while (kv < 32) {
-          while (++j < Q)
-            if (gu & need_of(j)) {
-              cnt = cnt + 1 == NG ? 0 : cnt + 1;
-              return true;
-            }
-          kv = next_bit(umask, kv);
-          j = -1;
-          gu = kv < 32 ? group_bits(um, kv) : 0u;
+    // ---- cursor over the global stage sequence: plan of the current super tile + index of the next stage in it
+    int st = -2, n = 0, i = 0, gs = 0;  // gs = (global stage number of plan index i) mod NG
+    unsigned masks[2] = {0u, 0u};
+    unsigned d_cur = 0;                 // descriptor of the stage the cursor delivered last
+    // Moves the cursor to this group's next stage: 1 = delivered (d_cur), 0 = no more work, 2 = the next plan is not
+    // published yet and `block` is false.  The non-blocking form exists because a producer must never wait for a plan
+    // while it owes an arrival on a full barrier: the planner waits for the MMA issuers to release old plans, and they
+    // wait for that arrival (a deadlock v9 hit as soon as tiles became one or two stages long).
+    auto advance_mine = [&](bool block) -> int {
+      for (;;) {
+        if (st >= 0) {
+          int skip = grp - gs;
+          if (skip < 0) skip += NG;
+          if (i + skip < n) {
+            i += skip;
+            d_cur = plans[pr.slot].stage[i];
+            ++i;
+            gs = grp + 1 == NG ? 0 : grp + 1;
+            return 1;
+          }
+          gs = (gs + (n - i)) % NG;
+          plan_release_warp();
+          st = -2;  // between plans
         }
-        return false;
+        if (st == -1) return 0;
+        if (!block) {
+          const int ready = __shfl_sync(0xffffffffu, (int)mbar_test(sfull0 + 8 * pr.slot, pr.phase), 0);
+          if (!ready) return 2;
+        }
+        const volatile Plan *pl = plan_wait();
+        st = pl->tile;
+        if (st < 0) {
+          plan_release_warp();
+          st = -1;
+          return 0;
+        }
+        n = pl->n;
+        masks[0] = pl->mask[0];
+        masks[1] = pl->mask[1];
+        i = 0;
+        TSG_STATE(st, n, gs, -1);
+      }
+    };
+    if (grp >= NG) {
+      for (;;) {  // fewer stages than groups: this group only keeps the plan ring moving
+        const int t = plan_wait()->tile;
+        plan_release_warp();
+        if (t < 0) break;
+      }
+    } else {
+      // ---- this lane's view of a stage (locate() fills it from the delivered descriptor)
+      struct View {
+        long long m0;       // first tile row of the super tile
+        const char *src;    // source tensor + byte offset of the lane's chunk inside a source row
+        uint32_t rb;        // source row pitch
+        uint32_t ioff;      // this lane's 32 bytes inside the warp's index buffer (sub-tile 0)
+        unsigned kbits;     // per sub-tile: the lane's offset is present
+        unsigned act;       // per sub-tile: the slice is needed
       };
-      auto next_mine = [&]() -> bool {   // advance to this group's next stage
-        while (next_stage())
-          if (cnt == grp) return true;
-        return false;
+      auto locate = [&](View &v) {
+        const int kv = d_cur & 31u, j = (d_cur >> 5) & 15u;
+        v.act = (d_cur >> 9) & 3u;
+        const uint32_t e = lut[j * 8 + chunk];
+        const int k = kv * P + (int)((e >> 2) & 3u);
+        const bool second = (e >> 4) & 1u;
+        v.src = (second ? in1 : in0) + (e >> 5) * 16u;
+        v.rb = second ? rb1 : rb0;
+        v.ioff = (e & 3u) * (uint32_t)(G * 128) + (uint32_t)rsl * 32u;
+        v.m0 = (long long)st * G * TC_BM;
+        v.kbits = ((masks[0] >> k) & 1u) | (((masks[1] >> k) & 1u) << 1);
       };
-      const long long m0 = (long long)st * G * TC_BM + rsub * V5_Q;  // first of this thread's 8 consecutive tile rows
-      int idx[G][V5_Q];  // neighbour row of tile row 8 rsub + q, or -1
-      int k_loaded = -1;
-      // this lane's chunk of slice j of virtual offset kv: offset k, source tensor, byte offset inside the source row
-      int k_cur = 0;
-      const char *src_cur = in0;
-      uint32_t rb_cur = rb0;
-      auto locate = [&]() {
-        const int f = 8 * j + chunk, ksub = f / cpo, cc = f - ksub * cpo;
-        k_cur = kv * P + ksub;
-        const bool second = cc >= c0c;
-        src_cur = (second ? in1 : in0) + (second ? cc - c0c : cc) * 16;
-        rb_cur = second ? rb1 : rb0;
+      // request the index lines of the delivered stage: per (offset of the slice, sub-tile) the warp's 32 rows = 128 B
+      auto prefetch_idx = [&](uint32_t buf) {
+        if (!nbr) return;
+        const int kv = d_cur & 31u, j = (d_cur >> 5) & 15u;
+        const unsigned need = need_of(j);
+        const int k0 = kv * P + __ffs(need) - 1, nks = __popc(need);
+        for (int t = lane; t < nks * G * 8; t += 32) {
+          const int ks = t / (G * 8), g = (t >> 3) % G, piece = t & 7;
+          const int k = k0 + ks;
+          if (((g ? masks[1] : masks[0]) >> k) & 1u)
+            cp_async16(buf + (uint32_t)((ks * G + g) * 128 + piece * 16),
+                       nbr + (long long)k * nbr_stride + (long long)st * G * TC_BM + g * TC_BM + wg * 32 + piece * 4, 16u);
+        }
       };
-      // eight consecutive indices = two 16-byte loads; rows past n_out read the -1 padding of the table
-      auto load_idx = [&]() {
-        if (k_cur == k_loaded) return;
-        k_loaded = k_cur;
-        const int4 *src = reinterpret_cast<const int4 *>(nbr + (long long)k_cur * nbr_stride + m0);
+      // Per stage: read the indices, wait for the slot, issue the copies, then (while they are in flight) find the
+      // group's next stage and request its index lines; cp.async.wait_all covers both, the writes are fenced towards
+      // the async proxy (the tensor core reads them) and each warp arrives once on the stage's full barrier.
+      // (An asynchronous hand-off — cp.async.mbarrier.arrive.noinc per thread and the proxy fence on the MMA thread —
+      // was 5 % faster but lost arrivals intermittently on the packed-slice layers; profiles/README.md.)
+      uint32_t slot = (uint32_t)grp, phase = 0;  // ring position of this group's next stage (always NG stages further)
+      int n_issued = 0;
+      View cur;
+      bool have = advance_mine(true) == 1;
+      if (have) {
+        locate(cur);
+        prefetch_idx(ibuf);
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncwarp();
+      }
+      while (have) {
+        int idx[G][V8_Q];  // neighbour row of tile row 8 rsub + q, or -1
+        const uint32_t ibase = ibuf + cur.ioff;
 #pragma unroll
         for (int g = 0; g < G; ++g) {
-          if (k_cur < K && ((masks[g] >> k_cur) & 1u)) {
+          if ((cur.kbits >> g) & 1u) {
             if (nbr) {
-              const int4 a = __ldg(src + g * (TC_BM / 4)), b = __ldg(src + g * (TC_BM / 4) + 1);
-              idx[g][0] = a.x; idx[g][1] = a.y; idx[g][2] = a.z; idx[g][3] = a.w;
-              idx[g][4] = b.x; idx[g][5] = b.y; idx[g][6] = b.z; idx[g][7] = b.w;
+              const uint4 a = lds128(ibase + g * 128), b = lds128(ibase + g * 128 + 16);
+              idx[g][0] = (int)a.x; idx[g][1] = (int)a.y; idx[g][2] = (int)a.z; idx[g][3] = (int)a.w;
+              idx[g][4] = (int)b.x; idx[g][5] = (int)b.y; idx[g][6] = (int)b.z; idx[g][7] = (int)b.w;
             } else {  // identity map (1x1x1 convolutions, point MLPs)
+              const long long r0 = cur.m0 + g * TC_BM + rsub * V8_Q;
 #pragma unroll
-              for (int q = 0; q < V5_Q; ++q) idx[g][q] = m0 + g * TC_BM + q < n_out ? (int)(m0 + g * TC_BM + q) : -1;
+              for (int q = 0; q < V8_Q; ++q) idx[g][q] = r0 + q < n_out ? (int)(r0 + q) : -1;
             }
           } else {
 #pragma unroll
-            for (int q = 0; q < V5_Q; ++q) idx[g][q] = -1;
+            for (int q = 0; q < V8_Q; ++q) idx[g][q] = -1;
           }
         }
-      };
-      bool have = next_mine();
-      if (have) {
-        locate();
-        load_idx();
-      }
-      while (have) {
-        const unsigned need = need_of(j);
-        unsigned act = 0;
-#pragma unroll
-        for (int g = 0; g < G; ++g) act |= ((group_bits(masks[g], kv) & need) ? 1u : 0u) << g;
-        const char *bp = src_cur;
-        const uint32_t rb = rb_cur;
+        TSG_STATE(st, n, i, n_issued);
         mbar_wait(empty0 + 8 * slot, phase ^ 1);
-        if (tid == 0 && grp == 0) TSG_TRACE(0, n_issued);
+        if (pw == 0 && lane == 0) TSG_TRACE(0, n_issued);
         const uint32_t dst = smem_base + slot * stage_bytes;
         if (!TSG_DBG(1)) {
 #pragma unroll
           for (int g = 0; g < G; ++g) {
-            if (!((act >> g) & 1u)) continue;
+            if (!((cur.act >> g) & 1u)) continue;
 #pragma unroll
-            for (int q = 0; q < V5_Q; ++q) {
+            for (int q = 0; q < V8_Q; ++q) {
               const int v = idx[g][q];
-              cp_async16(dst + g * TC_A_BYTES + dst_off[q], bp + (unsigned long long)(unsigned)max(v, 0) * rb, v >= 0 ? 16u : 0u);
+              cp_async16(dst + g * TC_A_BYTES + dst_off[q], cur.src + (unsigned long long)(unsigned)max(v, 0) * cur.rb, v >= 0 ? 16u : 0u);
             }
           }
         }
-        if (tid == 0 && grp == 0) TSG_TRACE(6, n_issued);
-        // the index registers are free again: fetch the neighbour rows of this group's next stage while the copies land
-        have = next_mine();
-        if (have) {
-          locate();
-          load_idx();
+        if (pw == 0 && lane == 0) TSG_TRACE(6, n_issued);
+        int r = advance_mine(false);
+        if (r == 1) {
+          locate(cur);
+          __syncwarp();  // every lane has read the current stage's indices out of the buffer
+          prefetch_idx(ibuf);
         }
-        if (tid == 0 && grp == 0) TSG_TRACE(7, n_issued);
+        if (pw == 0 && lane == 0) TSG_TRACE(7, n_issued);
         asm volatile("cp.async.wait_all;" ::: "memory");
         fence_async_proxy();  // generic-proxy writes -> visible to the async proxy (tensor core reads)
         __syncwarp();
         if (lane == 0) mbar_arrive(full0 + 8 * slot);
-        if (tid == 0 && grp == 0) TSG_TRACE(1, n_issued);
+        if (pw == 0 && lane == 0) TSG_TRACE(1, n_issued);
+        if (r == 2) {  // the next plan was not there yet: now that nothing is owed, wait for it
+          r = advance_mine(true);
+          if (r == 1) {
+            locate(cur);
+            prefetch_idx(ibuf);
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            __syncwarp();
+          }
+        }
+        have = r == 1;
         ++n_issued;
         slot += NG;
         if (slot >= nst) {
@@ -478,7 +691,7 @@ __global__ void __launch_bounds__(V5_THREADS, 1) conv_tc_kernel(const TcParams p
 
   tc_fence_before();
   __syncthreads();
-  if (warp == V5_MMA_WARP) {
+  if (warp == V8_MMA_WARP) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
   }
 }
@@ -486,7 +699,7 @@ __global__ void __launch_bounds__(V5_THREADS, 1) conv_tc_kernel(const TcParams p
 // K-slice packing of a layer with C = c0 + c1 input channels (both multiples of 16): the flat chunk stream repeats every
 // P offsets with Q slices; need[j] = which of the P offsets slice j touches.
 struct SlicePlan {
-  int P, Q, cpo;
+  int P, Q, cpo, ksmax;  // ksmax = most kernel offsets any one slice touches
   unsigned long long need;
 };
 static SlicePlan slice_plan(int c0, int c1) {
@@ -497,8 +710,10 @@ static SlicePlan slice_plan(int c0, int c1) {
   sp.P = 8 / g;
   sp.Q = sp.cpo / g;
   sp.need = 0;
+  sp.ksmax = 1;
   for (int j = 0; j < sp.Q && j < 16; ++j) {
     const int lo = (8 * j) / sp.cpo, hi = (8 * j + 7) / sp.cpo;
+    if (hi - lo + 1 > sp.ksmax) sp.ksmax = hi - lo + 1;
     unsigned long long bits = 0;
     for (int k = lo; k <= hi; ++k) bits |= 1ull << k;
     sp.need |= bits << (4 * j);
@@ -610,37 +825,50 @@ int tsg_conv_fwd_tc(const void *in0, int c0, const void *in1, int c1, int64_t n_
   p.residual = (const __nv_bfloat16 *)residual;
   p.relu = relu;
   p.sched = sched;
-  static const char *dbg_env = getenv("TSG_TC_DEBUG");  // profiling knock-outs (trace build only, wrong results): 1 no gathers,
-  p.dbg = dbg_env ? atoi(dbg_env) : 0;                  // 2 no weight copies, 4 no MMAs, 8 no epilogue stores, 128 trace
+#ifdef TSG_TC_TRACE  // profiling knock-outs (trace build only, wrong results): 1 no gathers, 2 no weight copies,
+  const char *dbg_env = getenv("TSG_TC_DEBUG");  // 4 no MMAs, 8 no epilogue stores, 128 trace; re-read on every launch
+  p.dbg = dbg_env ? atoi(dbg_env) : 0;
+#else
+  p.dbg = 0;
+#endif
   const int sms = num_sms_hint > 0 ? num_sms_hint : num_sms();
   const long long num_tiles = (n_out + TC_BM - 1) / TC_BM;
   // G sub-tiles share every weight slice; bounded by TMEM (2 buffers x G x c_out fp32 columns <= 512) and by the
   // number of super tiles needed to keep every SM busy
   int G = c_out <= 128 ? 2 : 1;  // (G = 4 spills the producers' index registers at 768 threads per CTA)
   while (G > 1 && (num_tiles + G - 1) / G < 2LL * sms) G >>= 1;
+#ifdef TSG_TC_TRACE
+  if (getenv("TSG_TC_G1")) G = 1;
+#endif
   uint32_t cols = 32;
   while (cols < 2u * (uint32_t)G * (uint32_t)c_out) cols <<= 1;
   p.tmem_cols = cols;
-  const size_t b_bytes = (size_t)c_out * 128, stage_bytes = b_bytes + (size_t)G * TC_A_BYTES, budget = 222 * 1024;
-  int stages = (int)(budget / stage_bytes);
-  if (stages > V5_MAX_STAGES) stages = V5_MAX_STAGES;
+  p.ksmax = sp.ksmax;
+  // dynamic shared memory: 1 KB alignment slack + stages + epilogue staging + the producers' index buffers
+  const size_t b_bytes = (size_t)c_out * 128, stage_bytes = b_bytes + (size_t)G * TC_A_BYTES;
+  const size_t fixed = 1024 + (size_t)V8_EPI_WARPS * V8_STG_BYTES + (size_t)V8_PROD_WARPS * sp.ksmax * G * 128;
+  int stages = (int)((V8_DYN_SMEM - fixed) / stage_bytes);
+  if (stages > V8_MAX_STAGES) stages = V8_MAX_STAGES;
+#ifdef TSG_TC_TRACE
+  if (const char *e = getenv("TSG_TC_STAGES")) stages = atoi(e) < stages ? atoi(e) : stages;
+#endif
   if (stages < 2) {
     set_error("tsg_conv_fwd_tc: not enough shared memory for the pipeline");
     return TSG_ERR_UNSUPPORTED;
   }
   p.na = stages;
   p.nb = stages;
-  const size_t smem = (size_t)stages * stage_bytes + 1024;
+  const size_t smem = (size_t)stages * stage_bytes + fixed;
   static bool configured = false;
   if (!configured) {
-    TSG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-    TSG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    TSG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, V8_DYN_SMEM));
+    TSG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, V8_DYN_SMEM));
     configured = true;
   }
   const long long num_super = (num_tiles + G - 1) / G;
   const unsigned grid = (unsigned)(num_super < sms ? num_super : sms);
-  if (G == 2) conv_tc_kernel<2><<<grid, V5_THREADS, smem, stream>>>(p);
-  else conv_tc_kernel<1><<<grid, V5_THREADS, smem, stream>>>(p);
+  if (G == 2) conv_tc_kernel<2><<<grid, V8_THREADS, smem, stream>>>(p);
+  else conv_tc_kernel<1><<<grid, V8_THREADS, smem, stream>>>(p);
   return check_launch("tsg_conv_fwd_tc");
 }
 

@@ -1,5 +1,6 @@
 // Inline-PTX helpers shared by the tensor-core convolution kernels (mbarrier, cp.async, bulk/TMA copies, tcgen05).
 #pragma once
+#include <cstdio>
 #include "common.cuh"
 
 namespace tsg {
@@ -8,6 +9,19 @@ constexpr int TC_BM = 128;
 constexpr int TC_KB = 64;                       // channels per unit (128 B of bf16)
 constexpr int TC_A_BYTES = TC_BM * TC_KB * 2;   // 16 KB
 constexpr int TC_EPI_WARPS = 4;
+
+#ifdef TSG_TC_TRACE
+__device__ int g_dbg[160][32][4];  // debugging build: per (block, warp) role state, printed by the hang watchdog
+#define TSG_STATE(a, b, c, d)                                                         \
+  do {                                                                                \
+    if ((threadIdx.x & 31) == 0) {                                                    \
+      int *q_ = g_dbg[blockIdx.x % 160][threadIdx.x >> 5];                            \
+      q_[0] = (a); q_[1] = (b); q_[2] = (c); q_[3] = (d);                             \
+    }                                                                                 \
+  } while (0)
+#else
+#define TSG_STATE(a, b, c, d) do { } while (0)
+#endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -38,9 +52,35 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if ((spin & 0xfffu) == 0) {
       const long long now = clock64();
       if (!t0) t0 = now;
+#ifdef TSG_TC_TRACE
+      else if (now - t0 > (1ll << 30)) {  // debugging build: say who hangs on what, give the printf time to drain, then trap
+        if ((threadIdx.x & 31) == 0) {
+          const int *q_ = g_dbg[blockIdx.x % 160][threadIdx.x >> 5];
+          unsigned long long w_[8];
+          for (int z_ = 0; z_ < 8; ++z_) asm volatile("ld.shared.b64 %0, [%1];" : "=l"(w_[z_]) : "r"(1024u + 8u * z_));
+          printf("HANG block %d warp %d bar %d parity %u state %d %d %d %d | full %llx %llx %llx %llx %llx | me %llx\n", blockIdx.x, threadIdx.x >> 5,
+                 (int)(bar - 1024) / 8, parity, q_[0], q_[1], q_[2], q_[3], w_[0], w_[1], w_[2], w_[3], w_[4], w_[((bar - 1024) / 8) & 7]);
+        }
+        __nanosleep(1000000);
+        if (now - t0 > (1ll << 31)) __trap();
+      }
+#else
       else if (now - t0 > (1ll << 33)) __trap();
+#endif
     }
   }
+}
+// one non-blocking probe of an mbarrier phase
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done != 0;
 }
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
@@ -92,6 +132,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// zero 16 accumulator columns of this warp's 32 TMEM lanes (complete after tcgen05.wait::st)
+__device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr), "r"(0u)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): rows of 128 B, 8-row groups
 // 1024 B apart (SBO), version 1, layout type 2.  `addr` may be advanced by 32 B per K=16 step inside the row.
 __device__ __forceinline__ uint64_t umma_desc(uint32_t addr) {
@@ -105,6 +152,7 @@ struct TcParams {
   unsigned long long slice_need;  // 4 bits per slice j < Q: which of the P offsets of a virtual offset slice j touches
   const uint8_t *packed_w;
   int K, c_out, na, nb;
+  int ksmax;                      // most kernel offsets one K slice touches (sizes the producers' index buffers)
   const int *nbr;
   long long nbr_stride;  // elements between offsets of nbr; multiple of 256, padding rows hold -1
   const unsigned *tile_mask;
@@ -153,7 +201,15 @@ __device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
     if ((spin & 0x3ffu) == 0) {
       const long long now = clock64();
       if (!t0) t0 = now;
+#ifdef TSG_TC_TRACE
+      else if (now - t0 > (1ll << 30)) {
+        if ((threadIdx.x & 31) == 0) printf("HANG block %d warp %d bar %d parity %u (sleep)\n", blockIdx.x, threadIdx.x >> 5, (int)(bar - 1024) / 8, parity);
+        __nanosleep(1000000);
+        if (now - t0 > (1ll << 31)) __trap();
+      }
+#else
       else if (now - t0 > (1ll << 33)) __trap();
+#endif
     }
   }
 }

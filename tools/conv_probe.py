@@ -20,15 +20,21 @@ for spec in os.environ.get("CASES", "0:96:96").split(","):
     x = torch.randn(lv.n, cin, device="cuda").bfloat16()
     packed = ops.pack_weights(torch.randn(27, cin, cout, device="cuda") * 0.05, cin)
     nbr, mask, perm = lv.km3.sorted()
-    ts = []
-    for i in range(int(os.environ.get("N", "20"))):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        ops.conv_forward_tc(x, None, packed, 27, cout, nbr, mask, lv.n, perm=perm)
-        e1.record()
-        torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1) * 1e3)
-    print("level %d %3d->%3d rows %d:" % (level, cin, cout, lv.n), " ".join("%.0f" % t for t in ts), "us")
+    res = torch.randn(lv.n, cout, device="cuda").bfloat16() if os.environ.get("RES") else None
+    if os.environ.get("NOPERM"):
+        perm = None
+    for dbg in os.environ.get("DBGS", os.environ.get("TSG_TC_DEBUG", "0")).split(","):   # knock-out sweep (trace build)
+        os.environ["TSG_TC_DEBUG"] = dbg
+        ts = []
+        for i in range(int(os.environ.get("N", "20"))):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            ops.conv_forward_tc(x, None, packed, 27, cout, nbr, mask, lv.n, perm=perm, residual=res, relu=True)
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e3)
+        print("level %d %3d->%3d rows %d dbg %s res %d perm %d:" % (level, cin, cout, lv.n, dbg, res is not None, perm is not None),
+              " ".join("%.0f" % t for t in ts[-6:]), "us")
     if int(os.environ.get("TSG_TC_DEBUG", "0")) & 128:
         import ctypes
         import numpy as np
