@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
   const uint32_t nst = (uint32_t)p.na;                               // stages
   const uint32_t stg0 = smem_base + nst * stage_bytes;               // epilogue staging, then the producers' index buffers
   const uint32_t idx0 = stg0 + V8_EPI_WARPS * V8_STG_BYTES;
-  const uint32_t idx_warp_bytes = (uint32_t)p.ksmax * G * 128u;      // per producer warp: [offset of the slice][sub-tile][32 rows]
+  const uint32_t idx_warp_bytes = (uint32_t)p.ksmax * G * 128u;      // per producer warp, twice: [offset of the slice][sub-tile][32 rows]
   const int num_tiles = (int)((p.n_out + TC_BM - 1) / TC_BM);
   const int num_super = (num_tiles + G - 1) / G;
   const unsigned kmask = p.K >= 32 ? 0xffffffffu : ((1u << p.K) - 1u);
@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
 
   if (threadIdx.x == 0) {
     for (uint32_t s = 0; s < nst; ++s) {
-      mbar_init(full0 + 8 * s, V8_GROUP_WARPS + 1);  // one arrival per warp of the owning producer group + the weight thread
+      mbar_init(full0 + 8 * s, V8_GROUP_WARPS * 32 + 1);  // every thread of the owning producer group (async, when its copies land) + the weight thread
       mbar_init(empty0 + 8 * s, G);                  // one tcgen05.commit per sub-tile (from the issuer that owns the stage)
     }
     for (int b = 0; b < 2; ++b) {
@@ -366,7 +366,8 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
             if (i + 1 < n) d_next = pl->stage[i + 1];  // off the critical path: read before the wait
             if (g == 0) TSG_TRACE(5, n_mma);
             TSG_STATE(pl->tile, n, i, n_mma);
-            mbar_wait(full0 + 8 * slot, phase);  // producers fenced their writes towards the async proxy before arriving
+            mbar_wait(full0 + 8 * slot, phase);  // the gathered rows (cp.async, generic proxy) and the weight slice have landed
+            fence_async_proxy();                 // ... order them before this thread's tensor-core (async proxy) reads
             tc_fence_after();
             if (g == 0) TSG_TRACE(2, n_mma);
             if (act) {  // every slice is a full 64-channel block: four K = 16 MMAs
@@ -515,7 +516,7 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
     uint32_t dst_off[V8_Q];                       // row 8 rsub + q sits at chunk position chunk ^ q of its 128-byte line
 #pragma unroll
     for (int q = 0; q < V8_Q; ++q) dst_off[q] = b_bytes + (uint32_t)(rsub * V8_Q + q) * 128u + (uint32_t)((chunk ^ q) << 4);
-    const uint32_t ibuf = idx0 + (uint32_t)pw * idx_warp_bytes;
+    const uint32_t ibuf = idx0 + (uint32_t)pw * 2u * idx_warp_bytes;  // double buffered
     const uint32_t rb0 = (uint32_t)p.c0 * 2u, rb1 = (uint32_t)p.c1 * 2u;
     const char *in0 = reinterpret_cast<const char *>(p.in0);
     const char *in1 = reinterpret_cast<const char *>(p.in1);
@@ -606,24 +607,38 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
                        nbr + (long long)k * nbr_stride + (long long)st * G * TC_BM + g * TC_BM + wg * 32 + piece * 4, 16u);
         }
       };
-      // Per stage: read the indices, wait for the slot, issue the copies, then (while they are in flight) find the
-      // group's next stage and request its index lines; cp.async.wait_all covers both, the writes are fenced towards
-      // the async proxy (the tensor core reads them) and each warp arrives once on the stage's full barrier.
-      // (An asynchronous hand-off — cp.async.mbarrier.arrive.noinc per thread and the proxy fence on the MMA thread —
-      // was 5 % faster but lost arrivals intermittently on the packed-slice layers; profiles/README.md.)
+      // Nothing in this loop waits for gathered rows to land: a slot stays occupied only from the first copy to the
+      // MMA's commit, and the (long, latency-bound) search for the next stage overlaps the landing without delaying the
+      // hand-off.  Each thread's copies of a stage are followed by cp.async.mbarrier.arrive.noinc on the stage's full
+      // barrier (the arrival fires when they have landed; the MMA thread issues the generic->async proxy fence after
+      // its wait).  Commit groups per thread, in order: idx(n), rows(n-1), idx(n+1), rows(n); cp.async.wait_group 2 at
+      // the top of iteration n guarantees idx(n).  The look-ahead never blocks on the plan ring (see advance_mine): if
+      // the next plan is not published yet, the stage in hand is issued first and the look-ahead is redone, blocking.
       uint32_t slot = (uint32_t)grp, phase = 0;  // ring position of this group's next stage (always NG stages further)
       int n_issued = 0;
-      View cur;
+      uint32_t ib = 0;                           // which half of the warp's index buffer holds the current stage
+      View cur, nxt;
       bool have = advance_mine(true) == 1;
       if (have) {
         locate(cur);
         prefetch_idx(ibuf);
-        asm volatile("cp.async.wait_all;" ::: "memory");
-        __syncwarp();
       }
+      nxt = cur;
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.commit_group;" ::: "memory");  // stands in for rows(-1)
       while (have) {
+        __syncwarp();  // every lane has read the indices that lived in the other half of the buffer
+        int r = advance_mine(false);
+        if (r == 1) {
+          locate(nxt);
+          prefetch_idx(ibuf + (ib ^ 1u) * idx_warp_bytes);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (pw == 0 && lane == 0) TSG_TRACE(7, n_issued);
+        asm volatile("cp.async.wait_group 2;" ::: "memory");
+        __syncwarp();
         int idx[G][V8_Q];  // neighbour row of tile row 8 rsub + q, or -1
-        const uint32_t ibase = ibuf + cur.ioff;
+        const uint32_t ibase = ibuf + ib * idx_warp_bytes + cur.ioff;
 #pragma unroll
         for (int g = 0; g < G; ++g) {
           if ((cur.kbits >> g) & 1u) {
@@ -656,36 +671,29 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
             }
           }
         }
+        cp_async_arrive(full0 + 8 * slot);  // fires once this thread's copies (all of them so far) have landed
+        asm volatile("cp.async.commit_group;" ::: "memory");
         if (pw == 0 && lane == 0) TSG_TRACE(6, n_issued);
-        int r = advance_mine(false);
-        if (r == 1) {
-          locate(cur);
-          __syncwarp();  // every lane has read the current stage's indices out of the buffer
-          prefetch_idx(ibuf);
-        }
-        if (pw == 0 && lane == 0) TSG_TRACE(7, n_issued);
-        asm volatile("cp.async.wait_all;" ::: "memory");
-        fence_async_proxy();  // generic-proxy writes -> visible to the async proxy (tensor core reads)
-        __syncwarp();
-        if (lane == 0) mbar_arrive(full0 + 8 * slot);
         if (pw == 0 && lane == 0) TSG_TRACE(1, n_issued);
-        if (r == 2) {  // the next plan was not there yet: now that nothing is owed, wait for it
-          r = advance_mine(true);
-          if (r == 1) {
-            locate(cur);
-            prefetch_idx(ibuf);
-            asm volatile("cp.async.wait_all;" ::: "memory");
-            __syncwarp();
-          }
-        }
-        have = r == 1;
         ++n_issued;
         slot += NG;
         if (slot >= nst) {
           slot -= nst;
           phase ^= 1;
         }
+        if (r == 2) {  // the next plan was not there yet: nothing is owed any more, so wait for it now
+          r = advance_mine(true);
+          if (r == 1) {
+            locate(nxt);
+            prefetch_idx(ibuf + (ib ^ 1u) * idx_warp_bytes);
+          }
+          asm volatile("cp.async.wait_all;" ::: "memory");
+        }
+        cur = nxt;
+        ib ^= 1u;
+        have = r == 1;
       }
+      asm volatile("cp.async.wait_all;" ::: "memory");
     }
   }
 
@@ -846,7 +854,7 @@ int tsg_conv_fwd_tc(const void *in0, int c0, const void *in1, int c1, int64_t n_
   p.ksmax = sp.ksmax;
   // dynamic shared memory: 1 KB alignment slack + stages + epilogue staging + the producers' index buffers
   const size_t b_bytes = (size_t)c_out * 128, stage_bytes = b_bytes + (size_t)G * TC_A_BYTES;
-  const size_t fixed = 1024 + (size_t)V8_EPI_WARPS * V8_STG_BYTES + (size_t)V8_PROD_WARPS * sp.ksmax * G * 128;
+  const size_t fixed = 1024 + (size_t)V8_EPI_WARPS * V8_STG_BYTES + (size_t)V8_PROD_WARPS * 2 * sp.ksmax * G * 128;
   int stages = (int)((V8_DYN_SMEM - fixed) / stage_bytes);
   if (stages > V8_MAX_STAGES) stages = V8_MAX_STAGES;
 #ifdef TSG_TC_TRACE

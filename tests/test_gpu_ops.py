@@ -297,6 +297,16 @@ def test_conv_tensor_core(ts, c0, c1, c_out, ks):
     assert err < 1e-2, (err, n)
 
 
+@pytest.mark.parametrize("c0,span", [(16, 160), (32, 160), (32, 60), (96, 160)])
+def test_conv_tensor_core_many_light_tiles(ts, c0, span):
+    """Hundreds of super tiles per SM-wave with only one or two pipeline stages each (two sub-tiles per CTA, packed K
+    slices, plans turning over faster than stages): the shape on which conv_tc v9 dead-locked, because a producer
+    waited for the next plan while it still owed an arrival on a full barrier."""
+    for rep in range(2):
+        err, n = _tc_case(900 + c0 + rep, 100000, c0, 0, 32, 3, True, rep == 1, torch.bfloat16, span)
+        assert n > 2 * 148 * 256 and err < 2e-2, (err, n)
+
+
 def test_backend_mirror(ts, golden):
     from taseg_b200 import backend as B
     g = golden("ops_kat")
