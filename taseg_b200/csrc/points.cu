@@ -102,12 +102,19 @@ __global__ void agg_warp_kernel(const float *__restrict__ pts, int c_in, const t
       mn[0] = fminf(mn[0], w.x); mn[1] = fminf(mn[1], w.y); mn[2] = fminf(mn[2], w.z);
     }
   }
-  if (f.is_cur) {
+  if (f.is_cur) {  // one atomic per block and axis: per-warp atomics on the same few words serialise in the L2
+    __shared__ float s_mn[8][3];
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
       float v = mn[j];
       for (int s = 16; s; s >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, s));
-      if ((threadIdx.x & 31) == 0 && v < __int_as_float(0x7f800000)) atomic_min_float(&ws[f.sample].cur_min[j], v);
+      if ((threadIdx.x & 31) == 0) s_mn[threadIdx.x >> 5][j] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+      float v = s_mn[0][threadIdx.x];
+      for (int w = 1; w < (int)(blockDim.x >> 5); ++w) v = fminf(v, s_mn[w][threadIdx.x]);
+      if (v < __int_as_float(0x7f800000)) atomic_min_float(&ws[f.sample].cur_min[threadIdx.x], v);
     }
   }
 }
@@ -136,6 +143,7 @@ __global__ void agg_quant_kernel(const float *__restrict__ feats, int c_out, con
       mx[0] = max(mx[0], qx); mx[1] = max(mx[1], qy); mx[2] = max(mx[2], qz);
     }
   }
+  __shared__ int s_mn[8][3], s_mx[8][3];  // one atomic pair per block and axis (see agg_warp_kernel)
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
     int v = mn[j], u = mx[j];
@@ -143,9 +151,21 @@ __global__ void agg_quant_kernel(const float *__restrict__ feats, int c_out, con
       v = min(v, __shfl_xor_sync(0xffffffffu, v, s));
       u = max(u, __shfl_xor_sync(0xffffffffu, u, s));
     }
-    if ((threadIdx.x & 31) == 0 && v != 0x7fffffff) {
-      atomicMin(&ws[f.sample].ms_min[j], v);
-      atomicMax(&ws[f.sample].ms_max[j], u);
+    if ((threadIdx.x & 31) == 0) {
+      s_mn[threadIdx.x >> 5][j] = v;
+      s_mx[threadIdx.x >> 5][j] = u;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    int v = s_mn[0][threadIdx.x], u = s_mx[0][threadIdx.x];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
+      v = min(v, s_mn[w][threadIdx.x]);
+      u = max(u, s_mx[w][threadIdx.x]);
+    }
+    if (v != 0x7fffffff) {
+      atomicMin(&ws[f.sample].ms_min[threadIdx.x], v);
+      atomicMax(&ws[f.sample].ms_max[threadIdx.x], u);
     }
   }
 }
@@ -193,7 +213,9 @@ __global__ void __launch_bounds__(256) cp_write_kernel(const uint8_t *__restrict
                                                        const int *__restrict__ blockoff, const uint32_t *rows_a, int wa,
                                                        uint32_t *out_a, const uint32_t *rows_b, int wb, uint32_t *out_b,
                                                        int *pos_out) {
-  const int64_t base = (int64_t)blockIdx.x * CP_ROWS + threadIdx.x * 4;
+  __shared__ int s_pos[CP_ROWS];  // destination row of each of the block's rows, or -1
+  const int64_t row0 = (int64_t)blockIdx.x * CP_ROWS;
+  const int64_t base = row0 + threadIdx.x * 4;
   bool k[4];
   int c = 0;
 #pragma unroll
@@ -204,15 +226,24 @@ __global__ void __launch_bounds__(256) cp_write_kernel(const uint8_t *__restrict
   int pos = block_exclusive_scan<256>(c, nullptr) + blockoff[blockIdx.x];
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
-    const int64_t i = base + r;
-    if (i >= n) break;
-    if (pos_out) pos_out[i] = k[r] ? pos : -1;
-    if (k[r]) {
-      if (rows_a) for (int j = 0; j < wa; ++j) out_a[(int64_t)pos * wa + j] = rows_a[i * wa + j];
-      if (rows_b) for (int j = 0; j < wb; ++j) out_b[(int64_t)pos * wb + j] = rows_b[i * wb + j];
-      ++pos;
-    }
+    s_pos[threadIdx.x * 4 + r] = k[r] ? pos : -1;
+    if (base + r < n && pos_out) pos_out[base + r] = k[r] ? pos : -1;
+    pos += k[r] ? 1 : 0;
   }
+  __syncthreads();
+  // the block's rows are one contiguous span of words: consecutive threads move consecutive words, and since kept
+  // rows stay in order the writes are (piecewise) contiguous as well
+  const int rows_here = (int)(n - row0 < CP_ROWS ? n - row0 : CP_ROWS);
+  if (rows_a)
+    for (int w = threadIdx.x; w < rows_here * wa; w += 256) {
+      const int r = w / wa, d = s_pos[r];
+      if (d >= 0) out_a[(int64_t)d * wa + (w - r * wa)] = rows_a[row0 * wa + w];
+    }
+  if (rows_b)
+    for (int w = threadIdx.x; w < rows_here * wb; w += 256) {
+      const int r = w / wb, d = s_pos[r];
+      if (d >= 0) out_b[(int64_t)d * wb + (w - r * wb)] = rows_b[row0 * wb + w];
+    }
 }
 
 __global__ void gather_rows_kernel(const uint32_t *__restrict__ src, int width, const int *__restrict__ idx, int64_t n,
