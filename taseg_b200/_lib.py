@@ -76,7 +76,13 @@ def ptr(t):
     return t
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def stream() -> ctypes.c_void_p:
+    """torch's current CUDA stream of the current device as a raw cudaStream_t (every kernel is launched on it)."""
+    if _raw_stream is not None:      # one C call instead of building a torch.cuda.Stream object per launch
+        return ctypes.c_void_p(_raw_stream(torch.cuda.current_device()))
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 

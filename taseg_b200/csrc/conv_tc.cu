@@ -62,7 +62,8 @@ constexpr int V8_STG_BYTES = 32 * V8_STG_PITCH;  // 2560
 constexpr int V8_DYN_SMEM = 221 * 1024;          // dynamic shared memory requested per CTA
 
 // What the planner publishes per super tile: the tile, the offset masks of its G tiles and the list of pipeline stages
-// (stage = bits 0-4 virtual offset kv, 5-8 slice j, 9-10 which sub-tiles multiply this slice).
+// (stage = bits 0-4 virtual offset kv, 5-8 slice j, 9-10 which sub-tiles multiply this slice, 11-12 it is the first
+// such stage of the super tile for sub-tile 0 / 1).
 struct __align__(16) Plan {
   int tile, n;
   unsigned mask[2];
@@ -191,7 +192,7 @@ __device__ __forceinline__ void epi_block(const TcParams &p, uint32_t taddr, boo
 template <int G>
 __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[2 * V8_MAX_STAGES + 4 + 2 * V8_PLAN_SLOTS];
+  __shared__ __align__(8) uint64_t bars[2 * V8_MAX_STAGES + 4 + 2 * V8_PLAN_SLOTS + 2];
   __shared__ Plan plans[V8_PLAN_SLOTS];
   __shared__ uint32_t tmem_base_slot;
   __shared__ __align__(16) float bias_s[256];
@@ -215,6 +216,7 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
   const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[V8_MAX_STAGES]);
   const uint32_t tfull0 = smem_u32(&bars[2 * V8_MAX_STAGES]), tempty0 = tfull0 + 16;
   const uint32_t sfull0 = tfull0 + 32, sempty0 = sfull0 + 8 * V8_PLAN_SLOTS;
+  const uint32_t obar0 = sempty0 + 8 * V8_PLAN_SLOTS;                // issue-order hand-off between the two MMA issuers (G == 1)
 
   if (threadIdx.x == 0) {
     for (uint32_t s = 0; s < nst; ++s) {
@@ -222,8 +224,9 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
       mbar_init(empty0 + 8 * s, G);                  // one tcgen05.commit per sub-tile (from the issuer that owns the stage)
     }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(tfull0 + 8 * b, G);
+      mbar_init(tfull0 + 8 * b, 2);                  // both MMA warps commit once per super tile
       mbar_init(tempty0 + 8 * b, V8_EPI_WARPS * 32);
+      mbar_init(obar0 + 8 * b, 1);
     }
     for (int s = 0; s < V8_PLAN_SLOTS; ++s) {
       mbar_init(sfull0 + 8 * s, 1);
@@ -333,72 +336,94 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
       if (threadIdx.x == 0) TSG_TRACE(11, it);
     }
   } else if (warp == V8_MMA_WARP || warp == V8_MMA_WARP + 1) {
-    // ================================================================= MMA issuers (one thread per sub-tile)
-    // Issuing a tcgen05.mma costs the issuing thread ~60 cycles and a tcgen05.commit ~150 whatever the MMA's size
-    // (tools/micro/mma_issue.cu, profiles/README.md): each of the G sub-tiles gets its own issuing warp, and the loop
-    // runs in one lane.
-    const int g = warp - V8_MMA_WARP;
+    // ================================================================= MMA issuers
+    // One thread needs ~900 cycles per stage (barrier wait + proxy fence ~200, four tcgen05.mma + commit ~470, loop
+    // ~230: traces in profiles/README.md), whatever the MMA's size.  G = 2: one issuer per sub-tile, each walks every
+    // stage.  G = 1: the two warps ALTERNATE stages of the one sub-tile, so waits, fences and commits of consecutive
+    // stages overlap; the MMAs themselves stay in stage order through a hand-off — the issuer of stage s executes
+    // tcgen05.fence::before_thread_sync and arrives on an mbarrier, the issuer of s + 1 waits for it and executes
+    // tcgen05.fence::after_thread_sync — so accumulation order (and the result) is the same as with one issuer.
+    const int mw = warp - V8_MMA_WARP;
     if (lane == 0) {
-      if (g < G) {
-        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.c_out >> 3) << 17) | ((TC_BM >> 4) << 24);
-        const uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);   // SBO 1024 B, version 1, SWIZZLE_128B
-        const uint32_t desc_lo_stage = stage_bytes >> 4;
-        const uint32_t b_lo0 = ((smem_base & 0x3FFFFu) >> 4) | (1u << 16);          // LBO field = 1 (ignored for swizzled K-major)
-        const uint32_t a_lo0 = b_lo0 + (b_bytes >> 4) + g * (TC_A_BYTES >> 4);
-        uint32_t slot = 0, phase = 0, it = 0;
-        int n_mma = 0;
-        for (;; ++it) {
-          const volatile Plan *pl = plan_wait();
-          if (pl->tile < 0) {
-            plan_release_lane();
-            break;
+      const int g = G == 2 ? mw : 0;
+      const int step = G == 2 ? 1 : 2;
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.c_out >> 3) << 17) | ((TC_BM >> 4) << 24);
+      const uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);   // SBO 1024 B, version 1, SWIZZLE_128B
+      const uint32_t desc_lo_stage = stage_bytes >> 4;
+      const uint32_t b_lo0 = ((smem_base & 0x3FFFFu) >> 4) | (1u << 16);          // LBO field = 1 (ignored for swizzled K-major)
+      const uint32_t a_lo0 = b_lo0 + (b_bytes >> 4) + g * (TC_A_BYTES >> 4);
+      const bool tracer = mw == 0;
+      uint32_t slot0 = 0, phase0 = 0, it = 0;  // ring position of the super tile's first stage
+      uint32_t gpar = 0;                       // parity of its global stage number
+      uint32_t mine = 0;                       // stages this thread has issued (G == 1: its k-th stage is global stage 2 k + mw)
+      int n_mma = 0;
+      for (;; ++it) {
+        const volatile Plan *pl = plan_wait();
+        if (pl->tile < 0) {
+          plan_release_lane();
+          break;
+        }
+        const int n = pl->n;
+        const uint32_t buf = it & 1, ph = (it >> 1) & 1;
+        mbar_wait(tempty0 + 8 * buf, ph ^ 1);
+        tc_fence_after();
+        if (tracer) TSG_TRACE(8, it);
+        const uint32_t d_tmem = tmem_base + (buf * G + g) * (uint32_t)p.c_out;
+        const int i0 = G == 2 ? 0 : (int)((mw ^ gpar) & 1u);
+        uint32_t slot = slot0 + i0, phase = phase0;
+        if (slot >= nst) {
+          slot -= nst;
+          phase ^= 1;
+        }
+        unsigned d_next = i0 < n ? pl->stage[i0] : 0u;
+        for (int i = i0; i < n; i += step) {
+          const unsigned d = d_next;
+          if (i + step < n) d_next = pl->stage[i + step];  // off the critical path: read before the wait
+          const bool act = ((d >> (9 + g)) & 1u) && !TSG_DBG(4);
+          if (tracer) TSG_TRACE(5, n_mma);
+          TSG_STATE(pl->tile, n, i, n_mma);
+          mbar_wait(full0 + 8 * slot, phase);  // the gathered rows (cp.async, generic proxy) and the weight slice have landed
+          fence_async_proxy();                 // ... order them before this thread's tensor-core (async proxy) reads
+          if (G == 1 && (mine | mw)) {         // every stage but global stage 0 follows the other issuer's previous stage
+            const uint32_t k = mw ? mine : mine - 1;
+            mbar_wait(obar0 + 8 * (mw ^ 1), k & 1);
           }
-          const int n = pl->n;
-          const uint32_t buf = it & 1, ph = (it >> 1) & 1;
-          mbar_wait(tempty0 + 8 * buf, ph ^ 1);
           tc_fence_after();
-          if (g == 0) TSG_TRACE(8, it);
-          const uint32_t d_tmem = tmem_base + (buf * G + g) * (uint32_t)p.c_out;
-          uint32_t started = 0;
-          unsigned d_next = n > 0 ? pl->stage[0] : 0u;
-          for (int i = 0; i < n; ++i) {
-            const bool act = ((d_next >> (9 + g)) & 1u) && !TSG_DBG(4);
-            if (i + 1 < n) d_next = pl->stage[i + 1];  // off the critical path: read before the wait
-            if (g == 0) TSG_TRACE(5, n_mma);
-            TSG_STATE(pl->tile, n, i, n_mma);
-            mbar_wait(full0 + 8 * slot, phase);  // the gathered rows (cp.async, generic proxy) and the weight slice have landed
-            fence_async_proxy();                 // ... order them before this thread's tensor-core (async proxy) reads
-            tc_fence_after();
-            if (g == 0) TSG_TRACE(2, n_mma);
-            if (act) {  // every slice is a full 64-channel block: four K = 16 MMAs
-              const uint32_t b_lo = b_lo0 + slot * desc_lo_stage, a_lo = a_lo0 + slot * desc_lo_stage;
-              umma_bf16(d_tmem, make_desc(a_lo, desc_hi), make_desc(b_lo, desc_hi), idesc, started);
-              umma_bf16(d_tmem, make_desc(a_lo + 2, desc_hi), make_desc(b_lo + 2, desc_hi), idesc, 1u);
-              umma_bf16(d_tmem, make_desc(a_lo + 4, desc_hi), make_desc(b_lo + 4, desc_hi), idesc, 1u);
-              umma_bf16(d_tmem, make_desc(a_lo + 6, desc_hi), make_desc(b_lo + 6, desc_hi), idesc, 1u);
-              started = 1;
-            }
-            umma_commit(empty0 + 8 * slot);  // this warp's share of "stage consumed" (arrives once its MMAs have read it)
-            if (g == 0) TSG_TRACE(3, n_mma);
-            ++n_mma;
-            if (++slot == nst) {
-              slot = 0;
-              phase ^= 1;
-            }
+          if (tracer) TSG_TRACE(2, n_mma);
+          if (act) {  // every slice is a full 64-channel block: four K = 16 MMAs
+            const uint32_t b_lo = b_lo0 + slot * desc_lo_stage, a_lo = a_lo0 + slot * desc_lo_stage;
+            umma_bf16(d_tmem, make_desc(a_lo, desc_hi), make_desc(b_lo, desc_hi), idesc, ((d >> (11 + g)) & 1u) ^ 1u);
+            umma_bf16(d_tmem, make_desc(a_lo + 2, desc_hi), make_desc(b_lo + 2, desc_hi), idesc, 1u);
+            umma_bf16(d_tmem, make_desc(a_lo + 4, desc_hi), make_desc(b_lo + 4, desc_hi), idesc, 1u);
+            umma_bf16(d_tmem, make_desc(a_lo + 6, desc_hi), make_desc(b_lo + 6, desc_hi), idesc, 1u);
           }
-          umma_commit(tfull0 + 8 * buf);  // this sub-tile's accumulator is complete (immediately if there was no work)
-          if (g == 0) TSG_TRACE(9, it);
+          if (G == 1) {
+            tc_fence_before();
+            mbar_arrive(obar0 + 8 * mw);       // the other issuer may issue the next stage
+          }
+          umma_commit(empty0 + 8 * slot);      // "stage consumed" (arrives once the MMAs have read it)
+          if (tracer) TSG_TRACE(3, n_mma);
+          ++n_mma;
+          ++mine;
+          slot += step;
+          if (slot >= nst) {
+            slot -= nst;
+            phase ^= 1;
+          }
+        }
+        umma_commit(tfull0 + 8 * buf);  // this issuer's share of the accumulator is complete (immediately if it had no stage)
+        if (tracer) TSG_TRACE(9, it);
 #ifdef TSG_TC_TRACE
-          if (g == 0 && (p.dbg & 128) && blockIdx.x == 0 && it < TRACE_N) g_trace[12][it] = n;
+        if (tracer && (p.dbg & 128) && blockIdx.x == 0 && it < TRACE_N) g_trace[12][it] = n;
 #endif
-          plan_release_lane();
+        // ring position and parity of the next super tile's first stage
+        gpar ^= (uint32_t)n & 1u;
+        slot0 += (uint32_t)n;
+        while (slot0 >= nst) {
+          slot0 -= nst;
+          phase0 ^= 1;
         }
-      } else {
-        for (;;) {  // spare MMA warp (G == 1): keep the plan ring moving
-          const int st = plan_wait()->tile;
-          plan_release_lane();
-          if (st < 0) break;
-        }
+        plan_release_lane();
       }
     }
     __syncwarp();
@@ -472,10 +497,27 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
       }
       int pos = incl - __popc(sl);
       Plan *pl = &plans[w.slot];
+      // first stage of the super tile that multiplies sub-tile 0 / 1: its first MMA overwrites the accumulator
+      int f0 = 0x7fffffff, f1 = 0x7fffffff;
+      {
+        int q = pos;
+        for (unsigned rest = sl; rest; rest &= rest - 1, ++q) {
+          const unsigned need = need_of(__ffs(rest) - 1);
+          if ((g0 & need) && f0 == 0x7fffffff) f0 = q;
+          if ((g1 & need) && f1 == 0x7fffffff) f1 = q;
+        }
+      }
+#pragma unroll
+      for (int d = 16; d; d >>= 1) {
+        f0 = min(f0, __shfl_xor_sync(0xffffffffu, f0, d));
+        f1 = min(f1, __shfl_xor_sync(0xffffffffu, f1, d));
+      }
       for (unsigned rest = sl; rest; rest &= rest - 1) {
         const int j = __ffs(rest) - 1;
         const unsigned need = need_of(j);
-        pl->stage[pos++] = (unsigned short)(lane | (j << 5) | ((g0 & need) ? 1u << 9 : 0u) | ((g1 & need) ? 1u << 10 : 0u));
+        pl->stage[pos] = (unsigned short)(lane | (j << 5) | ((g0 & need) ? 1u << 9 : 0u) | ((g1 & need) ? 1u << 10 : 0u) |
+                                          (pos == f0 ? 1u << 11 : 0u) | (pos == f1 ? 1u << 12 : 0u));
+        ++pos;
       }
       const int n_total = __shfl_sync(0xffffffffu, incl, 31);
       TSG_STATE(st, n_total, t, (int)w.slot);

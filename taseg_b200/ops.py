@@ -437,7 +437,7 @@ _SCHED = {}
 
 def _sched_ws(device) -> torch.Tensor:
     """Two zeroed int32 per (device, stream) for the convolution's dynamic tile scheduler (the kernel re-zeroes them)."""
-    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    key = (device, stream().value)
     t = _SCHED.get(key)
     if t is None:
         t = _SCHED[key] = torch.zeros(2, dtype=torch.int32, device=device)
