@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
   if (threadIdx.x == 0) {
     for (uint32_t s = 0; s < nst; ++s) {
       mbar_init(full0 + 8 * s, V8_GROUP_WARPS * 32 + 1);  // every thread of the owning producer group (async, when its copies land) + the weight thread
-      mbar_init(empty0 + 8 * s, G);                  // one tcgen05.commit per sub-tile (from the issuer that owns the stage)
+      mbar_init(empty0 + 8 * s, 1);                  // one tcgen05.commit, from the issuer that owns the stage
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull0 + 8 * b, 2);                  // both MMA warps commit once per super tile
@@ -338,24 +338,22 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
   } else if (warp == V8_MMA_WARP || warp == V8_MMA_WARP + 1) {
     // ================================================================= MMA issuers
     // One thread needs ~900 cycles per stage (barrier wait + proxy fence ~200, four tcgen05.mma + commit ~470, loop
-    // ~230: traces in profiles/README.md), whatever the MMA's size.  G = 2: one issuer per sub-tile, each walks every
-    // stage.  G = 1: the two warps ALTERNATE stages of the one sub-tile, so waits, fences and commits of consecutive
-    // stages overlap; the MMAs themselves stay in stage order through a hand-off — the issuer of stage s executes
-    // tcgen05.fence::before_thread_sync and arrives on an mbarrier, the issuer of s + 1 waits for it and executes
-    // tcgen05.fence::after_thread_sync — so accumulation order (and the result) is the same as with one issuer.
+    // ~230: traces in profiles/README.md) whatever the MMA's size, and that was the per-stage floor of v13.  The two
+    // MMA warps therefore ALTERNATE stages (each issues the MMAs of all G sub-tiles of its stage), so waits, fences
+    // and commits of consecutive stages overlap.  The MMAs stay in stage order through a hand-off: the issuer of stage s
+    // executes tcgen05.fence::before_thread_sync and arrives on an mbarrier, the issuer of s + 1 waits for it and
+    // executes tcgen05.fence::after_thread_sync — accumulation order, and the result, are those of a single issuer.
     const int mw = warp - V8_MMA_WARP;
     if (lane == 0) {
-      const int g = G == 2 ? mw : 0;
-      const int step = G == 2 ? 1 : 2;
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.c_out >> 3) << 17) | ((TC_BM >> 4) << 24);
       const uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);   // SBO 1024 B, version 1, SWIZZLE_128B
       const uint32_t desc_lo_stage = stage_bytes >> 4;
       const uint32_t b_lo0 = ((smem_base & 0x3FFFFu) >> 4) | (1u << 16);          // LBO field = 1 (ignored for swizzled K-major)
-      const uint32_t a_lo0 = b_lo0 + (b_bytes >> 4) + g * (TC_A_BYTES >> 4);
+      const uint32_t a_lo0 = b_lo0 + (b_bytes >> 4);
       const bool tracer = mw == 0;
       uint32_t slot0 = 0, phase0 = 0, it = 0;  // ring position of the super tile's first stage
       uint32_t gpar = 0;                       // parity of its global stage number
-      uint32_t mine = 0;                       // stages this thread has issued (G == 1: its k-th stage is global stage 2 k + mw)
+      uint32_t mine = 0;                       // stages this thread has issued: its k-th stage is global stage 2 k + mw
       int n_mma = 0;
       for (;; ++it) {
         const volatile Plan *pl = plan_wait();
@@ -368,50 +366,52 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
         mbar_wait(tempty0 + 8 * buf, ph ^ 1);
         tc_fence_after();
         if (tracer) TSG_TRACE(8, it);
-        const uint32_t d_tmem = tmem_base + (buf * G + g) * (uint32_t)p.c_out;
-        const int i0 = G == 2 ? 0 : (int)((mw ^ gpar) & 1u);
+        const uint32_t d_tmem = tmem_base + buf * G * (uint32_t)p.c_out;
+        const int i0 = (int)((mw ^ gpar) & 1u);
         uint32_t slot = slot0 + i0, phase = phase0;
         if (slot >= nst) {
           slot -= nst;
           phase ^= 1;
         }
         unsigned d_next = i0 < n ? pl->stage[i0] : 0u;
-        for (int i = i0; i < n; i += step) {
+        for (int i = i0; i < n; i += 2) {
           const unsigned d = d_next;
-          if (i + step < n) d_next = pl->stage[i + step];  // off the critical path: read before the wait
-          const bool act = ((d >> (9 + g)) & 1u) && !TSG_DBG(4);
+          if (i + 2 < n) d_next = pl->stage[i + 2];  // off the critical path: read before the wait
           if (tracer) TSG_TRACE(5, n_mma);
           TSG_STATE(pl->tile, n, i, n_mma);
           mbar_wait(full0 + 8 * slot, phase);  // the gathered rows (cp.async, generic proxy) and the weight slice have landed
           fence_async_proxy();                 // ... order them before this thread's tensor-core (async proxy) reads
-          if (G == 1 && (mine | mw)) {         // every stage but global stage 0 follows the other issuer's previous stage
+          if (mine | mw) {                     // every stage but global stage 0 follows the other issuer's previous stage
             const uint32_t k = mw ? mine : mine - 1;
             mbar_wait(obar0 + 8 * (mw ^ 1), k & 1);
           }
           tc_fence_after();
           if (tracer) TSG_TRACE(2, n_mma);
-          if (act) {  // every slice is a full 64-channel block: four K = 16 MMAs
-            const uint32_t b_lo = b_lo0 + slot * desc_lo_stage, a_lo = a_lo0 + slot * desc_lo_stage;
-            umma_bf16(d_tmem, make_desc(a_lo, desc_hi), make_desc(b_lo, desc_hi), idesc, ((d >> (11 + g)) & 1u) ^ 1u);
-            umma_bf16(d_tmem, make_desc(a_lo + 2, desc_hi), make_desc(b_lo + 2, desc_hi), idesc, 1u);
-            umma_bf16(d_tmem, make_desc(a_lo + 4, desc_hi), make_desc(b_lo + 4, desc_hi), idesc, 1u);
-            umma_bf16(d_tmem, make_desc(a_lo + 6, desc_hi), make_desc(b_lo + 6, desc_hi), idesc, 1u);
+          const uint32_t b_lo = b_lo0 + slot * desc_lo_stage;
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            if (!((d >> (9 + g)) & 1u) || TSG_DBG(4)) continue;
+            // every slice is a full 64-channel block: four K = 16 MMAs per sub-tile
+            const uint32_t a_lo = a_lo0 + slot * desc_lo_stage + g * (TC_A_BYTES >> 4);
+            const uint32_t dt = d_tmem + g * (uint32_t)p.c_out;
+            umma_bf16(dt, make_desc(a_lo, desc_hi), make_desc(b_lo, desc_hi), idesc, ((d >> (11 + g)) & 1u) ^ 1u);
+            umma_bf16(dt, make_desc(a_lo + 2, desc_hi), make_desc(b_lo + 2, desc_hi), idesc, 1u);
+            umma_bf16(dt, make_desc(a_lo + 4, desc_hi), make_desc(b_lo + 4, desc_hi), idesc, 1u);
+            umma_bf16(dt, make_desc(a_lo + 6, desc_hi), make_desc(b_lo + 6, desc_hi), idesc, 1u);
           }
-          if (G == 1) {
-            tc_fence_before();
-            mbar_arrive(obar0 + 8 * mw);       // the other issuer may issue the next stage
-          }
+          tc_fence_before();
+          mbar_arrive(obar0 + 8 * mw);         // the other issuer may issue the next stage
           umma_commit(empty0 + 8 * slot);      // "stage consumed" (arrives once the MMAs have read it)
           if (tracer) TSG_TRACE(3, n_mma);
           ++n_mma;
           ++mine;
-          slot += step;
+          slot += 2;
           if (slot >= nst) {
             slot -= nst;
             phase ^= 1;
           }
         }
-        umma_commit(tfull0 + 8 * buf);  // this issuer's share of the accumulator is complete (immediately if it had no stage)
+        umma_commit(tfull0 + 8 * buf);  // this issuer's share of the accumulators is complete (immediately if it had no stage)
         if (tracer) TSG_TRACE(9, it);
 #ifdef TSG_TC_TRACE
         if (tracer && (p.dbg & 128) && blockIdx.x == 0 && it < TRACE_N) g_trace[12][it] = n;
