@@ -1,38 +1,36 @@
 // Sparse convolution on the 5th-generation tensor cores (sm_100a): output-stationary implicit GEMM,
 //   out[row(r),:] = epilogue( sum_k in[nbr[k,r],:] @ W[k] ),   bf16 operands, fp32 accumulation in TMEM.
 //
-// One persistent CTA per SM walks "super tiles" of G x 128 tile rows (G in {1,2}), handed out by an in-kernel dynamic
-// scheduler (heaviest tiles first).  The unit of the shared-memory pipeline is a STAGE = one 64-channel K slice: the
-// pre-swizzled weight slice (c_out x 128 B) plus the G gathered 128 x 64 A tiles that multiply it, behind ONE full /
-// ONE empty mbarrier.  The K dimension is a flat stream of 16-byte chunks (8 channels): all chunks of offset 0 (first
-// source tensor, then the second), then offset 1, ...; a slice is the next 8 chunks of that stream, so every slice is
-// full whatever the channel count: 96 channels -> 3 slices per 2 offsets (not 2 per offset), 96 + 32 concatenated ->
-// 2 slices per offset (not 3), 32 channels -> 2 offsets per slice, 16 -> 4.  The pattern repeats every P = 8 / gcd(C/8, 8)
-// offsets ("virtual offset" kv = k / P) with Q = (C/8) / gcd slices.  Warp roles (768 threads):
-//   warps 0-3   epilogue   tcgen05.ld the G 128 x c_out fp32 accumulators (one TMEM lane quadrant per warp),
-//                          + bias + residual, ReLU, store bf16/fp32 rows (to row perm[r] when tiles are mask-sorted)
-//   warps 4-5   MMA        one issuing thread per sub-tile: tcgen05.mma (M=128, N=c_out, K=16) per 16 input channels,
-//                          tcgen05.commit on the stage's empty barrier; warp 4 owns the TMEM allocation
-//   warp  6     weights    one thread streams the weight slice into the stage with cp.async.bulk (UBLKCP, complete_tx)
-//   warp  7     scheduler  one thread takes super-tile tickets from a global counter and publishes them in a 4-deep
-//                          shared-memory ring read by every other warp (the last CTA to finish re-zeroes the counter)
-//   warps 8-23  producers  4 independent groups of 4 warps; group g fills every 4th stage: it gathers the neighbour rows
-//                          with 16-byte cp.async (LDGSTS, zero-fill for missing neighbours) into the 128B-swizzled K-major
-//                          A tiles, prefetches the indices of its next stage while the rows land, then cp.async.wait_all,
-//                          fence.proxy.async and ONE mbarrier arrival per warp.
-// History (profiles/README.md): v1 paid ~200 producer instructions per 16 KB slot and was bound by producer issue; v3
-// became bound by the single MMA thread's instruction latency; v4 (8 producer warps, 64-bit address arithmetic, static
-// tile striding) was bound by the producers' own dependent instruction chains (~125 SASS instructions per stage per
-// warp, stall_wait) and by a 2x imbalance between SMs.  v5: 16 producer warps with one IMAD.WIDE per copy, slice
-// packing, dynamic scheduling.  Knock-out runs of v5 (TSG_TC_DEBUG=15: no gathers, weights, MMAs or stores) still took
-// the full kernel time: the per-THREAD cp.async.mbarrier.arrive.noinc (513 arrivals per stage on one barrier word) was
-// the bottleneck suspect; arriving once per warp did not help either, and clock64 traces of the hand-offs (TSG_TC_DEBUG
-// bit 128) showed ~600 cycles between consecutive stages of an EMPTY pipeline: with all 16 producer warps taking part in
-// every stage the per-stage bookkeeping (x16 warps) saturates instruction issue and every hand-off is on the critical
-// path.  v6: producer groups own whole stages (hand-shake amortised over 8 G copies per thread, groups overlap).
-// Offsets for which a sub-tile has no neighbour at all are skipped by every role (tile_mask); with rows sorted by
-// their neighbour bit mask (tsg_kmap_sort_rows) that removes more than half of the (tile, offset) work.
-// Accumulators are double buffered in TMEM so the epilogue of super tile t overlaps the mainloop of t+1.
+// One persistent CTA per SM (896 threads) walks "super tiles" of G x 128 tile rows (G in {1,2}).  The unit of the
+// shared-memory pipeline is a STAGE = one 64-channel K slice: the pre-swizzled weight slice (c_out x 128 B) plus the G
+// gathered 128 x 64 A tiles that multiply it, behind ONE full / ONE empty mbarrier.  The K dimension is a flat stream of
+// 16-byte chunks (8 channels): all chunks of offset 0 (first source tensor, then the second), then offset 1, ...; a
+// slice is the next 8 chunks of that stream, so every slice is full whatever the channel count: 96 channels -> 3 slices
+// per 2 offsets (not 2 per offset), 96 + 32 concatenated -> 2 slices per offset (not 3), 32 channels -> 2 offsets per
+// slice, 16 -> 4.  The pattern repeats every P = 8 / gcd(C/8, 8) offsets ("virtual offset" kv = k / P) with
+// Q = (C/8) / gcd slices.  Offsets for which a sub-tile has no neighbour at all are skipped (tile_mask); with rows sorted
+// by their neighbour bit mask (tsg_kmap_sort_rows) that removes about two thirds of the (tile, offset) work.
+// Warp roles:
+//   warps 0-7    epilogue   two sets over the four TMEM lane quadrants: tcgen05.ld the 128 x c_out fp32 accumulators,
+//                           + bias + residual, ReLU, through a padded staging buffer to coalesced 64-byte row segments
+//                           (row perm[r] when tiles are mask-sorted)
+//   warps 8-9    MMA        one issuing thread each, alternating stages, ordered by an mbarrier hand-off: tcgen05.mma
+//                           (M=128, N=c_out, K=16) x 4 x G per stage, tcgen05.commit on the stage's empty barrier;
+//                           warp 8 owns the TMEM allocation
+//   warp  10     weights    one thread streams the weight slice into the stage with cp.async.bulk (UBLKCP, complete_tx)
+//   warp  11     planner    draws super-tile tickets from a global counter (heaviest first) and expands each into a stage
+//                           list {kv, slice, active sub-tiles, first-stage flags} in a 4-slot shared-memory ring
+//   warps 12-27  producers  4 groups of 4 warps, group g fills every 4th stage: neighbour indices arrive as 128-byte
+//                           lines in a private double-buffered buffer (cp.async, one stage ahead); rows are gathered with
+//                           16-byte cp.async (LDGSTS, zero-fill for missing neighbours) into the 128B-swizzled K-major A
+//                           tiles; hand-off by cp.async.mbarrier.arrive.noinc (nothing waits for rows to land)
+// Accumulators are double buffered in TMEM so the epilogue of super tile t overlaps the main loop of t+1.
+// History and measurements (profiles/README.md): v1-v7 were bound, in turn, by producer instruction count, the single MMA
+// thread, per-stage bookkeeping done by all 16 producer warps (~2000 cycles of branchy scalar code per group stage) and a
+// thread-per-row epilogue; v9 moved the stage enumeration into the planner warp, v12 doubled and coalesced the epilogue,
+// v13 made the producer hand-off asynchronous, v14/v15 alternate two MMA issuers.  What bounds v15: shared-memory
+// bandwidth for c_out <= 128 (operand fetch of an MMA is (4096 + 32 N)/128 cycles), L2->SM ingest for the dense small
+// layers, tile quantisation at strides 8/16.
 #include <cstdlib>
 #include <cstring>
 
