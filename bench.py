@@ -43,17 +43,17 @@ def peaks():
     return dict(bf16=1400.0, hbm=6650.0, source="fallback")
 
 
-def make_model(device="cuda"):
+def make_model(device="cuda", if_dist=False):
     import torch
     from taseg_b200.segmentor import MinkUNetMs, ModelCfg
     torch.manual_seed(0)
     cfg = ModelCfg(IN_FEATURE_DIM=5, BLOCK="ResBlock", NUM_LAYER=[2, 3, 4, 6, 2, 2, 2, 2], cr=1.0,
-                   PLANES=[32, 32, 64, 128, 256, 256, 128, 96, 96], pres=0.05, vres=0.05, IF_DIST=False, IGNORE_LABEL=0,
+                   PLANES=[32, 32, 64, 128, 256, 256, 128, 96, 96], pres=0.05, vres=0.05, IF_DIST=bool(if_dist), IGNORE_LABEL=0,
                    DROPOUT_P=0.0)
     model = MinkUNetMs(cfg, 20)
     g = torch.Generator().manual_seed(1)
     for m in model.modules():
-        if isinstance(m, torch.nn.BatchNorm1d):     # non-trivial eval-mode BN
+        if isinstance(m, torch.nn.modules.batchnorm._BatchNorm):     # non-trivial eval-mode BN
             m.running_mean.copy_(torch.randn(m.num_features, generator=g) * 0.1)
             m.running_var.copy_(torch.rand(m.num_features, generator=g) + 0.5)
     return model.to(device).eval()

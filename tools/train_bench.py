@@ -28,13 +28,14 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--batch", type=int, default=2)
+    ap.add_argument("--sync-bn", action="store_true", help="IF_DIST=True: SyncBatchNorm (batch statistics over all ranks, R/pcseg/model/segmentor/voxel/minkunet/minkunet.py:23-25)")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    model = bench.make_model().train()
+    model = bench.make_model(if_dist=args.sync_bn and world > 1).train()
     samples = bench.make_samples(5000 + rank * args.batch, args.batch)
     mfb = frontend.MultiFrameBatch([s[0] for s in samples], [s[1] for s in samples])
     pts = torch.from_numpy(mfb.points).cuda()
@@ -62,7 +63,8 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     ms = parallel.max_over_ranks(e0.elapsed_time(e1) / args.steps, "cuda")
-    check = torch.stack([p.detach().double().sum() for p in model.parameters()]).sum().reshape(1)
+    check = torch.stack([p.detach().double().sum() for p in list(model.parameters()) +
+                         [b for b in model.buffers() if b.dtype.is_floating_point]]).sum().reshape(1)   # parameters + BN running statistics
     spread = 0.0
     if world > 1:
         allc = [torch.zeros_like(check) for _ in range(world)]
@@ -70,7 +72,7 @@ def main():
         spread = float((torch.stack(allc).max() - torch.stack(allc).min()).abs())
     if rank == 0:
         print(json.dumps({"metric": "train step (MinkUNetMs mk34 cr1.0, 3-frame KITTI shape, bf16 autocast)", "n_gpus": world,
-                          "batch_per_gpu": args.batch, "ms_per_step": ms, "scans_per_s": args.batch * world / (ms * 1e-3),
+                          "batch_per_gpu": args.batch, "sync_bn": bool(args.sync_bn and world > 1), "ms_per_step": ms, "scans_per_s": args.batch * world / (ms * 1e-3),
                           "loss": loss, "voxels_per_gpu": int(coords.shape[0]),
                           "allreduce_bytes_per_step": reducer.bytes_per_step(), "buckets": len(reducer.buckets),
                           "param_checksum_spread_over_ranks": spread,
