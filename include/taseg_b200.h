@@ -219,6 +219,11 @@ int tsg_conv_dgrad(const float *grad_out, int64_t n_out, int c_out, const float 
                    const int32_t *nbr_t, int64_t n_in, float *grad_in, tsg_stream_t stream);
 int tsg_conv_wgrad(const float *in, int64_t n_in, int c_in, const float *grad_out, int64_t n_out, int c_out,
                    const int32_t *nbr, int k, float *grad_w, tsg_stream_t stream);
+/* The same weight gradient for the autocast (bf16) training path: bf16 `in` / `grad_out` rows (c_in, c_out multiples of
+ * 8), fp32 accumulation and fp32 grad_w.  Rows that have a neighbour at offset k are compacted into a pair list inside the
+ * kernel, so only the P = sum_k nbsizes[k] real pairs are multiplied (warp-level tensor-core MMAs). */
+int tsg_conv_wgrad_bf16(const void *in, int64_t n_in, int c_in, const void *grad_out, int64_t n_out, int c_out,
+                        const int32_t *nbr, int k, float *grad_w, tsg_stream_t stream);
 
 /* tcgen05/TMEM path (bf16 operands, fp32 accumulate in tensor memory).
  * Weights are packed once per layer into the shared-memory image the MMA consumes (128B-swizzled K-major

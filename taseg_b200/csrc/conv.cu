@@ -2,6 +2,8 @@
 // This is the exact-fp32 path used for parity runs, odd channel counts and training (dgrad/wgrad); the bf16
 // tcgen05/TMEM path lives in conv_tc.cu.  One launch per convolution: rows are gathered straight into shared
 // memory (no gather buffer), all K offsets accumulate in registers (no scatter, no atomics, deterministic).
+#include <mma.h>
+
 #include "common.cuh"
 
 namespace tsg {
@@ -139,6 +141,131 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const float *__restrict
     }
 }
 
+// ---------------------------------------------------------------- weight gradient on the tensor cores (bf16 operands)
+// grad_w[k] (c_in x c_out, fp32) = sum over the pairs (i, o) of offset k of in[i,:]^T gy[o,:].
+// grid = (K, splits, ceil(c_in/128) * ceil(c_out/128)), 256 threads = 8 warps as 4 (ci) x 2 (co), each warp owns a
+// 32 x 64 block of the CTA's 128 x 128 tile = 2 x 4 accumulator fragments (fp32).  The CTA scans its slab of output
+// rows 256 at a time, COMPACTS the rows that have a neighbour at offset k into a pair list in shared memory (warp
+// ballots; order preserved, so sums are deterministic per split) and multiplies 64 pairs at a time:
+//   A = X^T  (ci x pair)  read column-major from Xs[pair][ci],   B = gY (pair x co) read row-major from Gs[pair][co],
+// warp-level bf16 MMAs (mma.sync through the WMMA API — a GEMM whose K dimension is the gathered pair list does not
+// fit the tile-row pipeline of conv_tc.cu; tcgen05 for this kernel is future work).  Partial tiles of the splits are
+// added to grad_w with fp32 atomics.  The fp32 kernel above stays the exact path for parity runs.
+constexpr int WG_TILE = 128, WG_PAIRS = 64, WG_PITCH = WG_TILE + 8;  // +8 bf16: rows 272 B apart, conflict-free fragment loads
+
+__global__ void __launch_bounds__(256) conv_wgrad_bf16_kernel(const __nv_bfloat16 *__restrict__ in, int c_in,
+                                                              const __nv_bfloat16 *__restrict__ gy, int c_out,
+                                                              const int *__restrict__ nbr, int64_t n_out, int splits,
+                                                              int co_tiles, float *__restrict__ gw) {
+  using namespace nvcuda;
+  __shared__ __align__(32) __nv_bfloat16 Xs[WG_PAIRS][WG_PITCH];
+  __shared__ __align__(32) __nv_bfloat16 Gs[WG_PAIRS][WG_PITCH];
+  __shared__ int p_src[WG_PAIRS + 256], p_out[WG_PAIRS + 256];
+  __shared__ int warp_cnt[8];
+  __shared__ __align__(32) float scratch[8][16 * 16];
+  const int k = blockIdx.x, sp = blockIdx.y;
+  const int ci0 = (blockIdx.z / co_tiles) * WG_TILE, co0 = (blockIdx.z % co_tiles) * WG_TILE;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wi = warp >> 1, wj = warp & 1;  // warp's 32 x 64 block: ci tiles 2 wi, 2 wi + 1; co tiles 4 wj .. 4 wj + 3
+  const int64_t rows_per = ((n_out + splits - 1) / splits + 255) / 256 * 256;
+  const int64_t r_begin = sp * rows_per, r_end = min(n_out, r_begin + rows_per);
+  wmma::fragment<wmma::accumulator, 16, 16, 16, float> acc[2][4];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) wmma::fill_fragment(acc[a][b], 0.f);
+
+  // multiply the first `cnt` (<= 64) pairs of the list; rows beyond cnt are zero
+  auto multiply = [&](int cnt) {
+    // gather: 64 pairs x 128 channels of each operand, 16-byte chunks (8 channels), 4 + 4 chunks per thread
+    for (int c = tid; c < WG_PAIRS * (WG_TILE / 8); c += 256) {
+      const int r = c >> 4, q = c & 15;
+      uint4 x = make_uint4(0u, 0u, 0u, 0u), g = make_uint4(0u, 0u, 0u, 0u);
+      if (r < cnt) {
+        if (ci0 + q * 8 < c_in) x = __ldg(reinterpret_cast<const uint4 *>(in + (int64_t)p_src[r] * c_in + ci0 + q * 8));
+        if (co0 + q * 8 < c_out) g = __ldg(reinterpret_cast<const uint4 *>(gy + (int64_t)p_out[r] * c_out + co0 + q * 8));
+      }
+      *reinterpret_cast<uint4 *>(&Xs[r][q * 8]) = x;
+      *reinterpret_cast<uint4 *>(&Gs[r][q * 8]) = g;
+    }
+    __syncthreads();
+    if (ci0 + wi * 32 < c_in && co0 + wj * 64 < c_out) {  // warps whose whole block lies outside the layer skip the math
+#pragma unroll
+      for (int ks = 0; ks < WG_PAIRS; ks += 16) {
+        wmma::fragment<wmma::matrix_a, 16, 16, 16, __nv_bfloat16, wmma::col_major> fa[2];
+        wmma::fragment<wmma::matrix_b, 16, 16, 16, __nv_bfloat16, wmma::row_major> fb[4];
+#pragma unroll
+        for (int a = 0; a < 2; ++a) wmma::load_matrix_sync(fa[a], &Xs[ks][wi * 32 + a * 16], WG_PITCH);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) wmma::load_matrix_sync(fb[b], &Gs[ks][wj * 64 + b * 16], WG_PITCH);
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) wmma::mma_sync(acc[a][b], fa[a], fb[b], acc[a][b]);
+      }
+    }
+    __syncthreads();
+  };
+
+  int count = 0;  // pairs waiting in the list (uniform across the CTA)
+  for (int64_t r0 = r_begin; r0 < r_end; r0 += 256) {
+    const int64_t o = r0 + tid;
+    const int src = o < r_end ? __ldg(nbr + (int64_t)k * n_out + o) : -1;
+    const unsigned bal = __ballot_sync(0xffffffffu, src >= 0);
+    if (lane == 0) warp_cnt[warp] = __popc(bal);
+    __syncthreads();
+    int base = count, total = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      if (w < warp) base += warp_cnt[w];
+      total += warp_cnt[w];
+    }
+    if (src >= 0) {
+      const int pos = base + __popc(bal & ((1u << lane) - 1u));
+      p_src[pos] = src;
+      p_out[pos] = (int)o;
+    }
+    count += total;
+    __syncthreads();
+    while (count >= WG_PAIRS) {
+      multiply(WG_PAIRS);
+      // shift the rest of the list down (multiply() ended with a barrier: nobody reads the old positions any more)
+      const int rest = count - WG_PAIRS;
+      int s0 = -1, s1 = -1;
+      if (tid < rest) {
+        s0 = p_src[WG_PAIRS + tid];
+        s1 = p_out[WG_PAIRS + tid];
+      }
+      __syncthreads();
+      if (tid < rest) {
+        p_src[tid] = s0;
+        p_out[tid] = s1;
+      }
+      count = rest;
+      __syncthreads();
+    }
+  }
+  if (count > 0) multiply(count);
+
+  // add this split's tile to grad_w
+  if (ci0 + wi * 32 < c_in && co0 + wj * 64 < c_out) {
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        wmma::store_matrix_sync(scratch[warp], acc[a][b], 16, wmma::mem_row_major);
+        __syncwarp();
+        const int ci_base = ci0 + wi * 32 + a * 16, co_base = co0 + wj * 64 + b * 16;
+        for (int e = lane; e < 256; e += 32) {
+          const int ci = ci_base + (e >> 4), co = co_base + (e & 15);
+          const float v = scratch[warp][e];
+          if (ci < c_in && co < c_out && v != 0.f) atomicAdd(&gw[((int64_t)k * c_in + ci) * c_out + co], v);
+        }
+        __syncwarp();
+      }
+  }
+}
+
 }  // namespace tsg
 
 using namespace tsg;
@@ -202,6 +329,28 @@ int tsg_conv_wgrad(const float *in, int64_t n_in, int c_in, const float *grad_ou
   dim3 grid((unsigned)(k * splits), (unsigned)((c_in + 31) / 32), (unsigned)((c_out + 31) / 32));
   conv_wgrad_kernel<<<grid, 256, 0, stream>>>(in, c_in, grad_out, c_out, nbr, n_out, splits, grad_w);
   return check_launch("tsg_conv_wgrad");
+}
+
+/* bf16 operands (c_in, c_out multiples of 8), fp32 grad_w: the autocast training path. */
+int tsg_conv_wgrad_bf16(const void *in, int64_t n_in, int c_in, const void *grad_out, int64_t n_out, int c_out,
+                        const int32_t *nbr, int k, float *grad_w, tsg_stream_t stream) {
+  (void)n_in;
+  if (c_in % 8 || c_out % 8 || c_in <= 0 || c_out <= 0) {
+    set_error("tsg_conv_wgrad_bf16: c_in and c_out must be multiples of 8");
+    return TSG_ERR_UNSUPPORTED;
+  }
+  TSG_CUDA(cudaMemsetAsync(grad_w, 0, (size_t)k * c_in * c_out * sizeof(float), stream));
+  if (n_out <= 0 || k <= 0) return TSG_OK;
+  const int ci_tiles = (c_in + WG_TILE - 1) / WG_TILE, co_tiles = (c_out + WG_TILE - 1) / WG_TILE;
+  int splits = (int)((3LL * num_sms() + (int64_t)k * ci_tiles * co_tiles - 1) / ((int64_t)k * ci_tiles * co_tiles));
+  const int64_t max_splits = (n_out + 2047) / 2048;
+  if (splits > max_splits) splits = (int)max_splits;
+  if (splits < 1) splits = 1;
+  if (splits > 65535) splits = 65535;
+  dim3 grid((unsigned)k, (unsigned)splits, (unsigned)(ci_tiles * co_tiles));
+  conv_wgrad_bf16_kernel<<<grid, 256, 0, stream>>>((const __nv_bfloat16 *)in, c_in, (const __nv_bfloat16 *)grad_out, c_out,
+                                                   nbr, n_out, splits, co_tiles, grad_w);
+  return check_launch("tsg_conv_wgrad_bf16");
 }
 
 }  // extern "C"

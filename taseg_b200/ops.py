@@ -398,6 +398,17 @@ def conv_wgrad(feats: torch.Tensor, grad_out: torch.Tensor, nbr: torch.Tensor, k
     return gw
 
 
+def conv_wgrad_bf16(feats: torch.Tensor, grad_out: torch.Tensor, nbr: torch.Tensor, k: int) -> torch.Tensor:
+    """Weight gradient of the autocast path: bf16 rows in, fp32 (K, c_in, c_out) out (tensor-core MMAs over the real pairs)."""
+    feats = feats.to(torch.bfloat16).contiguous()
+    grad_out = grad_out.to(torch.bfloat16).contiguous()
+    c_in, c_out = feats.shape[1], grad_out.shape[1]
+    gw = torch.empty((k, c_in, c_out), dtype=torch.float32, device=feats.device)
+    call("tsg_conv_wgrad_bf16", ptr(feats), feats.shape[0], c_in, ptr(grad_out), grad_out.shape[0], c_out, ptr(nbr), k, ptr(gw),
+         stream())
+    return gw
+
+
 def pad16(c: int) -> int:
     return (c + 15) // 16 * 16
 

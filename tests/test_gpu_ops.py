@@ -307,6 +307,26 @@ def test_conv_tensor_core_many_light_tiles(ts, c0, span):
         assert n > 2 * 148 * 256 and err < 2e-2, (err, n)
 
 
+@pytest.mark.parametrize("c_in,c_out,ks,n", [(96, 96, 3, 30000), (16, 32, 3, 30000), (256, 256, 3, 6000), (128, 96, 2, 20000),
+                                             (40, 24, 3, 500)])
+def test_conv_wgrad_bf16(ts, c_in, c_out, ks, n):
+    """Tensor-core weight gradient (bf16 rows, in-kernel pair compaction) against the exact fp32 kernel on the same
+    bf16-representable inputs: both accumulate the same fp32 products, only the summation order differs."""
+    from taseg_b200 import ops
+    rng = np.random.default_rng(c_in + c_out)
+    c = np.unique(rng.integers(0, 36, (n, 3)).astype(np.int32), axis=0)
+    c = np.concatenate([c, np.zeros((len(c), 1), np.int32)], 1)
+    offs = T.get_kernel_offsets(ks, 1)
+    km = ops.build_kmap(ops.Table.from_coords(cu(c)), len(c), cu(c), offs)
+    x = torch.randn(len(c), c_in, device="cuda").bfloat16()
+    gy = torch.randn(len(c), c_out, device="cuda").bfloat16()
+    got = ops.conv_wgrad_bf16(x, gy, km.nbr, len(offs))
+    want = ops.conv_wgrad(x.float(), gy.float(), km.nbr, len(offs))
+    torch.cuda.synchronize()
+    assert got.shape == want.shape == (len(offs), c_in, c_out)
+    assert rel_err(npy(got), npy(want)) < 1e-4
+
+
 def test_backend_mirror(ts, golden):
     from taseg_b200 import backend as B
     g = golden("ops_kat")
