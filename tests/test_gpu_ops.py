@@ -137,6 +137,35 @@ def test_kernel_maps_and_convs(ts, golden):
     assert rel_err(npy(b.F), g["conv_out3"] + 1) < 1e-3
 
 
+@pytest.mark.parametrize("stride,ks,tstride", [((2, 2, 1), (2, 2, 1), 1), (2, 3, 1), ((2, 2, 1), 3, 1), ((2, 2, 1), 3, (2, 2, 1)),
+                                               ((1, 2, 2), (3, 1, 3), 1), (1, (3, 1, 3), 1)])
+def test_anisotropic_and_expanding_convs(ts, stride, ks, tstride):
+    """Cylinder3D-style geometries: anisotropic kernels / strides and the offset-expansion branch of
+    spdownsample — coarse coordinates and kernel maps bit-exact, features within fp32 tolerance of the oracle."""
+    from taseg_b200 import SparseTensor
+    from taseg_b200.nn import functional as F
+    from taseg_b200.utils import make_ntuple
+    rng = np.random.default_rng(11)
+    tsn = make_ntuple(tstride, 3)
+    c = np.unique(rng.integers(0, 28, (4000, 3)).astype(np.int32), axis=0) * np.asarray(tsn, np.int32)
+    c = np.concatenate([c, rng.integers(0, 2, (len(c), 1)).astype(np.int32)], 1)
+    c = c[np.lexsort((c[:, 2], c[:, 1], c[:, 0], c[:, 3]))]
+    feats = rng.normal(size=(len(c), 8)).astype(np.float32)
+    kvol = int(np.prod(make_ntuple(ks, 3)))
+    w = (rng.normal(size=(kvol, 8, 16)) * 0.2).astype(np.float32)
+    x = SparseTensor(cu(feats), cu(c), tsn)
+    y = F.conv3d(x, cu(w), ks, stride=stride)
+    strided = any(v != 1 for v in make_ntuple(stride, 3))
+    out_c = T.spdownsample(c, stride, ks, tstride) if strided else c
+    assert np.array_equal(npy(y.C), out_c)
+    assert y.s == tuple(a * b for a, b in zip(tsn, make_ntuple(stride, 3)))
+    nbmaps, nbsizes = T.build_kmap(c, out_c, ks, tsn)
+    nb, ns, sz = x.kmaps[(tsn, make_ntuple(ks, 3), make_ntuple(stride, 3), (1, 1, 1))]
+    assert np.array_equal(npy(nb), nbmaps) and np.array_equal(npy(ns), nbsizes) and sz == (len(c), len(out_c))
+    want = T.conv_forward(feats, w, nbmaps, nbsizes, (len(c), len(out_c)))
+    assert rel_err(npy(y.F), want) < 1e-3
+
+
 def test_conv_backward(ts, golden):
     from taseg_b200 import SparseTensor
     from taseg_b200.nn import functional as F

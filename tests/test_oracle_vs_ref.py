@@ -65,3 +65,45 @@ def test_network_on_reference_backend(golden):
     sd = {k[3:]: g[k] for k in g.files if k.startswith("sd/")}
     a = N.Net(sd, ops=RB.RefOps).spvcnn(g["coords"], g["feats"])
     assert rel_err(a[::4], g["voxel_logits"]) < 1e-4
+
+
+def _reference_downsample():
+    """spdownsample of the reference, executed from its own source inside package/torchsparse.zip (with the two helper
+    modules it imports) — no torchsparse install needed."""
+    import os
+    import types
+    import zipfile
+    zpath = "/root/reference/package/torchsparse.zip"
+    if not os.path.exists(zpath):
+        pytest.skip("reference tree only exists in the build container")
+    z = zipfile.ZipFile(zpath)
+
+    def src(suffix):
+        return z.read([x for x in z.namelist() if x.endswith(suffix)][0]).decode()
+    utils = types.ModuleType("ref_utils")
+    exec(src("torchsparse/utils/utils.py"), utils.__dict__)
+    kern = types.ModuleType("ref_kernel")
+    kern.__dict__["make_ntuple"] = utils.make_ntuple
+    exec(src("torchsparse/nn/utils/kernel.py").replace("from torchsparse.utils import make_ntuple", ""), kern.__dict__)
+    ds = types.ModuleType("ref_downsample")
+    ds.__dict__.update(get_kernel_offsets=kern.get_kernel_offsets, make_ntuple=utils.make_ntuple)
+    exec(src("nn/functional/downsample.py").replace("from torchsparse.nn.utils import get_kernel_offsets", "")
+         .replace("from torchsparse.utils import make_ntuple", ""), ds.__dict__)
+    return ds.spdownsample, utils.make_ntuple
+
+
+DOWNSAMPLE_CASES = [(2, 2, 1), ((2, 2, 1), (2, 2, 1), 1), (2, 3, 1), ((2, 2, 1), 3, 1), ((2, 2, 1), 3, (2, 2, 1)), (2, 3, 2),
+                    ((1, 2, 2), (3, 1, 3), 1)]
+
+
+@pytest.mark.parametrize("stride,ks,ts", DOWNSAMPLE_CASES)
+def test_spdownsample_all_branches(stride, ks, ts):
+    """Truncation branch (isotropic and anisotropic) and the offset-expansion branch (Cylinder3D's kernel 3 / stride
+    (2,2,1)) of the oracle against the reference's own function."""
+    import torch
+    ref, ntuple = _reference_downsample()
+    rng = np.random.default_rng(7)
+    c = np.unique(rng.integers(0, 24, (3000, 3)).astype(np.int32), axis=0) * np.asarray(ntuple(ts, 3), np.int32)
+    c = np.concatenate([c, rng.integers(0, 2, (len(c), 1)).astype(np.int32)], 1)
+    want = ref(torch.from_numpy(c), stride, ks, ts).numpy()
+    assert np.array_equal(T.spdownsample(c, stride, ks, ts), want)
