@@ -63,19 +63,20 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     ms = parallel.max_over_ranks(e0.elapsed_time(e1) / args.steps, "cuda")
-    check = torch.stack([p.detach().double().sum() for p in list(model.parameters()) +
-                         [b for b in model.buffers() if b.dtype.is_floating_point]]).sum().reshape(1)   # parameters + BN running statistics
-    spread = 0.0
+    check = torch.stack([torch.stack([p.detach().double().sum() for p in model.parameters()]).sum(),
+                         torch.stack([b.double().sum() for b in model.buffers() if b.dtype.is_floating_point]).sum()])
+    spread, bn_spread = 0.0, 0.0      # parameters / BN running statistics (the latter differ by design without --sync-bn)
     if world > 1:
         allc = [torch.zeros_like(check) for _ in range(world)]
         dist.all_gather(allc, check)
-        spread = float((torch.stack(allc).max() - torch.stack(allc).min()).abs())
+        allc = torch.stack(allc)
+        spread, bn_spread = [float(v) for v in (allc.max(dim=0).values - allc.min(dim=0).values).abs()]
     if rank == 0:
         print(json.dumps({"metric": "train step (MinkUNetMs mk34 cr1.0, 3-frame KITTI shape, bf16 autocast)", "n_gpus": world,
                           "batch_per_gpu": args.batch, "sync_bn": bool(args.sync_bn and world > 1), "ms_per_step": ms, "scans_per_s": args.batch * world / (ms * 1e-3),
                           "loss": loss, "voxels_per_gpu": int(coords.shape[0]),
                           "allreduce_bytes_per_step": reducer.bytes_per_step(), "buckets": len(reducer.buckets),
-                          "param_checksum_spread_over_ranks": spread,
+                          "param_checksum_spread_over_ranks": spread, "bn_running_stat_spread_over_ranks": bn_spread,
                           "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}))
     if world > 1:
         dist.destroy_process_group()
