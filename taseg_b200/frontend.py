@@ -57,5 +57,45 @@ def aggregate_voxelize(points: torch.Tensor, batch: MultiFrameBatch, voxel_size:
                 pos=pos, field_bits=bits)
 
 
+def aggregate_voxelize_nus(samples: Sequence[Sequence[torch.Tensor]], Rs: Sequence[Sequence[np.ndarray]],
+                           Ts: Sequence[Sequence[np.ndarray]], dts: Sequence[Sequence[float]], voxel_size: float):
+    """nuScenes multi-sweep front end (BASELINE configs[3]) on the device, for a batch of samples.
+    samples[b][k] (N_k, 5) fp32 device tensor [x, y, z, intensity, .] in sweep k's own frame (k = 0: key frame);
+    Rs/Ts[b][k] float64 with p_key = p_k @ R + T; dts[b][k] seconds.  Per sweep, as
+    R/pcseg/data/dataset/nuscenes/nuscenes_ms.py:284-341: the ego box |x| < 1 & |y| < 1.5 is tested on the RAW points,
+    dt goes to column 4, the sweep is warped in fp64 (`transform_point`, :348-373), then filtered.  Then the loader's
+    clamp / round / shift / sparse_quantize (nuscenes_voxel_ms.py:122-160 = the SemanticKITTI one) per sample, collated.
+    Returns the same dict as aggregate_voxelize (coords (M,4) [x,y,z,b], feats (M,5), inverse, cur_rows, point_ms, pc_ms, inds)."""
+    pts_all, pc_all, n_cur, cur_off = [], [], [], []
+    off = 0
+    for b, sweeps in enumerate(samples):
+        parts = []
+        for k, s in enumerate(sweeps):
+            s = s.float()
+            no_ego = ~((s[:, 0].abs() < 1.0) & (s[:, 1].abs() < 1.5))
+            s = s.clone()
+            s[:, 4] = float(dts[b][k])
+            if k > 0:
+                s = ops.transform_point(s, Rs[b][k], Ts[b][k])
+            parts.append(s[no_ego])
+        cur = parts[0]
+        ms = torch.cat(parts, 0)
+        mn = cur[:, :3].amin(dim=0)
+        ms = ms[(ms[:, 0] >= mn[0]) & (ms[:, 1] >= mn[1]) & (ms[:, 2] >= mn[2])]      # clamp to the key frame's min corner
+        pc = torch.round(ms[:, :3] / voxel_size).to(torch.int32)                       # fp32 divide, round half to even
+        pc = pc - pc.amin(dim=0, keepdim=True)
+        pts_all.append(ms)
+        pc_all.append(torch.cat([pc, torch.full((pc.shape[0], 1), b, dtype=torch.int32, device=pc.device)], 1))
+        n_cur.append(int(cur.shape[0]))                                                # key-frame points come first and all survive the clamp
+        cur_off.append(off)
+        off += ms.shape[0]
+    point_ms, pc_ms = torch.cat(pts_all, 0).contiguous(), torch.cat(pc_all, 0).contiguous()
+    vox, first, inverse = ops.unique_coords(pc_ms, want_index=True, want_inverse=True)
+    vfeat = ops.gather_rows(point_ms, first)
+    cur_idx = torch.cat([torch.arange(o, o + n, device=pc_ms.device) for o, n in zip(cur_off, n_cur)])
+    return dict(coords=vox, feats=vfeat, inverse=inverse, cur_rows=inverse[cur_idx], point_ms=point_ms, pc_ms=pc_ms, inds=first,
+                n_cur=n_cur)
+
+
 def as_lidar_ms(out: dict) -> SparseTensor:
     return SparseTensor(out["feats"], out["coords"], 1)

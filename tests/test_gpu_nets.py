@@ -118,6 +118,48 @@ def test_frontend_matches_reference_loader(golden):
     assert hashlib.sha256(out["point_ms"].cpu().numpy().tobytes()).hexdigest() != ""   # (N',5) clamped ms cloud
 
 
+def test_nuscenes_frontend_and_forward():
+    """BASELINE configs[3] shape (10 sweeps, 0.1 m voxels, IN_FEATURE_DIM 4, 17 classes): the device front end against
+    the data oracle (nuscenes_ms.py aggregation + the voxel loader), then bf16 engine vs fp32 module path."""
+    from taseg_b200 import frontend, synth
+    from taseg_b200.engine import Engine
+    from taseg_b200.segmentor import MinkUNetMs, ModelCfg
+    spec = synth.SensorSpec(16, -30.67, 10.67, 400, 1.84, 60.0)
+    batch = [synth.nus_sample(4000 + b, 10, spec=spec, n_boxes=30) for b in range(2)]
+    out = frontend.aggregate_voxelize_nus([[cu(s) for s in smp[0]] for smp in batch], [smp[1] for smp in batch],
+                                          [smp[2] for smp in batch], [smp[3] for smp in batch], 0.1)
+    pts = out["point_ms"].cpu().numpy()
+    row = 0
+    want_c, want_f, n_vox = [], [], 0
+    for b, (sweeps, Rs, Ts, dts) in enumerate(batch):
+        ms, n0 = D.aggregate_nus(sweeps, Rs, Ts, dts)
+        q = D.quantize_ms(ms[:n0], ms, 0.1)
+        n = len(q["point_ms"])
+        mine = pts[row:row + n]
+        assert mine.shape == q["point_ms"].shape and out["n_cur"][b] == n0
+        assert (mine.view(np.uint32) != q["point_ms"].view(np.uint32)).mean() < 1e-5          # fp64 warp, last-bit rounding at most
+        # the integer pipeline is bit-exact on identical points: re-run the oracle's quantisation on OUR warped points
+        q2 = D.quantize_ms(mine[:n0], mine, 0.1)
+        want_c.append(np.concatenate([q2["pc_ms"], np.full((len(q2["pc_ms"]), 1), b, np.int32)], 1))
+        want_f.append(q2["feat_ms"])
+        assert np.array_equal(out["inverse"].cpu().numpy()[row:row + n], q2["inverse_map_ms"] + n_vox)
+        n_vox += len(q2["pc_ms"])
+        row += n
+    assert np.array_equal(out["coords"].cpu().numpy(), np.concatenate(want_c))
+    assert np.array_equal(out["feats"].cpu().numpy().view(np.uint32), np.concatenate(want_f).view(np.uint32))
+    torch.manual_seed(0)
+    cfg = ModelCfg(IN_FEATURE_DIM=4, BLOCK="ResBlock", NUM_LAYER=[1, 1, 1, 1, 1, 1, 1, 1], cr=0.25, pres=0.1, vres=0.1,
+                   IF_DIST=False, IGNORE_LABEL=0, DROPOUT_P=0.0)
+    model = MinkUNetMs(cfg, 17).cuda().eval()
+    with torch.no_grad():
+        l32 = model.logits(frontend.as_lidar_ms(out)).cpu().numpy()
+    l16 = Engine(model)(out["coords"], out["feats"], out_rows=out["cur_rows"]).cpu().numpy()
+    want = l32[out["cur_rows"].cpu().numpy()]
+    assert l16.shape == (sum(out["n_cur"]), 17)
+    l2, agree = bf16_ok(l16, want)
+    assert l2 < 3e-2 and agree > 0.99, (l2, agree)
+
+
 def test_batched_forward_equals_per_sample(golden):
     """Batch index is a coordinate: a collated batch must give each sample the logits it gets alone (eval BN)."""
     from taseg_b200 import frontend, synth
