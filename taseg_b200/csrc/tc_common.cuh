@@ -31,9 +31,6 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
 // Spin on an mbarrier phase.  try_wait suspends the thread in hardware for a bounded time, so the loop is not hot;
 // the watchdog reads the cheap SM cycle counter (never %globaltimer, whose read costs ~1 us) once per 4096 failed
 // polls and traps after ~2^33 cycles (~4 s): a protocol bug must fail loudly, never hang the GPU.
@@ -120,31 +117,6 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,"
-      "%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// zero 16 accumulator columns of this warp's 32 TMEM lanes (complete after tcgen05.wait::st)
-__device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr), "r"(0u)
-               : "memory");
-}
-__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): rows of 128 B, 8-row groups
-// 1024 B apart (SBO), version 1, layout type 2.  `addr` may be advanced by 32 B per K=16 step inside the row.
-__device__ __forceinline__ uint64_t umma_desc(uint32_t addr) {
-  return (uint64_t)((addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
-}
-
 struct TcParams {
   const __nv_bfloat16 *in0, *in1;
   int c0, c1;
@@ -211,50 +183,6 @@ __device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
       else if (now - t0 > (1ll << 33)) __trap();
 #endif
     }
-  }
-}
-
-// Epilogue for 16 consecutive output channels of one row: + bias, + residual (bf16), ReLU, store bf16 or fp32.
-__device__ __forceinline__ void epilogue_store16(const TcParams &p, long long row, int c, const uint32_t (&v)[16]) {
-  float f[16];
-#pragma unroll
-  for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
-  if (p.bias) {
-    const float4 *bp = reinterpret_cast<const float4 *>(p.bias + c);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float4 b = __ldg(bp + j);
-      f[4 * j] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
-    }
-  }
-  if (p.residual) {
-    const uint4 *rp = reinterpret_cast<const uint4 *>(p.residual + row * p.c_out + c);
-    const uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
-    const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      f[2 * j] += __uint_as_float(rw[j] << 16);
-      f[2 * j + 1] += __uint_as_float(rw[j] & 0xffff0000u);
-    }
-  }
-  if (p.relu) {
-#pragma unroll
-    for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
-  }
-  if (p.out_f32) {
-    float4 *op = reinterpret_cast<float4 *>(reinterpret_cast<float *>(p.out) + row * p.c_out + c);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-  } else {
-    uint32_t w[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-      w[j] = *reinterpret_cast<const uint32_t *>(&h);
-    }
-    uint4 *op = reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(p.out) + row * p.c_out + c);
-    op[0] = make_uint4(w[0], w[1], w[2], w[3]);
-    op[1] = make_uint4(w[4], w[5], w[6], w[7]);
   }
 }
 
