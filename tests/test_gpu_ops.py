@@ -318,7 +318,8 @@ def _tc_case(seed, n, c0, c1, c_out, ks, relu, residual, out_dtype, dense_span):
 
 
 @pytest.mark.parametrize("c0,c1,c_out,ks", [(16, 0, 32, 3), (32, 0, 32, 3), (64, 0, 64, 3), (96, 32, 96, 3), (128, 0, 128, 3),
-                                            (256, 128, 256, 3), (32, 0, 32, 2), (128, 64, 128, 1), (256, 0, 256, 3)])
+                                            (256, 128, 256, 3), (32, 0, 32, 2), (128, 64, 128, 1), (256, 0, 256, 3),
+                                            (16, 0, 256, 3)])   # last: 3 pipeline stages < 4 producer groups
 def test_conv_tensor_core(ts, c0, c1, c_out, ks):
     err, n = _tc_case(c0 + c_out, 30000, c0, c1, c_out, ks, True, True, torch.bfloat16, 40)
     assert err < 2e-2, (err, n)
