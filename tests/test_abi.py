@@ -88,3 +88,21 @@ def test_collate_and_containers():
     assert s.kmaps is out["lidar"].kmaps and s.cmaps is out["lidar"].cmaps and float(s.F.sum()) == 20.0
     z = taseg_b200.PointTensor(torch.zeros(2, 2), torch.zeros(2, 4))
     assert z.additional_features == {"idx_query": {}, "counts": {}} and (z + z).idx_query is z.idx_query
+
+
+def test_slice_plan_host_logic():
+    """K-slice packing of the tensor-core convolution (host arithmetic only, no device call): the flat chunk stream of a
+    layer with C = c0 + c1 input channels repeats every P = 8 / gcd(C/8, 8) offsets with Q = (C/8) / gcd 64-channel slices,
+    so the packed weights hold ceil(K / P) * Q blocks of c_out x 64 bf16."""
+    from math import gcd
+    from taseg_b200 import _lib
+    L = _lib.lib()
+    for k, c0, c1, c_out in [(27, 96, 0, 96), (27, 96, 32, 96), (27, 32, 0, 32), (27, 16, 0, 32), (8, 64, 0, 64), (27, 256, 128, 256),
+                             (1, 128, 64, 128), (27, 48, 0, 80), (9, 128, 0, 16)]:
+        cpo = (c0 + c1) // 8
+        g = gcd(cpo, 8)
+        p, q = 8 // g, cpo // g
+        want = -(-k // p) * q * c_out * 64 * 2
+        assert L.tsg_conv_pack_bytes(k, c0, c1, c_out) == want, (k, c0, c1, c_out)
+        # every slice is full: the blocks cover exactly ceil(K/P)*P offsets x C channels
+        assert -(-k // p) * q * 64 == -(-k // p) * p * (c0 + c1)
