@@ -19,7 +19,7 @@ from .blocks import BLOCKS, BasicConvolutionBlock, BasicDeconvolutionBlock, norm
 from .utils import initial_voxelize, point_to_voxel, voxel_to_point
 from .. import nn as spnn
 
-__all__ = ['MinkUNet', 'MinkUNetMs', 'SPVCNN', 'ModelCfg']
+__all__ = ['MinkUNet', 'MinkUNetMs', 'MinkUNetMsKd', 'SPVCNN', 'ModelCfg']
 
 DEFAULT_PLANES = [32, 32, 64, 128, 256, 256, 128, 96, 96]
 
@@ -93,37 +93,43 @@ class _SparseUNet(nn.Module):
                 picked[key] = value
         return self.load_state_dict(picked, strict=strict)
 
-    def backbone(self, x, z):
-        """x: input SparseTensor (voxels), z: PointTensor -> per-point (or per-voxel for Ms) logits."""
+    def features(self, x, z, sfx: str = ''):
+        """x: input SparseTensor (voxels), z: PointTensor -> the concatenated multi-scale point features the classifier
+        reads.  `sfx` selects a second set of backbone modules (`stem_gt`, ... of the distillation model)."""
+        m = (lambda name: getattr(self, name + sfx)) if sfx else (lambda name: getattr(self, name))
         spv = self.point_branch
-        x0 = self.stem(x)
+        x0 = m('stem')(x)
         z0 = voxel_to_point(x0, z, nearest=False)
-        x1 = self.stage1(point_to_voxel(x0, z0) if spv else x0)
-        x2 = self.stage2(x1)
-        x3 = self.stage3(x2)
-        x4 = self.stage4(x3)
+        x1 = m('stage1')(point_to_voxel(x0, z0) if spv else x0)
+        x2 = m('stage2')(x1)
+        x3 = m('stage3')(x2)
+        x4 = m('stage4')(x3)
         z1 = voxel_to_point(x4, z0)
         if spv:
             z1.F = z1.F + self.point_transforms[0](z0.F)
             y1 = point_to_voxel(x4, z1)
         else:
             y1 = x4
-        y1.F = self.dropout(y1.F)
-        y1 = self.up1[1](cat([self.up1[0](y1), x3]))
-        y2 = self.up2[1](cat([self.up2[0](y1), x2]))
+        y1.F = m('dropout')(y1.F)
+        y1 = m('up1')[1](cat([m('up1')[0](y1), x3]))
+        y2 = m('up2')[1](cat([m('up2')[0](y1), x2]))
         z2 = voxel_to_point(y2, z1)
         if spv:
             z2.F = z2.F + self.point_transforms[1](z1.F)
             y3 = point_to_voxel(y2, z2)
         else:
             y3 = y2
-        y3.F = self.dropout(y3.F)
-        y3 = self.up3[1](cat([self.up3[0](y3), x1]))
-        y4 = self.up4[1](cat([self.up4[0](y3), x0]))
+        y3.F = m('dropout')(y3.F)
+        y3 = m('up3')[1](cat([m('up3')[0](y3), x1]))
+        y4 = m('up4')[1](cat([m('up4')[0](y3), x0]))
         z3 = voxel_to_point(y4, z2)
         if spv:
             z3.F = z3.F + self.point_transforms[2](z2.F)
-        return self.classifier(torch.cat([z1.F, z2.F, z3.F], dim=1))
+        return torch.cat([z1.F, z2.F, z3.F], dim=1)
+
+    def backbone(self, x, z):
+        """x: input SparseTensor (voxels), z: PointTensor -> per-point (or per-voxel for Ms) logits."""
+        return self.classifier(self.features(x, z))
 
     def logits(self, lidar):
         lidar.F = lidar.F[:, :self.in_feature_dim]
@@ -174,6 +180,65 @@ class MinkUNet(_SparseUNet):
 class MinkUNetMs(_SparseUNet):
     voxelize_input = False
     lidar_key, inverse_key = 'lidar_ms', 'inverse_map_ms'
+
+
+class MinkUNetMsKd(MinkUNetMs):
+    """TASeg's distillation segmentor (R/pcseg/model/segmentor/voxel/minkunet/minkunet_ms_kd.py:200-666): a frozen
+    teacher backbone — modules `stem_gt`, `stage1_gt` .. `up4_gt`, `classifier_gt`, `dropout_gt`, fed `lidar_ms_gt` (the
+    multi-frame cloud aggregated with ground-truth FSA masks) — next to the student backbone on `lidar_ms`.  Training adds
+    an MSE feature-distillation term on the voxels both inputs contain: student rows are matched to teacher rows with
+    sphash / sphashquery (:613-615), per sample at most MAX_VOXEL matched voxels are drawn (SAMPLING_TYPE 'random',
+    :617-633; other sampling types add nothing in the reference either).  Eval is the student's (:637-666).
+    Module names, hence state_dict keys, are the reference's."""
+    TWIN = ('stem', 'stage1', 'stage2', 'stage3', 'stage4', 'up1', 'up2', 'up3', 'up4', 'classifier', 'dropout')
+
+    def __init__(self, model_cfgs, num_class: int, criterion: Optional[Callable] = None):
+        super().__init__(model_cfgs, num_class, criterion)
+        teacher = MinkUNetMs(model_cfgs, num_class)
+        for name in self.TWIN:
+            setattr(self, name + '_gt', getattr(teacher, name))
+        self.sampling_type = model_cfgs.get('SAMPLING_TYPE', 'uncertain')
+        self.max_voxel = model_cfgs.get('MAX_VOXEL', 3000)
+        self.feat_kd_weight = model_cfgs.get('FEAT_KD_WEIGHT', 1.0)
+
+    def teacher_features(self, batch_dict):
+        with torch.no_grad():
+            x_gt = batch_dict['lidar_ms_gt']
+            x_gt.F = x_gt.F[:, :self.in_feature_dim]
+            return x_gt, self.features(x_gt, PointTensor(x_gt.F, x_gt.C.float()), '_gt')
+
+    def distillation_loss(self, x, feat, x_gt, feat_gt):
+        """MSE between the student's and the (detached) teacher's point features on the voxels they share."""
+        from ..nn import functional as F
+        s2d = F.sphashquery(F.sphash(x.C.int()), F.sphash(x_gt.C.int()))
+        loss = feat.new_zeros(())
+        if self.sampling_type != 'random':
+            return loss, s2d
+        batch_size = int(x.C[:, -1].max().item()) + 1
+        for b in range(batch_size):
+            mask = (s2d >= 0) & (x.C[:, -1] == b)
+            if int(mask.sum().item()) > self.max_voxel:
+                inds = mask.nonzero().reshape(-1)
+                mask = mask.clone()
+                mask[inds[torch.randperm(len(inds), device=inds.device)][self.max_voxel:]] = False
+            loss = loss + nn.functional.mse_loss(feat[mask], feat_gt[s2d[mask]].detach()) * self.feat_kd_weight / batch_size
+        return loss, s2d
+
+    def forward(self, batch_dict, return_logit=False, return_tta=False):
+        x_gt, feat_gt = self.teacher_features(batch_dict)
+        x = batch_dict['lidar_ms']
+        x.F = x.F[:, :self.in_feature_dim]
+        feat = self.features(x, PointTensor(x.F, x.C.float()))
+        out = self.classifier(feat)
+        if not self.training:
+            return self.eval_outputs(batch_dict, x, out, return_logit or return_tta)
+        target = batch_dict['targets_ms'].F.long().cuda(non_blocking=True)
+        crit = self.criterion or (lambda o, t: nn.functional.cross_entropy(o, t, ignore_index=self.model_cfgs.IGNORE_LABEL))
+        loss_seg = crit(out, target)
+        loss_kd, _ = self.distillation_loss(x, feat, x_gt, feat_gt)
+        loss = loss_seg + loss_kd
+        info = {'loss': loss.item(), 'loss_seg': loss_seg.item(), 'loss_feat_kd': float(loss_kd)}
+        return {'loss': loss}, dict(info), dict(info)
 
 
 class SPVCNN(_SparseUNet):

@@ -106,3 +106,18 @@ def test_slice_plan_host_logic():
         assert L.tsg_conv_pack_bytes(k, c0, c1, c_out) == want, (k, c0, c1, c_out)
         # every slice is full: the blocks cover exactly ceil(K/P)*P offsets x C channels
         assert -(-k // p) * q * 64 == -(-k // p) * p * (c0 + c1)
+
+
+def test_kd_model_state_dict_matches_reference():
+    """MinkUNetMsKd mirror: parameter / buffer names and shapes are those of the reference model (the fixture holds the
+    reference's own state_dict, tests/golden/make_golden_kd.py), so reference checkpoints load."""
+    import os
+    import numpy as np
+    from taseg_b200.segmentor import MinkUNetMsKd, ModelCfg
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "kd.npz"))
+    cfg = ModelCfg(IN_FEATURE_DIM=5, BLOCK="ResBlock", NUM_LAYER=[1, 1, 1, 1, 1, 1, 1, 1], cr=0.125, pres=0.05, vres=0.05,
+                   IF_DIST=False, IGNORE_LABEL=0, DROPOUT_P=0.0, SAMPLING_TYPE="random", MAX_VOXEL=10 ** 9, FEAT_KD_WEIGHT=2.0)
+    mine = {k: tuple(v.shape) for k, v in MinkUNetMsKd(cfg, 20).state_dict().items()}
+    ref = {k[3:]: tuple(g[k].shape) for k in g.files if k.startswith("sd/")}
+    assert mine == ref
+    assert sum(k.startswith("stem_gt.") for k in mine) == sum(k.startswith("stem.") for k in mine) > 0

@@ -160,6 +160,39 @@ def test_nuscenes_frontend_and_forward():
     assert l2 < 3e-2 and agree > 0.99, (l2, agree)
 
 
+def test_kd_twin_backbone(golden):
+    """MinkUNetMsKd in training mode against the unmodified reference (tests/golden/kd.npz): teacher /
+    student point features on the matched voxels, the sphashquery matching (bit-exact) and the distillation loss."""
+    from taseg_b200 import SparseTensor
+    from taseg_b200.segmentor import MinkUNetMsKd, ModelCfg
+    g = golden("kd")
+    cfg = ModelCfg(IN_FEATURE_DIM=5, BLOCK="ResBlock", NUM_LAYER=[1, 1, 1, 1, 1, 1, 1, 1], cr=0.125, pres=0.05, vres=0.05,
+                   IF_DIST=False, IGNORE_LABEL=0, DROPOUT_P=0.0, SAMPLING_TYPE="random", MAX_VOXEL=10 ** 9, FEAT_KD_WEIGHT=2.0)
+    model = MinkUNetMsKd(cfg, 20)
+    model.load_state_dict({k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd/")})
+    model = model.cuda().train()
+    batch = dict(lidar_ms_gt=SparseTensor(cu(g["feats_t"]), cu(g["coords_t"]), 1), lidar_ms=SparseTensor(cu(g["feats_s"]), cu(g["coords_s"]), 1))
+    x_gt, feat_gt = model.teacher_features(batch)
+    x = batch["lidar_ms"]
+    x.F = x.F[:, :5]
+    from taseg_b200 import PointTensor
+    feat = model.features(x, PointTensor(x.F, x.C.float()))
+    loss, s2d = model.distillation_loss(x, feat, x_gt, feat_gt)
+    assert sha(s2d.cpu().numpy(), np.int64) == str(g["s2d_sha"])
+    mask = s2d >= 0
+    assert int(mask.sum()) == int(g["n_matched"])
+    assert rel_err(feat[mask].detach().cpu().numpy()[::8], g["feat_s"]) < 2e-3
+    assert rel_err(feat_gt[s2d[mask]].cpu().numpy()[::8], g["feat_t"]) < 2e-3
+    assert abs(float(loss) - float(g["loss_feat_kd"])) < 2e-3 * float(g["loss_feat_kd"])
+    # the whole training forward (cross-entropy in place of pcseg.loss.Losses) runs and back-propagates into the student only
+    labels = torch.randint(1, 20, (x.C.shape[0],), device="cuda")
+    batch = dict(lidar_ms_gt=SparseTensor(cu(g["feats_t"]), cu(g["coords_t"]), 1), lidar_ms=SparseTensor(cu(g["feats_s"]), cu(g["coords_s"]), 1),
+                 targets_ms=SparseTensor(labels, cu(g["coords_s"]), 1))
+    ret, tb, _ = model(batch)
+    ret["loss"].backward()
+    assert tb["loss_feat_kd"] > 0 and model.stem[0].kernel.grad is not None and model.stem_gt[0].kernel.grad is None
+
+
 def test_batched_forward_equals_per_sample(golden):
     """Batch index is a coordinate: a collated batch must give each sample the logits it gets alone (eval BN)."""
     from taseg_b200 import frontend, synth
