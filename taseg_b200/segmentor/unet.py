@@ -237,7 +237,7 @@ class MinkUNetMsKd(MinkUNetMs):
         loss_seg = crit(out, target)
         loss_kd, _ = self.distillation_loss(x, feat, x_gt, feat_gt)
         loss = loss_seg + loss_kd
-        info = {'loss': loss.item(), 'loss_seg': loss_seg.item(), 'loss_feat_kd': float(loss_kd)}
+        info = {'loss': loss.item(), 'loss_seg': loss_seg.item(), 'loss_feat_kd': float(loss_kd.detach())}
         return {'loss': loss}, dict(info), dict(info)
 
 

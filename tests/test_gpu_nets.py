@@ -183,7 +183,7 @@ def test_kd_twin_backbone(golden):
     assert int(mask.sum()) == int(g["n_matched"])
     assert rel_err(feat[mask].detach().cpu().numpy()[::8], g["feat_s"]) < 2e-3
     assert rel_err(feat_gt[s2d[mask]].cpu().numpy()[::8], g["feat_t"]) < 2e-3
-    assert abs(float(loss) - float(g["loss_feat_kd"])) < 2e-3 * float(g["loss_feat_kd"])
+    assert abs(float(loss.detach()) - float(g["loss_feat_kd"])) < 2e-3 * float(g["loss_feat_kd"])
     # the whole training forward (cross-entropy in place of pcseg.loss.Losses) runs and back-propagates into the student only
     labels = torch.randint(1, 20, (x.C.shape[0],), device="cuda")
     batch = dict(lidar_ms_gt=SparseTensor(cu(g["feats_t"]), cu(g["coords_t"]), 1), lidar_ms=SparseTensor(cu(g["feats_s"]), cu(g["coords_s"]), 1),
