@@ -243,3 +243,18 @@ class Engine:
         x = batch_dict[self.model.lidar_key]
         out = self(x.C, x.F)
         return self.model.eval_outputs(batch_dict, x, out, return_logit or return_tta)
+
+
+def tta_vote(point_logits, save_score: bool = False):
+    """Test-time-augmentation vote of the reference's evaluation loop (R/train.py:471-475, :497-503): the per-point
+    logits of the `votes` augmented copies of one scan (one entry of `point_predict_logits` each) are SUMMED and the
+    arg-max is the prediction, returned as the uint32 column the `.label` dump holds (`taseg_b200.io.write_labels`), or
+    the float32 summed scores with `save_score`.  Stays on the tensors' device: one D2H copy of N x 4 bytes per scan
+    instead of votes x N x classes x 4."""
+    total = point_logits[0].clone() if isinstance(point_logits, (list, tuple)) else point_logits.sum(dim=0)
+    if isinstance(point_logits, (list, tuple)):
+        for extra in point_logits[1:]:
+            total += extra
+    if save_score:
+        return total.float()
+    return total.argmax(dim=1).to(torch.int64)

@@ -96,3 +96,20 @@ def test_calib_and_poses_match_reference_parser(tmp_path):
     poses_ref = [p.astype(np.float32) for p in ref.parse_poses(os.path.join(seq_dir, "poses.txt"), calib_ref)]
     poses = parse_poses(os.path.join(seq_dir, "poses.txt"), calib)
     assert len(poses) == len(poses_ref) and all(np.array_equal(a_, b_) for a_, b_ in zip(poses, poses_ref))
+
+
+def test_tta_vote_and_label_dump(tmp_path):
+    """Vote accumulation of R/train.py:471-503 (sum of the votes' logits, arg-max, uint32 .label file)."""
+    import torch
+    from taseg_b200.engine import tta_vote
+    rng = np.random.default_rng(0)
+    votes = [torch.from_numpy(rng.normal(size=(300, 20)).astype(np.float32)) for _ in range(4)]
+    want = votes[0].numpy().copy()
+    for v in votes[1:]:
+        want += v.numpy()
+    labels = tta_vote(votes)
+    assert np.array_equal(labels.numpy(), want.argmax(1)) and np.array_equal(tta_vote(torch.stack(votes)).numpy(), want.argmax(1))
+    assert np.allclose(tta_vote(votes, save_score=True).numpy(), want, atol=1e-6)
+    path = str(tmp_path / "000000.label")
+    write_labels(path, labels.numpy())
+    assert np.array_equal(read_labels(path), want.argmax(1))
