@@ -251,6 +251,23 @@ int tsg_conv_fwd_tc(const void *in0, int c0, const void *in1, int c1, int64_t n_
                     int c_out, const int32_t *nbr, int64_t nbr_stride, const uint32_t *tile_mask, const int32_t *perm, int64_t n_out,
                     void *out, int out_dtype, const float *bias, const void *residual, int relu, int num_sms,
                     int32_t *sched, tsg_stream_t stream);
+/* Same convolution with an optional SECOND K PHASE accumulated into the same output tile before the epilogue: the
+ * 1x1x1 shortcut convolution of a residual block (R/pcseg/model/segmentor/voxel/minkunet/minkunet.py:83-129:
+ * relu(net(x) + downsample(x)); downsample = spnn.Conv3d(inc, outc, 1) + BN), i.e.
+ *   out[o] = epilogue( sum_k in[nbr[k,o]] @ W[k]  +  sc_in[o] @ W_sc ),
+ * which removes the shortcut launch, its (n_out, c_out) output and the residual read of the block's last convolution.
+ * sc_in0/sc_in1 (n_out, sc_c0 / sc_c1) bf16 are the block's input (two tensors when it is a decoder concat), sc_packed_w =
+ * tsg_conv_pack_weights(k = 1, sc_c0, sc_c1, c_out) with the shortcut's folded BN scale; bias must hold the SUM of both
+ * folded BN shifts.  sc_idx: index line of the identity in TILE-ROW order, nbr_stride entries with -1 in the padding —
+ * for a 3x3x3 stride-1 map this is the centre offset's line of the (sorted) table, nbr + (K/2) * nbr_stride; NULL = tile
+ * row r reads row r (only valid without perm).  sc_in0 == NULL: no second phase (== tsg_conv_fwd_tc).
+ * Launches with fewer tiles than SMs and c_out >= 128 are split into (tile, column half) work items (bit-identical
+ * results: every output element still sees the same MMAs in the same order). */
+int tsg_conv_fwd_tc2(const void *in0, int c0, const void *in1, int c1, int64_t n_in, const void *packed_w, int k,
+                     int c_out, const int32_t *nbr, int64_t nbr_stride, const uint32_t *tile_mask, const int32_t *perm,
+                     int64_t n_out, const void *sc_in0, int sc_c0, const void *sc_in1, int sc_c1,
+                     const void *sc_packed_w, const int32_t *sc_idx, void *out, int out_dtype, const float *bias,
+                     const void *residual, int relu, int num_sms, int32_t *sched, tsg_stream_t stream);
 /* Tile-row order for tsg_conv_fwd_tc: stable sort of the n_out output rows by a K-bit key built from their neighbour
  * mask (offset k present iff nbr[k, o] >= 0; for K = 27 the rarest offsets — cube corners, then edges — are the most
  * significant key bits, otherwise bit k = offset k).  Outputs: perm (n_out) int32 = output row of tile row r, nbr_sorted (K, out_stride) with

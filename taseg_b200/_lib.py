@@ -14,7 +14,7 @@ import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 HEADER = os.path.join(HERE, "..", "include", "taseg_b200.h")
-LIB_PATH = os.path.join(HERE, "libtaseg_b200.so")
+LIB_PATH = os.environ.get("TSG_LIB") or os.path.join(HERE, "libtaseg_b200.so")   # TSG_LIB: profiling build
 
 TSG_OK, TSG_ERR_INVALID, TSG_ERR_CUDA, TSG_ERR_WORKSPACE, TSG_ERR_RANGE, TSG_ERR_UNSUPPORTED = range(6)
 TSG_F32, TSG_BF16, TSG_F16 = 0, 1, 2

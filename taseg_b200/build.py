@@ -27,11 +27,15 @@ def _stale() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not _stale():
+    """TSG_TC_TRACE=1 builds the profiling variant (knock-outs + clock64 traces) as libtaseg_b200_trace.so next to the
+    production library; select it at run time with TSG_LIB=<path> (taseg_b200/_lib.py)."""
+    trace = bool(os.environ.get("TSG_TC_TRACE"))
+    lib_path = LIB.replace(".so", "_trace.so") if trace else LIB
+    if not force and not trace and not _stale():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    flags = NVCC_FLAGS + (["-DTSG_TC_TRACE"] if os.environ.get("TSG_TC_TRACE") else [])   # profiling build: knock-outs + traces
-    objdir = os.path.join(HERE, "build")
+    flags = NVCC_FLAGS + (["-DTSG_TC_TRACE"] if trace else [])
+    objdir = os.path.join(HERE, "build_trace" if trace else "build")
     os.makedirs(objdir, exist_ok=True)
     procs = []
     for src in SOURCES:
@@ -49,8 +53,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         f.write("\n".join(log))
     if verbose:
         print("\n".join(log))
-    subprocess.check_call([nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"])
-    return LIB
+    subprocess.check_call([nvcc, "-shared", "-o", lib_path] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"])
+    return lib_path
 
 
 if __name__ == "__main__":

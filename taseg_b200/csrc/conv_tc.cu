@@ -25,6 +25,11 @@
 //                           16-byte cp.async (LDGSTS, zero-fill for missing neighbours) into the 128B-swizzled K-major A
 //                           tiles; hand-off by cp.async.mbarrier.arrive.noinc (nothing waits for rows to land)
 // Accumulators are double buffered in TMEM so the epilogue of super tile t overlaps the main loop of t+1.
+// v16: a launch may carry a second K PHASE — the 1x1x1 shortcut convolution of a residual block, gathered through the
+// centre offset's index line and accumulated into the same TMEM tile (no shortcut launch, no residual read: 66 -> 59
+// launches and -0.2 ms per benchmark step).  Two measured-and-rejected switches stay behind environment variables:
+// (tile, column half) work items for launches with fewer tiles than SMs (TSG_TC_NSPLIT=2) and programmatic dependent
+// launch (TSG_TC_PDL=1); see the host function for the numbers.
 // History and measurements (profiles/README.md): v1-v7 were bound, in turn, by producer instruction count, the single MMA
 // thread, per-stage bookkeeping done by all 16 producer warps (~2000 cycles of branchy scalar code per group stage) and a
 // thread-per-row epilogue; v9 moved the stage enumeration into the planner warp, v12 doubled and coalesced the epilogue,
@@ -61,9 +66,9 @@ constexpr int V8_DYN_SMEM = 221 * 1024;          // dynamic shared memory reques
 
 // What the planner publishes per super tile: the tile, the offset masks of its G tiles and the list of pipeline stages
 // (stage = bits 0-4 virtual offset kv, 5-8 slice j, 9-10 which sub-tiles multiply this slice, 11-12 it is the first
-// such stage of the super tile for sub-tile 0 / 1).
+// such stage of the super tile for sub-tile 0 / 1, 13 the K phase).
 struct __align__(16) Plan {
-  int tile, n;
+  int tile, n;      // n: bits 0-15 number of stages, bit 16 column half of the work item (N split)
   unsigned mask[2];
   unsigned short stage[V8_PLAN_MAX];
 };
@@ -194,14 +199,16 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
   __shared__ Plan plans[V8_PLAN_SLOTS];
   __shared__ uint32_t tmem_base_slot;
   __shared__ __align__(16) float bias_s[256];
-  __shared__ uint32_t lut[128];  // per (slice j, 16-byte chunk c of the slice): which offset / source tensor / source chunk
+  __shared__ uint16_t lut[256];  // per (phase, slice j, 16-byte chunk c of the slice): which offset / source tensor / source chunk
 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int P = p.pk, Q = p.kq;                                      // offsets per virtual offset, slices per virtual offset
-  const unsigned subP = (1u << P) - 1u;
-  const unsigned long long slice_need = p.slice_need;                // 4 bits per slice: which of the P offsets it touches
-  const uint32_t b_bytes = (uint32_t)p.c_out * 128u;                 // multiple of 2048
+  const int NPH = p.n_phases;
+  const int P0 = p.ph[0].pk, Q0 = p.ph[0].kq, P1 = p.ph[1].pk, Q1 = p.ph[1].kq;  // offsets / slices per virtual offset
+  const unsigned long long need0 = p.ph[0].slice_need, need1 = p.ph[1].slice_need;
+  const int NS = p.ns, n_eff = p.n_eff;
+  const uint32_t b_bytes = (uint32_t)n_eff * 128u;                   // weight slice of one work item; multiple of 2048
+  const uint32_t b_full = (uint32_t)p.c_out * 128u;                  // ... of all output channels (block pitch of packed_w)
   const uint32_t stage_bytes = b_bytes + (uint32_t)G * TC_A_BYTES;   // [W slice][A tile 0]..[A tile G-1]
   const uint32_t nst = (uint32_t)p.na;                               // stages
   const uint32_t stg0 = smem_base + nst * stage_bytes;               // epilogue staging, then the producers' index buffers
@@ -209,13 +216,15 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
   const uint32_t idx_warp_bytes = (uint32_t)p.ksmax * G * 128u;      // per producer warp, twice: [offset of the slice][sub-tile][32 rows]
   const int num_tiles = (int)((p.n_out + TC_BM - 1) / TC_BM);
   const int num_super = (num_tiles + G - 1) / G;
-  const unsigned kmask = p.K >= 32 ? 0xffffffffu : ((1u << p.K) - 1u);
-  const int KV = (p.K + P - 1) / P;                                  // virtual offsets
+  const unsigned kmask = p.ph[0].K >= 32 ? 0xffffffffu : ((1u << p.ph[0].K) - 1u);
+  const int KV0 = (p.ph[0].K + P0 - 1) / P0, KV1 = NPH > 1 ? (p.ph[1].K + P1 - 1) / P1 : 0;  // virtual offsets
   const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[V8_MAX_STAGES]);
   const uint32_t tfull0 = smem_u32(&bars[2 * V8_MAX_STAGES]), tempty0 = tfull0 + 16;
   const uint32_t sfull0 = tfull0 + 32, sempty0 = sfull0 + 8 * V8_PLAN_SLOTS;
   const uint32_t obar0 = sempty0 + 8 * V8_PLAN_SLOTS;                // issue-order hand-off between the two MMA issuers (G == 1)
 
+  // programmatic dependent launch: the next kernel of the stream may start its prologue while this grid drains
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (threadIdx.x == 0) {
     for (uint32_t s = 0; s < nst; ++s) {
       mbar_init(full0 + 8 * s, V8_GROUP_WARPS * 32 + 1);  // every thread of the owning producer group (async, when its copies land) + the weight thread
@@ -232,17 +241,19 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  // ... and nothing produced by the previous kernel is read before it has completed and flushed
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   if (threadIdx.x < 256) bias_s[threadIdx.x] = (p.bias && (int)threadIdx.x < p.c_out) ? __ldg(p.bias + threadIdx.x) : 0.f;
-  if (threadIdx.x >= 256 && threadIdx.x < 256 + 128) {
-    const int t = threadIdx.x - 256, j = t >> 3, c = t & 7;
+  if (threadIdx.x >= 256 && threadIdx.x < 256 + 256) {
+    const int t = threadIdx.x - 256, phi = t >> 7, j = (t >> 3) & 15, c = t & 7;
     uint32_t e = 0;
-    if (j < Q) {
-      const int cpo = p.cpo, c0c = p.c0 >> 3;
+    if (phi < NPH && j < (phi ? Q1 : Q0)) {
+      const int cpo = phi ? p.ph[1].cpo : p.ph[0].cpo, c0c = (phi ? p.ph[1].c0 : p.ph[0].c0) >> 3;
       const int f = 8 * j + c, ksub = f / cpo, cc = f - ksub * cpo, lo = (8 * j) / cpo;
       const bool second = cc >= c0c;
       e = (uint32_t)(ksub - lo) | ((uint32_t)ksub << 2) | ((second ? 1u : 0u) << 4) | ((uint32_t)(second ? cc - c0c : cc) << 5);
     }
-    lut[t] = e;
+    lut[t] = (uint16_t)e;
   }
   if (warp == V8_MMA_WARP) {  // TMEM allocation by the MMA warp
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
@@ -255,8 +266,7 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
 
-  auto group_bits = [&](unsigned m, int kv) -> unsigned { return (m >> (kv * P)) & subP; };
-  auto need_of = [&](int j) -> unsigned { return (unsigned)(slice_need >> (4 * j)) & 15u; };
+  auto need_of = [&](unsigned phi, int j) -> unsigned { return (unsigned)((phi ? need1 : need0) >> (4 * j)) & 15u; };
   // Plan ring, consumer side: wait for the next plan; release it when the role is done with the super tile.
   Ring pr;
   auto plan_wait = [&]() -> const volatile Plan * {
@@ -293,7 +303,7 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
     const int bw = f32 ? 16 : 32;                           // full block width in columns (64 B of output per row)
     const int cstep = G == 2 ? bw : 2 * bw;                 // this warp's blocks start at cfirst, cfirst + cstep, ...
     const int cfirst = G == 2 ? 0 : eset * bw;
-    auto blk_cols = [&](int c0) -> int { return c_out - c0 >= bw ? bw : 16; };  // the last block may be 16 columns wide
+    auto blk_cols = [&](int lc) -> int { return n_eff - lc >= bw ? bw : 16; };  // the last block may be 16 columns wide
     auto prefetch_res = [&](int rows_g, int c0, int ncols) {
       const char *src = resp + (long long)c0 * 2;
       if (ncols == 32) epi_prefetch_res<32>(stg, src, res_pitch, rows_g, lane);
@@ -304,29 +314,30 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
       const volatile Plan *pl = plan_wait();
       const int st = pl->tile;
       const unsigned mask_g = pl->mask[g];
+      const int cbase = (pl->n >> 16) * n_eff;              // first output channel of this work item
       plan_release_warp();
       if (st < 0) break;
       const uint32_t buf = it & 1, ph = (it >> 1) & 1;
       const long long r = (long long)(st * G + g) * TC_BM + quad * 32 + lane;  // destination row: fetched before the long wait
       const int rows_g = r < p.n_out ? (p.perm ? __ldg(p.perm + r) : (int)r) : -1;
-      const bool live = st * G + g < num_tiles && cfirst < c_out;
-      if (res_staged && live) prefetch_res(rows_g, cfirst, blk_cols(cfirst));  // lands while the main loop still runs
+      const bool live = st * G + g < num_tiles && cfirst < n_eff;
+      if (res_staged && live) prefetch_res(rows_g, cbase + cfirst, blk_cols(cfirst));  // lands while the main loop still runs
       mbar_wait_sleep(tfull0 + 8 * buf, ph);
       tc_fence_after();
       if (threadIdx.x == 0) TSG_TRACE(10, it);
       if (live) {
-        const bool have_acc = mask_g != 0u;
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (buf * G + g) * (uint32_t)c_out;
-        for (int c0 = cfirst; c0 < c_out; c0 += cstep) {
-          const int ncols = blk_cols(c0);
+        const bool have_acc = mask_g != 0u || NPH > 1;   // a folded shortcut multiplies every live tile
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (buf * G + g) * (uint32_t)n_eff;
+        for (int lc = cfirst; lc < n_eff; lc += cstep) {     // lc: column inside the work item, c0: output channel
+          const int ncols = blk_cols(lc), c0 = cbase + lc;
           if (res_staged) {
-            if (c0 != cfirst) prefetch_res(rows_g, c0, ncols);
+            if (lc != cfirst) prefetch_res(rows_g, c0, ncols);
             asm volatile("cp.async.wait_all;" ::: "memory");
             __syncwarp();
           }
-          if (f32) epi_block<16, true>(p, taddr + c0, have_acc, bias_s + c0, stg, lane, rows_g, c0, res_staged, no_store);
-          else if (ncols == 32) epi_block<32, false>(p, taddr + c0, have_acc, bias_s + c0, stg, lane, rows_g, c0, res_staged, no_store);
-          else epi_block<16, false>(p, taddr + c0, have_acc, bias_s + c0, stg, lane, rows_g, c0, res_staged, no_store);
+          if (f32) epi_block<16, true>(p, taddr + lc, have_acc, bias_s + c0, stg, lane, rows_g, c0, res_staged, no_store);
+          else if (ncols == 32) epi_block<32, false>(p, taddr + lc, have_acc, bias_s + c0, stg, lane, rows_g, c0, res_staged, no_store);
+          else epi_block<16, false>(p, taddr + lc, have_acc, bias_s + c0, stg, lane, rows_g, c0, res_staged, no_store);
         }
       }
       tc_fence_before();
@@ -343,7 +354,7 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
     // executes tcgen05.fence::after_thread_sync — accumulation order, and the result, are those of a single issuer.
     const int mw = warp - V8_MMA_WARP;
     if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.c_out >> 3) << 17) | ((TC_BM >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n_eff >> 3) << 17) | ((TC_BM >> 4) << 24);
       const uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);   // SBO 1024 B, version 1, SWIZZLE_128B
       const uint32_t desc_lo_stage = stage_bytes >> 4;
       const uint32_t b_lo0 = ((smem_base & 0x3FFFFu) >> 4) | (1u << 16);          // LBO field = 1 (ignored for swizzled K-major)
@@ -359,12 +370,12 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
           plan_release_lane();
           break;
         }
-        const int n = pl->n;
+        const int n = pl->n & 0xffff;
         const uint32_t buf = it & 1, ph = (it >> 1) & 1;
         mbar_wait(tempty0 + 8 * buf, ph ^ 1);
         tc_fence_after();
         if (tracer) TSG_TRACE(8, it);
-        const uint32_t d_tmem = tmem_base + buf * G * (uint32_t)p.c_out;
+        const uint32_t d_tmem = tmem_base + buf * G * (uint32_t)n_eff;
         const int i0 = (int)((mw ^ gpar) & 1u);
         uint32_t slot = slot0 + i0, phase = phase0;
         if (slot >= nst) {
@@ -391,7 +402,7 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
             if (!((d >> (9 + g)) & 1u) || TSG_DBG(4)) continue;
             // every slice is a full 64-channel block: four K = 16 MMAs per sub-tile
             const uint32_t a_lo = a_lo0 + slot * desc_lo_stage + g * (TC_A_BYTES >> 4);
-            const uint32_t dt = d_tmem + g * (uint32_t)p.c_out;
+            const uint32_t dt = d_tmem + g * (uint32_t)n_eff;
             umma_bf16(dt, make_desc(a_lo, desc_hi), make_desc(b_lo, desc_hi), idesc, ((d >> (11 + g)) & 1u) ^ 1u);
             umma_bf16(dt, make_desc(a_lo + 2, desc_hi), make_desc(b_lo + 2, desc_hi), idesc, 1u);
             umma_bf16(dt, make_desc(a_lo + 4, desc_hi), make_desc(b_lo + 4, desc_hi), idesc, 1u);
@@ -436,10 +447,13 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
           plan_release_lane();
           break;
         }
-        const int n = pl->n;
+        const int n = pl->n & 0xffff;
+        const size_t hoff = (size_t)(pl->n >> 16) * b_bytes;   // this work item's rows of every [c_out][64] block
         for (int i = 0; i < n; ++i) {
           const unsigned d = pl->stage[i];
-          const uint8_t *src = p.packed_w + (size_t)((d & 31u) * Q + ((d >> 5) & 15u)) * b_bytes;
+          const unsigned phi = (d >> 13) & 1u;
+          const uint8_t *src = (phi ? p.ph[1].packed_w : p.ph[0].packed_w) +
+                               (size_t)((d & 31u) * (phi ? Q1 : Q0) + ((d >> 5) & 15u)) * b_full + hoff;
           TSG_STATE(pl->tile, n, i, n_w);
           mbar_wait(empty0 + 8 * r.slot, r.phase ^ 1);
           TSG_TRACE(4, n_w);
@@ -476,52 +490,76 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
         }
       }
       t = __shfl_sync(0xffffffffu, t, 0);
-      const int st = t < num_super ? num_super - 1 - t : -1;  // heavy (high-key) tiles first
-      unsigned mm = 0;
+      const int st = t < num_super * NS ? num_super - 1 - t / NS : -1;  // heavy (high-key) tiles first; NS column blocks each
+      const int half = t < num_super * NS ? t % NS : 0;
+      unsigned mm = 0, lv = 0;
       if (st >= 0 && lane < G) {
         const int tile = st * G + lane;
-        mm = tile < num_tiles ? ((p.tile_mask ? __ldg(p.tile_mask + tile) : 0xffffffffu) & kmask) : 0u;
+        lv = tile < num_tiles ? 1u : 0u;
+        mm = lv ? ((p.tile_mask ? __ldg(p.tile_mask + tile) : 0xffffffffu) & kmask) : 0u;
       }
       const unsigned m0 = __shfl_sync(0xffffffffu, mm, 0), m1 = G > 1 ? __shfl_sync(0xffffffffu, mm, 1) : 0u;
-      const unsigned g0 = lane < KV ? group_bits(m0, lane) : 0u, g1 = lane < KV ? group_bits(m1, lane) : 0u;
-      const unsigned gu = g0 | g1;
-      unsigned sl = 0;  // slices of virtual offset `lane` that some tile of the super tile needs
-      for (int j = 0; j < Q; ++j) sl |= (gu & need_of(j)) ? (1u << j) : 0u;
-      int incl = __popc(sl);
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const int o = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += o;
-      }
-      int pos = incl - __popc(sl);
+      const unsigned l0 = __shfl_sync(0xffffffffu, lv, 0), l1 = G > 1 ? __shfl_sync(0xffffffffu, lv, 1) : 0u;
       Plan *pl = &plans[w.slot];
-      // first stage of the super tile that multiplies sub-tile 0 / 1: its first MMA overwrites the accumulator
-      int f0 = 0x7fffffff, f1 = 0x7fffffff;
-      {
-        int q = pos;
-        for (unsigned rest = sl; rest; rest &= rest - 1, ++q) {
-          const unsigned need = need_of(__ffs(rest) - 1);
-          if ((g0 & need) && f0 == 0x7fffffff) f0 = q;
-          if ((g1 & need) && f1 == 0x7fffffff) f1 = q;
+      // per phase: the slices of virtual offset `lane` that some tile of the super tile needs, and their positions in
+      // the stage list (phase 0 first); f0 / f1 = first stage that multiplies sub-tile 0 / 1 (its first MMA overwrites
+      // the accumulator)
+      unsigned sl_ph[2] = {0u, 0u}, g0_ph[2] = {0u, 0u}, g1_ph[2] = {0u, 0u};
+      int pos_ph[2] = {0, 0};
+      int base = 0, f0 = 0x7fffffff, f1 = 0x7fffffff;
+#pragma unroll
+      for (int phi = 0; phi < 2; ++phi) {
+        if (phi >= NPH) break;
+        const int Pp = phi ? P1 : P0, Qp = phi ? Q1 : Q0, KVp = phi ? KV1 : KV0;
+        const unsigned subP = (1u << Pp) - 1u;
+        const unsigned a0 = phi ? l0 : m0, a1 = phi ? l1 : m1;   // the shortcut phase has one offset, present in every live tile
+        const unsigned g0 = lane < KVp ? (a0 >> (lane * Pp)) & subP : 0u, g1 = lane < KVp ? (a1 >> (lane * Pp)) & subP : 0u;
+        const unsigned gu = g0 | g1;
+        unsigned sl = 0;
+        for (int j = 0; j < Qp; ++j) sl |= (gu & need_of(phi, j)) ? (1u << j) : 0u;
+        int incl = __popc(sl);
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int o = __shfl_up_sync(0xffffffffu, incl, d);
+          if (lane >= d) incl += o;
         }
+        const int pos = base + incl - __popc(sl);
+        {
+          int q = pos;
+          for (unsigned rest = sl; rest; rest &= rest - 1, ++q) {
+            const unsigned need = need_of(phi, __ffs(rest) - 1);
+            if ((g0 & need) && f0 == 0x7fffffff) f0 = q;
+            if ((g1 & need) && f1 == 0x7fffffff) f1 = q;
+          }
+        }
+        base += __shfl_sync(0xffffffffu, incl, 31);
+        sl_ph[phi] = sl;
+        g0_ph[phi] = g0;
+        g1_ph[phi] = g1;
+        pos_ph[phi] = pos;
       }
 #pragma unroll
       for (int d = 16; d; d >>= 1) {
         f0 = min(f0, __shfl_xor_sync(0xffffffffu, f0, d));
         f1 = min(f1, __shfl_xor_sync(0xffffffffu, f1, d));
       }
-      for (unsigned rest = sl; rest; rest &= rest - 1) {
-        const int j = __ffs(rest) - 1;
-        const unsigned need = need_of(j);
-        pl->stage[pos] = (unsigned short)(lane | (j << 5) | ((g0 & need) ? 1u << 9 : 0u) | ((g1 & need) ? 1u << 10 : 0u) |
-                                          (pos == f0 ? 1u << 11 : 0u) | (pos == f1 ? 1u << 12 : 0u));
-        ++pos;
+#pragma unroll
+      for (int phi = 0; phi < 2; ++phi) {
+        if (phi >= NPH) break;
+        int pos = pos_ph[phi];
+        for (unsigned rest = sl_ph[phi]; rest; rest &= rest - 1) {
+          const int j = __ffs(rest) - 1;
+          const unsigned need = need_of(phi, j);
+          pl->stage[pos] = (unsigned short)(lane | (j << 5) | ((g0_ph[phi] & need) ? 1u << 9 : 0u) | ((g1_ph[phi] & need) ? 1u << 10 : 0u) |
+                                            (pos == f0 ? 1u << 11 : 0u) | (pos == f1 ? 1u << 12 : 0u) | ((unsigned)phi << 13));
+          ++pos;
+        }
       }
-      const int n_total = __shfl_sync(0xffffffffu, incl, 31);
+      const int n_total = base;
       TSG_STATE(st, n_total, t, (int)w.slot);
       if (lane == 0) {
         pl->tile = st;
-        pl->n = n_total;
+        pl->n = n_total | (half << 16);
         pl->mask[0] = m0;
         pl->mask[1] = m1;
       }
@@ -557,14 +595,11 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
 #pragma unroll
     for (int q = 0; q < V8_Q; ++q) dst_off[q] = b_bytes + (uint32_t)(rsub * V8_Q + q) * 128u + (uint32_t)((chunk ^ q) << 4);
     const uint32_t ibuf = idx0 + (uint32_t)pw * 2u * idx_warp_bytes;  // double buffered
-    const uint32_t rb0 = (uint32_t)p.c0 * 2u, rb1 = (uint32_t)p.c1 * 2u;
-    const char *in0 = reinterpret_cast<const char *>(p.in0);
-    const char *in1 = reinterpret_cast<const char *>(p.in1);
-    const long long n_out = p.n_out, nbr_stride = p.nbr_stride;
-    const int *nbr = p.nbr;
+    const long long n_out = p.n_out;
     // ---- cursor over the global stage sequence: plan of the current super tile + index of the next stage in it
     int st = -2, n = 0, i = 0, gs = 0;  // gs = (global stage number of plan index i) mod NG
-    unsigned masks[2] = {0u, 0u};
+    unsigned masks[2] = {0u, 0u};       // offset masks of the super tile's sub-tiles (phase 0)
+    unsigned lives = 0;                 // bit g: sub-tile g exists (the one offset of the shortcut phase)
     unsigned d_cur = 0;                 // descriptor of the stage the cursor delivered last
     // Moves the cursor to this group's next stage: 1 = delivered (d_cur), 0 = no more work, 2 = the next plan is not
     // published yet and `block` is false.  The non-blocking form exists because a producer must never wait for a plan
@@ -598,9 +633,10 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
           st = -1;
           return 0;
         }
-        n = pl->n;
+        n = pl->n & 0xffff;
         masks[0] = pl->mask[0];
         masks[1] = pl->mask[1];
+        lives = (st * G < num_tiles ? 1u : 0u) | ((G > 1 && st * G + 1 < num_tiles) ? 2u : 0u);
         i = 0;
         TSG_STATE(st, n, gs, -1);
       }
@@ -620,29 +656,37 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
         uint32_t ioff;      // this lane's 32 bytes inside the warp's index buffer (sub-tile 0)
         unsigned kbits;     // per sub-tile: the lane's offset is present
         unsigned act;       // per sub-tile: the slice is needed
+        bool indexed;       // neighbour indices come from an index line (false: identity map)
       };
       auto locate = [&](View &v) {
+        const unsigned phi = (d_cur >> 13) & 1u;
         const int kv = d_cur & 31u, j = (d_cur >> 5) & 15u;
         v.act = (d_cur >> 9) & 3u;
-        const uint32_t e = lut[j * 8 + chunk];
-        const int k = kv * P + (int)((e >> 2) & 3u);
+        const uint32_t e = lut[phi * 128 + j * 8 + chunk];
+        const int k = kv * (phi ? P1 : P0) + (int)((e >> 2) & 3u);
         const bool second = (e >> 4) & 1u;
-        v.src = (second ? in1 : in0) + (e >> 5) * 16u;
-        v.rb = second ? rb1 : rb0;
+        const __nv_bfloat16 *base = phi ? (second ? p.ph[1].in1 : p.ph[1].in0) : (second ? p.ph[0].in1 : p.ph[0].in0);
+        v.src = reinterpret_cast<const char *>(base) + (e >> 5) * 16u;
+        v.rb = (uint32_t)(phi ? (second ? p.ph[1].c1 : p.ph[1].c0) : (second ? p.ph[0].c1 : p.ph[0].c0)) * 2u;
         v.ioff = (e & 3u) * (uint32_t)(G * 128) + (uint32_t)rsl * 32u;
         v.m0 = (long long)st * G * TC_BM;
-        v.kbits = ((masks[0] >> k) & 1u) | (((masks[1] >> k) & 1u) << 1);
+        v.kbits = phi ? (k == 0 ? lives : 0u) : (((masks[0] >> k) & 1u) | (((masks[1] >> k) & 1u) << 1));
+        v.indexed = (phi ? p.ph[1].nbr : p.ph[0].nbr) != nullptr;
       };
       // request the index lines of the delivered stage: per (offset of the slice, sub-tile) the warp's 32 rows = 128 B
       auto prefetch_idx = [&](uint32_t buf) {
+        const unsigned phi = (d_cur >> 13) & 1u;
+        const int *nbr = phi ? p.ph[1].nbr : p.ph[0].nbr;
         if (!nbr) return;
+        const long long nbr_stride = phi ? p.ph[1].nbr_stride : p.ph[0].nbr_stride;
         const int kv = d_cur & 31u, j = (d_cur >> 5) & 15u;
-        const unsigned need = need_of(j);
-        const int k0 = kv * P + __ffs(need) - 1, nks = __popc(need);
+        const unsigned need = need_of(phi, j);
+        const int k0 = kv * (phi ? P1 : P0) + __ffs(need) - 1, nks = __popc(need);
         for (int t = lane; t < nks * G * 8; t += 32) {
           const int ks = t / (G * 8), g = (t >> 3) % G, piece = t & 7;
           const int k = k0 + ks;
-          if (((g ? masks[1] : masks[0]) >> k) & 1u)
+          const bool present = phi ? (k == 0 && ((lives >> g) & 1u)) : (((g ? masks[1] : masks[0]) >> k) & 1u);
+          if (present)
             cp_async16(buf + (uint32_t)((ks * G + g) * 128 + piece * 16),
                        nbr + (long long)k * nbr_stride + (long long)st * G * TC_BM + g * TC_BM + wg * 32 + piece * 4, 16u);
         }
@@ -682,7 +726,7 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
 #pragma unroll
         for (int g = 0; g < G; ++g) {
           if ((cur.kbits >> g) & 1u) {
-            if (nbr) {
+            if (cur.indexed) {
               const uint4 a = lds128(ibase + g * 128), b = lds128(ibase + g * 128 + 16);
               idx[g][0] = (int)a.x; idx[g][1] = (int)a.y; idx[g][2] = (int)a.z; idx[g][3] = (int)a.w;
               idx[g][4] = (int)b.x; idx[g][5] = (int)b.y; idx[g][6] = (int)b.z; idx[g][7] = (int)b.w;
@@ -827,14 +871,42 @@ int tsg_debug_conv_trace(long long *host) {
   return TSG_OK;
 }
 
-int tsg_conv_fwd_tc(const void *in0, int c0, const void *in1, int c1, int64_t n_in, const void *packed_w, int k,
-                    int c_out, const int32_t *nbr, int64_t nbr_stride, const uint32_t *tile_mask, const int32_t *perm,
-                    int64_t n_out, void *out, int out_dtype, const float *bias, const void *residual, int relu,
-                    int num_sms_hint, int32_t *sched, tsg_stream_t stream) {
+static int fill_phase(TcPhase &h, const void *in0, int c0, const void *in1, int c1, const void *packed_w, int k,
+                      const int32_t *nbr, int64_t nbr_stride, int *ksmax, const char *what) {
+  const SlicePlan sp = slice_plan(c0, c1);
+  if (sp.Q > 16) {
+    set_error("%s: unsupported channel count (more than 16 slices per offset group)", what);
+    return TSG_ERR_UNSUPPORTED;
+  }
+  h.in0 = (const __nv_bfloat16 *)in0;
+  h.in1 = (const __nv_bfloat16 *)in1;
+  h.packed_w = (const uint8_t *)packed_w;
+  h.nbr = nbr;
+  h.nbr_stride = nbr_stride;
+  h.slice_need = sp.need;
+  h.c0 = c0;
+  h.c1 = c1;
+  h.pk = sp.P;
+  h.kq = sp.Q;
+  h.cpo = sp.cpo;
+  h.K = k;
+  if (sp.ksmax > *ksmax) *ksmax = sp.ksmax;
+  return TSG_OK;
+}
+
+int tsg_conv_fwd_tc2(const void *in0, int c0, const void *in1, int c1, int64_t n_in, const void *packed_w, int k,
+                     int c_out, const int32_t *nbr, int64_t nbr_stride, const uint32_t *tile_mask, const int32_t *perm,
+                     int64_t n_out, const void *sc_in0, int sc_c0, const void *sc_in1, int sc_c1,
+                     const void *sc_packed_w, const int32_t *sc_idx, void *out, int out_dtype, const float *bias,
+                     const void *residual, int relu, int num_sms_hint, int32_t *sched, tsg_stream_t stream) {
   if (c0 % 16 || c1 % 16 || c_out % 16 || c_out > 256 || c_out <= 0 || c0 <= 0 || k <= 0 || k > 32 ||
       (out_dtype != TSG_BF16 && out_dtype != TSG_F32)) {
     set_error("tsg_conv_fwd_tc: need c0,c1,c_out multiples of 16, c_out<=256, K<=32, out bf16/f32");
     return TSG_ERR_UNSUPPORTED;
+  }
+  if (sc_in0 && (sc_c0 % 16 || sc_c1 % 16 || sc_c0 <= 0 || !sc_packed_w || (perm && !sc_idx))) {
+    set_error("tsg_conv_fwd_tc: shortcut needs sc_c0,sc_c1 multiples of 16, packed weights and (with perm) its index line");
+    return TSG_ERR_INVALID;
   }
   if (n_out <= 0) return TSG_OK;
   if (nbr && (nbr_stride % 256 || nbr_stride < (n_out + 255) / 256 * 256)) {
@@ -845,25 +917,24 @@ int tsg_conv_fwd_tc(const void *in0, int c0, const void *in1, int c1, int64_t n_
     set_error("tsg_conv_fwd_tc: tensor too large for 32-bit row arithmetic");
     return TSG_ERR_UNSUPPORTED;
   }
-  const SlicePlan sp = slice_plan(c0, c1);
-  if (sp.Q > 16) {
-    set_error("tsg_conv_fwd_tc: unsupported channel count (more than 16 slices per offset group)");
-    return TSG_ERR_UNSUPPORTED;
-  }
   TcParams p;
-  p.in0 = (const __nv_bfloat16 *)in0;
-  p.in1 = (const __nv_bfloat16 *)in1;
-  p.c0 = c0;
-  p.c1 = c1;
-  p.pk = sp.P;
-  p.kq = sp.Q;
-  p.cpo = sp.cpo;
-  p.slice_need = sp.need;
-  p.packed_w = (const uint8_t *)packed_w;
-  p.K = k;
+  memset(&p, 0, sizeof(p));
+  int ksmax = 1;
+  int rc = fill_phase(p.ph[0], in0, c0, in1, c1, packed_w, k, nbr, nbr_stride, &ksmax, "tsg_conv_fwd_tc");
+  if (rc != TSG_OK) return rc;
+  p.n_phases = 1;
+  p.ph[1] = p.ph[0];
+  if (sc_in0) {
+    rc = fill_phase(p.ph[1], sc_in0, sc_c0, sc_in1, sc_c1, sc_packed_w, 1, sc_idx, nbr_stride, &ksmax, "tsg_conv_fwd_tc (shortcut)");
+    if (rc != TSG_OK) return rc;
+    p.n_phases = 2;
+    const int stages0 = (k + p.ph[0].pk - 1) / p.ph[0].pk * p.ph[0].kq;
+    if (stages0 + p.ph[1].kq > V8_PLAN_MAX) {
+      set_error("tsg_conv_fwd_tc: too many pipeline stages per tile");
+      return TSG_ERR_UNSUPPORTED;
+    }
+  }
   p.c_out = c_out;
-  p.nbr = nbr;
-  p.nbr_stride = nbr_stride;
   p.tile_mask = tile_mask;
   p.perm = perm;
   p.n_out = n_out;
@@ -879,22 +950,33 @@ int tsg_conv_fwd_tc(const void *in0, int c0, const void *in1, int c1, int64_t n_
 #else
   p.dbg = 0;
 #endif
-  const int sms = num_sms_hint > 0 ? num_sms_hint : num_sms();
+  int dev = 0;
+  TSG_CUDA(cudaGetDevice(&dev));
+  int sms = num_sms_hint;
+  if (sms <= 0) TSG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const long long num_tiles = (n_out + TC_BM - 1) / TC_BM;
-  // G sub-tiles share every weight slice; bounded by TMEM (2 buffers x G x c_out fp32 columns <= 512) and by the
+  // N split (TSG_TC_NSPLIT=2, off by default): launches with fewer tiles than SMs hand out (tile, column half) work
+  // items, halving the serial stage chain of the heaviest tile.  Measured on the 256->256 layers at stride 16 (120 tiles):
+  // 52 -> 63 us — a stage costs about the same whatever its width (the pipeline is hand-shake bound, profiles/README.md), so
+  // twice the stages on 148 instead of 120 SMs is a loss.  Kept as a tested switch for wider / shallower launches.
+  const char *ns_env = getenv("TSG_TC_NSPLIT");
+  const int ns = (ns_env && atoi(ns_env) == 2 && c_out >= 64 && c_out % 32 == 0 && num_tiles <= sms) ? 2 : 1;
+  p.ns = ns;
+  p.n_eff = c_out / ns;
+  // G sub-tiles share every weight slice; bounded by TMEM (2 buffers x G x n_eff fp32 columns <= 512) and by the
   // number of super tiles needed to keep every SM busy
-  int G = c_out <= 128 ? 2 : 1;  // (G = 4 spills the producers' index registers at 768 threads per CTA)
-  while (G > 1 && (num_tiles + G - 1) / G < 2LL * sms) G >>= 1;
+  int G = p.n_eff <= 128 ? 2 : 1;  // (G = 4 spills the producers' index registers at 768 threads per CTA)
+  while (G > 1 && (num_tiles + G - 1) / G * ns < 2LL * sms) G >>= 1;
 #ifdef TSG_TC_TRACE
   if (getenv("TSG_TC_G1")) G = 1;
 #endif
   uint32_t cols = 32;
-  while (cols < 2u * (uint32_t)G * (uint32_t)c_out) cols <<= 1;
+  while (cols < 2u * (uint32_t)G * (uint32_t)p.n_eff) cols <<= 1;
   p.tmem_cols = cols;
-  p.ksmax = sp.ksmax;
+  p.ksmax = ksmax;
   // dynamic shared memory: 1 KB alignment slack + stages + epilogue staging + the producers' index buffers
-  const size_t b_bytes = (size_t)c_out * 128, stage_bytes = b_bytes + (size_t)G * TC_A_BYTES;
-  const size_t fixed = 1024 + (size_t)V8_EPI_WARPS * V8_STG_BYTES + (size_t)V8_PROD_WARPS * 2 * sp.ksmax * G * 128;
+  const size_t b_bytes = (size_t)p.n_eff * 128, stage_bytes = b_bytes + (size_t)G * TC_A_BYTES;
+  const size_t fixed = 1024 + (size_t)V8_EPI_WARPS * V8_STG_BYTES + (size_t)V8_PROD_WARPS * 2 * ksmax * G * 128;
   int stages = (int)((V8_DYN_SMEM - fixed) / stage_bytes);
   if (stages > V8_MAX_STAGES) stages = V8_MAX_STAGES;
 #ifdef TSG_TC_TRACE
@@ -905,19 +987,41 @@ int tsg_conv_fwd_tc(const void *in0, int c0, const void *in1, int c1, int64_t n_
     return TSG_ERR_UNSUPPORTED;
   }
   p.na = stages;
-  p.nb = stages;
   const size_t smem = (size_t)stages * stage_bytes + fixed;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[64] = {false};   // the >48 KB shared-memory opt-in is per device
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
     TSG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, V8_DYN_SMEM));
     TSG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, V8_DYN_SMEM));
-    configured = true;
+    if (dev >= 0 && dev < 64) configured[dev] = true;
   }
-  const long long num_super = (num_tiles + G - 1) / G;
-  const unsigned grid = (unsigned)(num_super < sms ? num_super : sms);
-  if (G == 2) conv_tc_kernel<2><<<grid, V8_THREADS, smem, stream>>>(p);
-  else conv_tc_kernel<1><<<grid, V8_THREADS, smem, stream>>>(p);
+  const long long items = (num_tiles + G - 1) / G * ns;
+  // programmatic dependent launch (TSG_TC_PDL=1, off by default): this grid's CTAs may be scheduled while the previous
+  // kernel of the stream drains; the kernel executes griddepcontrol.wait before it reads anything.  Measured: +1 % with one
+  // batch in flight, -8 % with two (early CTAs of one stream's next convolution hold the SMs the other stream's small
+  // kernels would have used), so the benchmark configuration leaves it off.
+  static const bool pdl = getenv("TSG_TC_PDL") && atoi(getenv("TSG_TC_PDL")) == 1;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(items < sms ? items : sms));
+  cfg.blockDim = dim3(V8_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  if (G == 2) TSG_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<2>, p));
+  else TSG_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<1>, p));
   return check_launch("tsg_conv_fwd_tc");
+}
+
+int tsg_conv_fwd_tc(const void *in0, int c0, const void *in1, int c1, int64_t n_in, const void *packed_w, int k,
+                    int c_out, const int32_t *nbr, int64_t nbr_stride, const uint32_t *tile_mask, const int32_t *perm,
+                    int64_t n_out, void *out, int out_dtype, const float *bias, const void *residual, int relu,
+                    int num_sms_hint, int32_t *sched, tsg_stream_t stream) {
+  return tsg_conv_fwd_tc2(in0, c0, in1, c1, n_in, packed_w, k, c_out, nbr, nbr_stride, tile_mask, perm, n_out, nullptr, 0,
+                          nullptr, 0, nullptr, nullptr, out, out_dtype, bias, residual, relu, num_sms_hint, sched, stream);
 }
 
 }  // extern "C"

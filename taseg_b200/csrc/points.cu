@@ -418,47 +418,62 @@ __global__ void __launch_bounds__(256) devoxelize_multi_kernel(DevoxScales sc, c
     const float pv[3] = {p.x, p.y, p.z};
     const int b = (int)p.w;
     const int ix = sub >> 2, iy = (sub >> 1) & 1, iz = sub & 1;
-    for (int ch = 4 * sub; ch < c; ch += 32) {   // one pass for c <= 32
+    // (1) every lane probes ITS corner of every scale and the 8 lanes normalise the weights (calc_ti_weights): done once
+    // per point, outside the channel loop, so all 8 lanes take part in the shuffles whatever the channel count
+    int ids[4];
+    float wts[4];
+#pragma unroll
+    for (int si = 0; si < 4; ++si) {
+      ids[si] = -1;
+      wts[si] = 0.f;
+      if (si >= sc.count) continue;
+      const int s = sc.stride[si];
+      const float fs = (float)s;
+      float pf[3], lo[3], hi[3];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        pf[a] = (s != 1) ? __fmul_rn(floorf(__fdiv_rn(pv[a], fs)), fs) : floorf(pv[a]);
+        lo[a] = __fsub_rn(__fadd_rn(pf[a], fs), pv[a]);
+        hi[a] = __fsub_rn(pv[a], pf[a]);
+      }
+      float wk = __fmul_rn(__fmul_rn(ix ? hi[0] : lo[0], iy ? hi[1] : lo[1]), iz ? hi[2] : lo[2]);
+      if (s != 1) wk = __fdiv_rn(wk, (float)(s * s * s));
+      int id = -1;
+      if (wk != 0.f && live) {   // a zero-weight corner contributes nothing whether it exists or not
+        const int x = floor_to_stride(pv[0], s) + ix * s, y = floor_to_stride(pv[1], s) + iy * s,
+                  z = floor_to_stride(pv[2], s) + iz * s;
+        if (coord_in_range(x, y, z, b)) id = table_find_coord(sc.tab[si], sc.mask[si], pack_coord(x, y, z, b));
+      }
+      if (id < 0) wk = 0.f;
+      float sum = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) sum = __fadd_rn(sum, __shfl_sync(gmask, wk, gl0 + k));
+      ids[si] = id;
+      wts[si] = __fdiv_rn(wk, __fadd_rn(sum, 1e-8f));
+    }
+    // (2) channel passes: lane `sub` owns channels ch0 + 4 sub .. + 3 of every pass (one pass for c <= 32); lanes whose
+    // channels lie beyond c still run the shuffles and skip only the loads / stores
+    for (int ch0 = 0; ch0 < c; ch0 += 32) {
+      const int ch = ch0 + 4 * sub;
+      const bool mine = ch < c;
       float4 total = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int si = 0; si < 4; ++si) {
-        if (si >= sc.count) break;
-        const int s = sc.stride[si];
-        const float fs = (float)s;
-        float pf[3], lo[3], hi[3];
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-          pf[a] = (s != 1) ? __fmul_rn(floorf(__fdiv_rn(pv[a], fs)), fs) : floorf(pv[a]);
-          lo[a] = __fsub_rn(__fadd_rn(pf[a], fs), pv[a]);
-          hi[a] = __fsub_rn(pv[a], pf[a]);
-        }
-        float wk = __fmul_rn(__fmul_rn(ix ? hi[0] : lo[0], iy ? hi[1] : lo[1]), iz ? hi[2] : lo[2]);
-        if (s != 1) wk = __fdiv_rn(wk, (float)(s * s * s));
-        int id = -1;
-        if (wk != 0.f && live) {   // a zero-weight corner contributes nothing whether it exists or not
-          const int x = floor_to_stride(pv[0], s) + ix * s, y = floor_to_stride(pv[1], s) + iy * s,
-                    z = floor_to_stride(pv[2], s) + iz * s;
-          if (coord_in_range(x, y, z, b)) id = table_find_coord(sc.tab[si], sc.mask[si], pack_coord(x, y, z, b));
-        }
-        if (id < 0) wk = 0.f;
-        float sum = 0.f;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) sum = __fadd_rn(sum, __shfl_sync(gmask, wk, gl0 + k));
-        wk = __fdiv_rn(wk, __fadd_rn(sum, 1e-8f));
+        if (si >= sc.count) continue;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         const float *f = sc.feats[si];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          const int v = __shfl_sync(gmask, id, gl0 + k);
-          const float w = __shfl_sync(gmask, wk, gl0 + k);
-          if (v >= 0) {
+          const int v = __shfl_sync(gmask, ids[si], gl0 + k);
+          const float w = __shfl_sync(gmask, wts[si], gl0 + k);
+          if (v >= 0 && mine) {
             const float4 r = __ldg(reinterpret_cast<const float4 *>(f + (int64_t)v * c + ch));
             acc.x += w * r.x; acc.y += w * r.y; acc.z += w * r.z; acc.w += w * r.w;
           }
         }
         total.x += acc.x; total.y += acc.y; total.z += acc.z; total.w += acc.w;
       }
-      if (live) {
+      if (live && mine) {
         float *o = out + j * c_out + ch;
         if (ch + 0 < c_out) o[0] = total.x;
         if (ch + 1 < c_out) o[1] = total.y;

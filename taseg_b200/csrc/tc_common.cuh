@@ -117,16 +117,26 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-struct TcParams {
+// One K stream accumulated into an output tile: the kernel offsets of a convolution over (in0 | in1), or a folded 1x1x1
+// shortcut convolution of a residual block (K = 1, its index line = the centre offset of the block's kernel map).
+struct TcPhase {
   const __nv_bfloat16 *in0, *in1;
+  const uint8_t *packed_w;
+  const int *nbr;                 // NULL = identity map (tile row r reads row r; only without perm)
+  long long nbr_stride;           // elements between offsets of nbr; multiple of 256, padding rows hold -1
+  unsigned long long slice_need;  // 4 bits per slice j < Q: which of the P offsets of a virtual offset slice j touches
   int c0, c1;
   int pk, kq, cpo;                // K-slice packing: offsets per virtual offset (P), slices per virtual offset (Q), chunks per offset
-  unsigned long long slice_need;  // 4 bits per slice j < Q: which of the P offsets of a virtual offset slice j touches
-  const uint8_t *packed_w;
-  int K, c_out, na, nb;
-  int ksmax;                      // most kernel offsets one K slice touches (sizes the producers' index buffers)
-  const int *nbr;
-  long long nbr_stride;  // elements between offsets of nbr; multiple of 256, padding rows hold -1
+  int K;
+};
+struct TcParams {
+  TcPhase ph[2];
+  int n_phases;
+  int c_out;   // row pitch of out / residual / bias
+  int n_eff;   // accumulator width of one work item: c_out / ns
+  int ns;      // N split: work item = (super tile, column block of n_eff channels)
+  int na;      // pipeline stages
+  int ksmax;   // most kernel offsets one K slice touches, over both phases (sizes the producers' index buffers)
   const unsigned *tile_mask;
   const int *perm;  // tile row r -> output row (NULL = identity); nbr / tile_mask are indexed by tile row
   long long n_out;

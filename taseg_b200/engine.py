@@ -44,33 +44,56 @@ def conv_map(km, transposed: bool = False):
     return (km.nbr_t if transposed else km.nbr, km.tile_mask(transposed), None)
 
 
+FOLD_SHORTCUT = os.environ.get("TSG_FOLD_SHORTCUT", "1") != "0"   # A/B switch: 1x1 shortcut as a second K phase of conv 2
+
+
+def _fold_pack(kernel: torch.Tensor, bn, r0: int, r1: int, c_out_pad: int, bias: Optional[torch.Tensor] = None):
+    """(K, r0 + r1, c_out) kernel + BN -> (packed bf16 image with the BN scale folded in, fp32 shift (c_out_pad))."""
+    w = kernel.detach().float()
+    if w.dim() == 2:
+        w = w.unsqueeze(0)
+    k, c_in, c_out = w.shape
+    assert c_in == r0 + r1, (c_in, r0, r1)
+    c0, c1 = pad16(r0), pad16(r1) if r1 else 0
+    scale, shift = _fold(bn, c_out, w.device)
+    if bias is not None:
+        shift = shift + bias.detach().float() * scale
+    wp = torch.zeros((k, c0 + c1, c_out_pad), device=w.device)
+    wp[:, :r0, :c_out] = w[:, :r0] * scale
+    if r1:
+        wp[:, c0:c0 + r1, :c_out] = w[:, r0:] * scale
+    sh = torch.zeros(c_out_pad, device=w.device)
+    sh[:c_out] = shift
+    return ops.pack_weights(wp, c0, c1), sh, k, c0, c1
+
+
 class FusedConv:
-    """Conv3d (+BN) compiled for tsg_conv_fwd_tc.  r0/r1 = real channels of the (up to) two input tensors."""
+    """Conv3d (+BN) compiled for tsg_conv_fwd_tc2.  r0/r1 = real channels of the (up to) two input tensors.
+    shortcut = (kernel, bn, s0, s1): a 1x1x1 convolution (+BN) of a second pair of tensors with s0/s1 real channels,
+    accumulated into the same output tile (ResidualBlock's downsample branch)."""
 
-    def __init__(self, kernel: torch.Tensor, bn, r0: int, r1: int = 0, relu: bool = False, bias: Optional[torch.Tensor] = None):
-        w = kernel.detach().float()
-        if w.dim() == 2:
-            w = w.unsqueeze(0)
-        k, c_in, c_out = w.shape
-        assert c_in == r0 + r1, (c_in, r0, r1)
-        self.k, self.c_out, self.relu = k, c_out, relu
-        self.c0, self.c1, self.c_out_pad = pad16(r0), pad16(r1) if r1 else 0, pad16(c_out)
-        scale, shift = _fold(bn, c_out, w.device)
-        if bias is not None:
-            shift = shift + bias.detach().float() * scale
-        wp = torch.zeros((k, self.c0 + self.c1, self.c_out_pad), device=w.device)
-        wp[:, :r0, :c_out] = w[:, :r0] * scale
-        if r1:
-            wp[:, self.c0:self.c0 + r1, :c_out] = w[:, r0:] * scale
-        self.packed = ops.pack_weights(wp, self.c0, self.c1)
-        self.bias = torch.zeros(self.c_out_pad, device=w.device)
-        self.bias[:c_out] = shift
+    def __init__(self, kernel: torch.Tensor, bn, r0: int, r1: int = 0, relu: bool = False, bias: Optional[torch.Tensor] = None,
+                 shortcut=None):
+        c_out = kernel.shape[-1]
+        self.c_out, self.relu, self.c_out_pad = c_out, relu, pad16(c_out)
+        self.packed, self.bias, self.k, self.c0, self.c1 = _fold_pack(kernel, bn, r0, r1, self.c_out_pad, bias)
+        self.sc_packed = None
+        if shortcut is not None:
+            sk, sbn, s0, s1 = shortcut
+            assert sk.shape[-1] == c_out
+            self.sc_packed, sc_shift, _, self.sc0, self.sc1 = _fold_pack(sk, sbn, s0, s1, self.c_out_pad)
+            self.bias = self.bias + sc_shift
 
-    def __call__(self, x0, x1, m, n_out, residual=None, out_dtype=torch.bfloat16):
-        """m = (nbr, tile_mask, perm) from conv_map(), or None for the identity map (1x1x1 convolutions, point MLPs)."""
+    def __call__(self, x0, x1, m, n_out, residual=None, out_dtype=torch.bfloat16, sc_in=None):
+        """m = (nbr, tile_mask, perm) from conv_map(), or None for the identity map (1x1x1 convolutions, point MLPs).
+        sc_in = (s0, s1 | None): the inputs of the folded shortcut."""
         nbr, tile_mask, perm = m if m is not None else (None, None, None)
+        shortcut = None
+        if self.sc_packed is not None:
+            centre = nbr[self.k // 2] if perm is not None else None     # identity in tile-row order = the centre offset's line
+            shortcut = (sc_in[0], sc_in[1], self.sc_packed, centre)
         return ops.conv_forward_tc(x0, x1, self.packed, self.k, self.c_out_pad, nbr, tile_mask, n_out, bias=self.bias,
-                                   residual=residual, relu=self.relu, out_dtype=out_dtype, perm=perm)
+                                   residual=residual, relu=self.relu, out_dtype=out_dtype, perm=perm, shortcut=shortcut)
 
 
 class FusedBlock:
@@ -80,14 +103,23 @@ class FusedBlock:
         net = block.net
         assert isinstance(net[0], Conv3d) and len(net) == 5, "engine supports ResBlock (the only block TASeg configures)"
         self.a = FusedConv(net[0].kernel, net[1], r0, r1, relu=True)
-        self.b = FusedConv(net[3].kernel, net[4], net[3].in_channels, 0, relu=True)
-        self.shortcut = None
-        if not isinstance(block.downsample, nn.Identity):
-            self.shortcut = FusedConv(block.downsample[0].kernel, block.downsample[1], r0, r1, relu=False)
+        self.shortcut, self.folded = None, False
+        has_sc = not isinstance(block.downsample, nn.Identity)
+        fold = has_sc and FOLD_SHORTCUT and net[3].kernel.dim() == 3 and net[3].kernel.shape[0] == 27
+        if fold:    # shortcut as extra K slices of the second convolution (same accumulator, one launch less)
+            self.b = FusedConv(net[3].kernel, net[4], net[3].in_channels, 0, relu=True,
+                               shortcut=(block.downsample[0].kernel, block.downsample[1], r0, r1))
+            self.folded = True
+        else:
+            self.b = FusedConv(net[3].kernel, net[4], net[3].in_channels, 0, relu=True)
+            if has_sc:
+                self.shortcut = FusedConv(block.downsample[0].kernel, block.downsample[1], r0, r1, relu=False)
 
     def __call__(self, x0, x1, km):
         n, m = km.n_out, conv_map(km)
         h = self.a(x0, x1, m, n)
+        if self.folded:
+            return self.b(h, None, m, n, sc_in=(x0, x1))
         res = self.shortcut(x0, x1, None, n) if self.shortcut is not None else x0
         return self.b(h, None, m, n, residual=res)
 

@@ -462,9 +462,11 @@ PROFILE = None   # set to a list to record (tag, start_event, end_event, pairs, 
 def conv_forward_tc(in0: torch.Tensor, in1: Optional[torch.Tensor], packed_w: torch.Tensor, k: int, c_out: int,
                     nbr: torch.Tensor, tile_mask: torch.Tensor, n_out: int, bias: Optional[torch.Tensor] = None,
                     residual: Optional[torch.Tensor] = None, relu: bool = False, out_dtype=torch.bfloat16,
-                    num_sms: int = 0, perm: Optional[torch.Tensor] = None) -> torch.Tensor:
+                    num_sms: int = 0, perm: Optional[torch.Tensor] = None, shortcut=None) -> torch.Tensor:
     """tcgen05/TMEM implicit GEMM; in0/in1 bf16 (n_in, c) with c % 16 == 0.  With `perm`, nbr/tile_mask are in the
-    mask-sorted tile-row order of KernelMap.sorted() and tile row r is written to out[perm[r]]."""
+    mask-sorted tile-row order of KernelMap.sorted() and tile row r is written to out[perm[r]].
+    shortcut = (sc_in0, sc_in1 | None, sc_packed_w, sc_idx | None): a 1x1x1 convolution of (sc_in0 | sc_in1) (n_out rows)
+    accumulated into the same tile (tsg_conv_fwd_tc2); sc_idx = the centre offset's line of `nbr` for sorted maps."""
     assert in0.dtype == torch.bfloat16 and in0.is_contiguous()
     c0 = in0.shape[1]
     c1 = 0
@@ -481,13 +483,26 @@ def conv_forward_tc(in0: torch.Tensor, in1: Optional[torch.Tensor], packed_w: to
             nbr = torch.nn.functional.pad(nbr, (0, want - nbr.shape[1]), value=-1)
         assert nbr.is_contiguous()
         nbr_stride = nbr.shape[1]
+    s0 = s1 = sw = sidx = None
+    sc0 = sc1 = 0
+    if shortcut is not None:
+        s0, s1, sw, sidx = shortcut
+        assert s0.dtype == torch.bfloat16 and s0.is_contiguous() and s0.shape[0] == n_out
+        sc0 = s0.shape[1]
+        if s1 is not None:
+            assert s1.dtype == torch.bfloat16 and s1.is_contiguous() and s1.shape[0] == n_out
+            sc1 = s1.shape[1]
+        if sidx is not None:
+            assert sidx.dtype == torch.int32 and sidx.is_contiguous() and sidx.numel() >= nbr_stride
     if PROFILE is not None:
         pairs = (nbr >= 0).sum() if nbr is not None else torch.tensor(n_out * k, device=in0.device)
+        if shortcut is not None:     # the folded 1x1 convolution's MACs, expressed in pairs of the main phase's width
+            pairs = pairs.double() + n_out * (sc0 + sc1) / (c0 + c1)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    call("tsg_conv_fwd_tc", ptr(in0), c0, ptr(in1), c1, in0.shape[0], ptr(packed_w), k, c_out, ptr(nbr), nbr_stride, ptr(tile_mask),
-         ptr(perm), int(n_out), ptr(out), L.DTYPES[out_dtype], ptr(bias), ptr(residual), int(relu), int(num_sms),
-         ptr(_sched_ws(in0.device)) if DYNAMIC_TILES else None, stream())
+    call("tsg_conv_fwd_tc2", ptr(in0), c0, ptr(in1), c1, in0.shape[0], ptr(packed_w), k, c_out, ptr(nbr), nbr_stride,
+         ptr(tile_mask), ptr(perm), int(n_out), ptr(s0), sc0, ptr(s1), sc1, ptr(sw), ptr(sidx), ptr(out), L.DTYPES[out_dtype],
+         ptr(bias), ptr(residual), int(relu), int(num_sms), ptr(_sched_ws(in0.device)) if DYNAMIC_TILES else None, stream())
     if PROFILE is not None:
         e1.record()
         PROFILE.append((k, e0, e1, pairs, c0 + c1, c_out, n_out))

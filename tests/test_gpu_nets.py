@@ -249,6 +249,39 @@ def test_full_width_network_against_oracle():
     assert l2 < 3e-2 and agree > 0.99, (l2, agree)
 
 
+def test_full_size_batch4_against_reference(golden):
+    """BASELINE configs[1] at FULL size — the exact batch bench.py times (seeds 2000..2003, 3 frames, 702 k voxels,
+    MinkUNetMs mk34 cr1.0, bench.make_model weights) — against the reference run in the build container
+    (tests/golden/make_golden_full.py: compiled reference CPU backend, one scan at a time): voxel counts and coordinate
+    hashes bit-exact, bf16 engine logits within 3e-2 / 99 % arg-max, fp32 module path within 1e-3."""
+    import bench
+    from taseg_b200 import frontend
+    from taseg_b200.engine import Engine
+    g = golden("full_cfg1")
+    step = int(g["step"])
+    model = bench.make_model()
+    samples = bench.make_samples(2000, bench.BATCH)
+    mfb = frontend.MultiFrameBatch([s[0] for s in samples], [s[1] for s in samples])
+    pts, cur_idx = cu(mfb.points), cu(mfb.cur_idx)
+    out = frontend.aggregate_voxelize(pts, mfb, bench.VOXEL, cur_idx)
+    coords = out["coords"].cpu().numpy()
+    for b in range(bench.BATCH):
+        cb = coords[coords[:, 3] == b][:, :3]
+        assert len(cb) == int(g[f"n_vox_{b}"]) and mfb.n_cur[b] == int(g[f"n_cur_{b}"])
+        assert sha(cb, np.int32) == str(g[f"coords_sha_{b}"]), b
+    logits = Engine(model)(out["coords"], out["feats"], field_bits=out["field_bits"], out_rows=out["cur_rows"]).cpu().numpy()
+    assert logits.shape == (sum(mfb.n_cur), 20)
+    with torch.no_grad():
+        l32 = model.logits(frontend.as_lidar_ms(out))[out["cur_rows"].long()].cpu().numpy()
+    row = 0
+    for b in range(bench.BATCH):
+        want = g[f"logits_{b}"]
+        l2, agree = bf16_ok(logits[row:row + mfb.n_cur[b]][::step], want)
+        assert l2 < 3e-2 and agree > 0.99, (b, l2, agree)
+        assert rel_err(l32[row:row + mfb.n_cur[b]][::step], want) < 1e-3, b
+        row += mfb.n_cur[b]
+
+
 def test_full_size_properties():
     """BASELINE config-2 size (3 frames, full scan): size-independent invariants of the integer path and the convs."""
     from taseg_b200 import frontend, ops, synth

@@ -275,6 +275,41 @@ def test_fuse_and_aggregate(ts, golden):
     assert np.array_equal(npy(f2).view(np.uint32), wf.view(np.uint32)) and np.array_equal(npy(c2), wc)
 
 
+def test_aggregate_with_fsa_keep_mask(ts):
+    """Flexible Step Aggregation on the device (semantickitti_ms.py:303-308): a per-point keep mask over the history
+    scans (class c of scan -j kept iff j % step_c == 0) drives `tsg_aggregate_quantize`'s device `keep` input; the whole
+    front end (warp, FSA drop, clamp, round, shift, dedup) against the data oracle run with the same pseudo labels."""
+    from taseg_b200 import frontend, synth
+    spec = synth.SensorSpec(16, -24.8, 2.0, 300, 1.73, 60.0)
+    steps = [0, 1, 2, 3, 1, 2]                           # class 0 never kept, class 3 only every third scan
+    class_ids = list(range(len(steps)))
+    samples, pseudos, keeps = [], [], []
+    for b in range(2):
+        frames, poses = synth.kitti_sample(500 + b, 4, spec=spec, n_boxes=30)
+        rng = np.random.default_rng(50 + b)
+        pseudo = [rng.integers(0, len(steps), len(f)) for f in frames]
+        samples.append((frames, poses))
+        pseudos.append(pseudo)
+        keep = [np.ones(len(frames[0]), np.uint8)]       # layout of MultiFrameBatch: current, then history oldest first
+        for j in range(len(frames) - 1, 0, -1):
+            keep.append(D.fsa_mask(pseudo[j], -j, steps, class_ids).astype(np.uint8))
+        keeps.append(np.concatenate(keep))
+    mfb = frontend.MultiFrameBatch([s[0] for s in samples], [s[1] for s in samples])
+    keep = np.concatenate(keeps)
+    assert len(keep) == mfb.total and 0.2 < keep.mean() < 0.95
+    out = frontend.aggregate_voxelize(cu(mfb.points), mfb, 0.05, cu(mfb.cur_idx), keep=cu(keep))
+    want_c, want_f, want_pts = [], [], []
+    for b, (frames, poses) in enumerate(samples):
+        ms, n0 = D.aggregate_kitti(frames, poses, pseudo=pseudos[b], flexible_steps=steps, class_ids=class_ids)
+        q = D.quantize_ms(ms[:n0], ms, 0.05)
+        want_c.append(np.concatenate([q["pc_ms"], np.full((len(q["pc_ms"]), 1), b, np.int32)], 1))
+        want_f.append(q["feat_ms"])
+        want_pts.append(q["point_ms"])
+    assert np.array_equal(npy(out["point_ms"]).view(np.uint32), np.concatenate(want_pts).view(np.uint32))
+    assert np.array_equal(npy(out["coords"]), np.concatenate(want_c))
+    assert np.array_equal(npy(out["feats"]).view(np.uint32), np.concatenate(want_f).view(np.uint32))
+
+
 def _tc_case(seed, n, c0, c1, c_out, ks, relu, residual, out_dtype, dense_span):
     from taseg_b200 import ops
     rng = np.random.default_rng(seed)
@@ -325,6 +360,87 @@ def test_conv_tensor_core(ts, c0, c1, c_out, ks):
     assert err < 2e-2, (err, n)
     err, n = _tc_case(c0 + c_out + 1, 700, c0, c1, c_out, ks, False, False, torch.float32, 12)   # partial last tile
     assert err < 1e-2, (err, n)
+
+
+@pytest.mark.parametrize("c_mid,s0,s1,c_out,n", [(96, 96, 32, 96, 40000), (64, 32, 0, 64, 40000), (256, 256, 128, 256, 40000),
+                                                 (256, 128, 0, 256, 9000), (128, 192, 0, 128, 9000), (32, 16, 0, 32, 900)])
+def test_conv_tensor_core_folded_shortcut(ts, c_mid, s0, s1, c_out, n):
+    """Second K phase (tsg_conv_fwd_tc2): out = relu(conv3(h) + [x0|x1] @ Ws + bias) in one launch, sorted and unsorted
+    tile rows, against the fp32 kernel + a torch matmul on the same bf16-representable operands.  The 9000-row cases have
+    fewer tiles than SMs (N-split work items)."""
+    from taseg_b200 import ops
+    rng = np.random.default_rng(c_mid + s0 + n)
+    c = np.unique(rng.integers(0, 44, (n, 3)).astype(np.int32), axis=0)
+    c = np.concatenate([c, np.zeros((len(c), 1), np.int32)], 1)
+    n = len(c)
+    km = ops.build_kmap(ops.Table.from_coords(cu(c)), n, cu(c), T.get_kernel_offsets(3, 1))
+    h = torch.randn(n, c_mid, device="cuda").bfloat16()
+    x0 = torch.randn(n, s0, device="cuda").bfloat16()
+    x1 = torch.randn(n, s1, device="cuda").bfloat16() if s1 else None
+    w = torch.randn(27, c_mid, c_out, device="cuda") * 0.1
+    ws = torch.randn(1, s0 + s1, c_out, device="cuda") * 0.1
+    bias = torch.randn(c_out, device="cuda")
+    packed, packed_s = ops.pack_weights(w, c_mid), ops.pack_weights(ws, s0, s1)
+    xin = torch.cat([x0, x1], 1).float() if s1 else x0.float()
+    want = torch.relu(ops.conv_forward(h.float(), w.bfloat16().float(), km.nbr, n) + xin @ ws[0].bfloat16().float() + bias)
+    got = ops.conv_forward_tc(h, None, packed, 27, c_out, km.nbr, km.tile_mask(), n, bias=bias, relu=True,
+                              shortcut=(x0, x1, packed_s, None))
+    nbr_s, mask_s, perm = km.sorted()
+    got_s = ops.conv_forward_tc(h, None, packed, 27, c_out, nbr_s, mask_s, n, bias=bias, relu=True, perm=perm,
+                                shortcut=(x0, x1, packed_s, nbr_s[13]))
+    torch.cuda.synchronize()
+    assert torch.equal(got, got_s), "sorted tile rows change the result of the folded shortcut"
+    assert rel_err(npy(got), npy(want)) < 2e-2
+
+
+def test_conv_tensor_core_column_split(ts, monkeypatch):
+    """TSG_TC_NSPLIT=2: (tile, column half) work items for launches with fewer tiles than SMs must give bit-identical
+    results (every output element sees the same MMAs in the same order)."""
+    from taseg_b200 import ops
+    rng = np.random.default_rng(3)
+    c = np.unique(rng.integers(0, 30, (9000, 3)).astype(np.int32), axis=0)
+    c = np.concatenate([c, np.zeros((len(c), 1), np.int32)], 1)
+    n = len(c)
+    km = ops.build_kmap(ops.Table.from_coords(cu(c)), n, cu(c), T.get_kernel_offsets(3, 1))
+    nbr_s, mask_s, perm = km.sorted()
+    for c_in, c_out in [(256, 256), (64, 128), (32, 96)]:
+        x = torch.randn(n, c_in, device="cuda").bfloat16()
+        res = torch.randn(n, c_out, device="cuda").bfloat16()
+        bias = torch.randn(c_out, device="cuda")
+        packed = ops.pack_weights(torch.randn(27, c_in, c_out, device="cuda") * 0.1, c_in)
+        outs = []
+        for ns in ("1", "2"):
+            monkeypatch.setenv("TSG_TC_NSPLIT", ns)
+            outs.append(ops.conv_forward_tc(x, None, packed, 27, c_out, nbr_s, mask_s, n, bias=bias, residual=res, relu=True, perm=perm))
+        torch.cuda.synchronize()
+        assert torch.equal(outs[0], outs[1]), (c_in, c_out)
+
+
+def test_conv_tensor_core_vs_oracle(ts):
+    """The tensor-core forward and the bf16 weight gradient directly against the numpy oracle (TS conv semantics,
+    oracle/ts_oracle.py conv_forward / conv_backward) on bf16-representable inputs — no detour through our own fp32 kernel."""
+    from taseg_b200 import ops
+    rng = np.random.default_rng(7)
+    c = np.unique(rng.integers(0, 24, (6000, 3)).astype(np.int32), axis=0)
+    c = np.concatenate([c, np.zeros((len(c), 1), np.int32)], 1)
+    n = len(c)
+    offs = T.get_kernel_offsets(3, 1)
+    km = ops.build_kmap(ops.Table.from_coords(cu(c)), n, cu(c), offs)
+    nbmaps, nbsizes = npy(km.nbmaps), npy(km.nbsizes)
+    x = torch.randn(n, 64, device="cuda").bfloat16()
+    w = (torch.randn(27, 64, 96, device="cuda") * 0.1).bfloat16()
+    gy = torch.randn(n, 96, device="cuda").bfloat16()
+    nbr_s, mask_s, perm = km.sorted()
+    got = ops.conv_forward_tc(x, None, ops.pack_weights(w.float(), 64), 27, 96, nbr_s, mask_s, n, perm=perm, out_dtype=torch.float32)
+    want = T.conv_forward(npy(x.float()), npy(w.float()), nbmaps, nbsizes, (n, n), False)
+    assert rel_err(npy(got), want) < 1e-3          # same bf16 operands, fp32 accumulation on both sides
+    gx_ref, gw_ref = T.conv_backward(npy(x.float()), npy(gy.float()), npy(w.float()), nbmaps, nbsizes, False)
+    gw = ops.conv_wgrad_bf16(x, gy, km.nbr, 27)
+    assert rel_err(npy(gw), gw_ref) < 1e-3
+    # bf16 data gradient: tensor-core kernel over the transposed map with W[k]^T (output rounded to bf16)
+    packed_t = ops.pack_weights(w.float().transpose(1, 2).contiguous(), 96)
+    gx = ops.conv_forward_tc(gy, None, packed_t, 27, 64, km.nbr_t, km.tile_mask(True), n, out_dtype=torch.float32)
+    assert rel_err(npy(gx), gx_ref) < 1e-3
 
 
 @pytest.mark.parametrize("c0,span", [(16, 160), (32, 160), (32, 60), (96, 160)])
