@@ -105,6 +105,27 @@ def test_network_bf16_engine(golden, kind):
     assert l2 < 3e-2 and agree > 0.99, (l2, agree)
 
 
+@pytest.mark.parametrize("num_class", [11, 16, 40])
+def test_engine_head_widths(golden, num_class):
+    """Head widths that pad to 16 or 48 channels (the fused devoxelisation tail owns 4 channels per lane, 8 lanes per
+    point: c % 32 != 0 used to leave corner lanes out of the shuffles): bf16 engine vs the fp32 module path."""
+    from taseg_b200 import SparseTensor
+    from taseg_b200.engine import Engine
+    from taseg_b200.segmentor import MinkUNetMs, ModelCfg
+    g = golden("net_minkunet_ms")
+    torch.manual_seed(num_class)
+    cfg = ModelCfg(IN_FEATURE_DIM=5, BLOCK="ResBlock", NUM_LAYER=[1, 1, 1, 1, 1, 1, 1, 1], cr=0.25, IF_DIST=False,
+                   IGNORE_LABEL=0, DROPOUT_P=0.0)
+    model = MinkUNetMs(cfg, num_class).cuda().eval()
+    with torch.no_grad():
+        want = model.logits(SparseTensor(cu(g["feats"]), cu(g["coords"]), 1)).cpu().numpy()
+    rows = torch.arange(0, len(g["coords"]), 3, device="cuda", dtype=torch.int32)
+    got = Engine(model)(cu(g["coords"]), cu(g["feats"]), out_rows=rows).cpu().numpy()
+    assert got.shape == (len(rows), num_class)
+    l2, agree = bf16_ok(got, want[::3])
+    assert l2 < 3e-2 and agree > 0.99, (l2, agree)
+
+
 def test_frontend_matches_reference_loader(golden):
     from taseg_b200 import frontend
     g = golden("net_minkunet_ms")
