@@ -268,6 +268,43 @@ int tsg_conv_fwd_tc2(const void *in0, int c0, const void *in1, int c1, int64_t n
                      int64_t n_out, const void *sc_in0, int sc_c0, const void *sc_in1, int sc_c1,
                      const void *sc_packed_w, const int32_t *sc_idx, void *out, int out_dtype, const float *bias,
                      const void *residual, int relu, int num_sms, int32_t *sched, tsg_stream_t stream);
+/* ---- sync-free variants (graph-capturable inference pipeline, taseg_b200/pipeline.py).
+ * The reference reads every data-dependent size back to the host (`torch.unique`, `nonzero`, `.item()` in
+ * TS/nn/functional/{conv,downsample}.py, TS/utils/quantize.py).  These entry points take the row count from a DEVICE
+ * counter instead: buffers and grids are sized by a host-side capacity `n_cap`, the kernels process
+ * min(*n_dev, n_cap) rows, producers of counters clamp them to the consumer's capacity and set status bit 1 (value 2)
+ * on overflow.  Nothing here allocates, copies from pageable host memory or synchronises, so a whole forward can be
+ * captured into one CUDA graph and replayed. */
+int tsg_conv_fwd_tc3(const void *in0, int c0, const void *in1, int c1, int64_t n_in, const void *packed_w, int k,
+                     int c_out, const int32_t *nbr, int64_t nbr_stride, const uint32_t *tile_mask, const int32_t *perm,
+                     int64_t n_out_cap, const int32_t *n_out_dev, const void *sc_in0, int sc_c0, const void *sc_in1,
+                     int sc_c1, const void *sc_packed_w, const int32_t *sc_idx, void *out, int out_dtype,
+                     const float *bias, const void *residual, int relu, int num_sms, int32_t *sched, tsg_stream_t stream);
+int tsg_unique_coords_dev(const int32_t *in_coords, int64_t n_cap, const int32_t *n_dev, int trunc_stride,
+                          const int32_t *field_bits_host, int32_t *out_coords, int64_t out_cap, int32_t *first_idx,
+                          int32_t *inverse, int32_t *m_dev, int32_t *status, void *ws, size_t ws_bytes, tsg_stream_t stream);
+int tsg_coord_table_build_dev(const int32_t *coords, int64_t n_cap, const int32_t *n_dev, void *table, int64_t slots,
+                              int32_t *status, tsg_stream_t stream);
+/* nbr is (K, n_cap): row stride = capacity; rows >= *n_dev are left untouched */
+int tsg_kmap_build_dev(const void *table, int64_t slots, const int32_t *out_coords, int64_t n_cap, const int32_t *n_dev,
+                       const int32_t *offsets_host, int k, int32_t *nbr, int32_t *nbsizes, int32_t *blockcnt,
+                       tsg_stream_t stream);
+/* nbr (K, n_out_cap) -> nbr_t (K, n_in_cap), -1 where an input row has no output at that offset */
+int tsg_kmap_transpose_dev(const int32_t *nbr, int k, int64_t n_out_cap, const int32_t *n_out_dev, int64_t n_in_cap,
+                           int32_t *nbr_t, tsg_stream_t stream);
+/* nbr (K, in_stride) -> perm (n_cap), nbr_sorted (K, out_stride) with -1 in rows >= *n_dev, tile_mask (ceil(n_cap/128)) */
+int tsg_kmap_sort_rows_dev(const int32_t *nbr, int k, int64_t n_cap, const int32_t *n_dev, int64_t in_stride, int32_t *perm,
+                           int32_t *nbr_sorted, int64_t out_stride, uint32_t *tile_mask, void *ws, size_t ws_bytes,
+                           tsg_stream_t stream);
+int tsg_gather_rows_dev(const void *src, int width, const int32_t *idx, int64_t n_cap, const int32_t *n_dev, void *out,
+                        tsg_stream_t stream);
+int tsg_cast_pad_bf16_dev(const float *in, int64_t n_cap, const int32_t *n_dev, int c, int c_pad, void *out,
+                          tsg_stream_t stream);
+/* tsg_aggregate_quantize with the frame table already on the device (no host copy inside); max_count >= every frame's count */
+int tsg_aggregate_quantize_dev(const float *pts, int c_in, const tsg_frame *frames_dev, int n_frames, int64_t max_count,
+                               int n_samples, const uint8_t *keep, float voxel_size, float *feats, int32_t *coords,
+                               uint8_t *flags, void *ws, size_t ws_bytes, tsg_stream_t stream);
+
 /* Tile-row order for tsg_conv_fwd_tc: stable sort of the n_out output rows by a K-bit key built from their neighbour
  * mask (offset k present iff nbr[k, o] >= 0; for K = 27 the rarest offsets — cube corners, then edges — are the most
  * significant key bits, otherwise bit k = offset k).  Outputs: perm (n_out) int32 = output row of tile row r, nbr_sorted (K, out_stride) with

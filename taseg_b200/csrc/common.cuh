@@ -49,6 +49,14 @@ inline int grid_for(int64_t work_items, int threads, int ctas_per_sm = 8) {
   return (int)(need < cap ? need : cap);
 }
 
+// Row count of a launch: the host value, or — on the sync-free pipeline, where data-dependent sizes never travel to the
+// host — a device counter clamped to the capacity the buffers and the grid were sized for.
+__device__ __forceinline__ int64_t dev_count(const int *n_dev, int64_t n_cap) {
+  if (!n_dev) return n_cap;
+  const int64_t v = *reinterpret_cast<const volatile int *>(n_dev);
+  return v < n_cap ? (v > 0 ? v : 0) : n_cap;
+}
+
 // ------------------------------------------------------------------ coordinate keys
 constexpr int COORD_BITS = 19;
 constexpr int COORD_BIAS = 1 << 18;

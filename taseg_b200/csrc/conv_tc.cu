@@ -214,8 +214,6 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
   const uint32_t stg0 = smem_base + nst * stage_bytes;               // epilogue staging, then the producers' index buffers
   const uint32_t idx0 = stg0 + V8_EPI_WARPS * V8_STG_BYTES;
   const uint32_t idx_warp_bytes = (uint32_t)p.ksmax * G * 128u;      // per producer warp, twice: [offset of the slice][sub-tile][32 rows]
-  const int num_tiles = (int)((p.n_out + TC_BM - 1) / TC_BM);
-  const int num_super = (num_tiles + G - 1) / G;
   const unsigned kmask = p.ph[0].K >= 32 ? 0xffffffffu : ((1u << p.ph[0].K) - 1u);
   const int KV0 = (p.ph[0].K + P0 - 1) / P0, KV1 = NPH > 1 ? (p.ph[1].K + P1 - 1) / P1 : 0;  // virtual offsets
   const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[V8_MAX_STAGES]);
@@ -243,6 +241,9 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
   }
   // ... and nothing produced by the previous kernel is read before it has completed and flushed
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  const long long n_rows = dev_count(p.n_out_dev, p.n_out);   // host value, or the device counter of the sync-free pipeline
+  const int num_tiles = (int)((n_rows + TC_BM - 1) / TC_BM);
+  const int num_super = (num_tiles + G - 1) / G;
   if (threadIdx.x < 256) bias_s[threadIdx.x] = (p.bias && (int)threadIdx.x < p.c_out) ? __ldg(p.bias + threadIdx.x) : 0.f;
   if (threadIdx.x >= 256 && threadIdx.x < 256 + 256) {
     const int t = threadIdx.x - 256, phi = t >> 7, j = (t >> 3) & 15, c = t & 7;
@@ -319,7 +320,7 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
       if (st < 0) break;
       const uint32_t buf = it & 1, ph = (it >> 1) & 1;
       const long long r = (long long)(st * G + g) * TC_BM + quad * 32 + lane;  // destination row: fetched before the long wait
-      const int rows_g = r < p.n_out ? (p.perm ? __ldg(p.perm + r) : (int)r) : -1;
+      const int rows_g = r < n_rows ? (p.perm ? __ldg(p.perm + r) : (int)r) : -1;
       const bool live = st * G + g < num_tiles && cfirst < n_eff;
       if (res_staged && live) prefetch_res(rows_g, cbase + cfirst, blk_cols(cfirst));  // lands while the main loop still runs
       mbar_wait_sleep(tfull0 + 8 * buf, ph);
@@ -595,7 +596,7 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
 #pragma unroll
     for (int q = 0; q < V8_Q; ++q) dst_off[q] = b_bytes + (uint32_t)(rsub * V8_Q + q) * 128u + (uint32_t)((chunk ^ q) << 4);
     const uint32_t ibuf = idx0 + (uint32_t)pw * 2u * idx_warp_bytes;  // double buffered
-    const long long n_out = p.n_out;
+    const long long n_out = n_rows;
     // ---- cursor over the global stage sequence: plan of the current super tile + index of the next stage in it
     int st = -2, n = 0, i = 0, gs = 0;  // gs = (global stage number of plan index i) mod NG
     unsigned masks[2] = {0u, 0u};       // offset masks of the super tile's sub-tiles (phase 0)
@@ -894,9 +895,9 @@ static int fill_phase(TcPhase &h, const void *in0, int c0, const void *in1, int 
   return TSG_OK;
 }
 
-int tsg_conv_fwd_tc2(const void *in0, int c0, const void *in1, int c1, int64_t n_in, const void *packed_w, int k,
+int tsg_conv_fwd_tc3(const void *in0, int c0, const void *in1, int c1, int64_t n_in, const void *packed_w, int k,
                      int c_out, const int32_t *nbr, int64_t nbr_stride, const uint32_t *tile_mask, const int32_t *perm,
-                     int64_t n_out, const void *sc_in0, int sc_c0, const void *sc_in1, int sc_c1,
+                     int64_t n_out, const int32_t *n_out_dev, const void *sc_in0, int sc_c0, const void *sc_in1, int sc_c1,
                      const void *sc_packed_w, const int32_t *sc_idx, void *out, int out_dtype, const float *bias,
                      const void *residual, int relu, int num_sms_hint, int32_t *sched, tsg_stream_t stream) {
   if (c0 % 16 || c1 % 16 || c_out % 16 || c_out > 256 || c_out <= 0 || c0 <= 0 || k <= 0 || k > 32 ||
@@ -938,6 +939,7 @@ int tsg_conv_fwd_tc2(const void *in0, int c0, const void *in1, int c1, int64_t n
   p.tile_mask = tile_mask;
   p.perm = perm;
   p.n_out = n_out;
+  p.n_out_dev = n_out_dev;
   p.out = out;
   p.out_f32 = out_dtype == TSG_F32;
   p.bias = bias;
@@ -1014,6 +1016,16 @@ int tsg_conv_fwd_tc2(const void *in0, int c0, const void *in1, int c1, int64_t n
   if (G == 2) TSG_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<2>, p));
   else TSG_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<1>, p));
   return check_launch("tsg_conv_fwd_tc");
+}
+
+int tsg_conv_fwd_tc2(const void *in0, int c0, const void *in1, int c1, int64_t n_in, const void *packed_w, int k,
+                     int c_out, const int32_t *nbr, int64_t nbr_stride, const uint32_t *tile_mask, const int32_t *perm,
+                     int64_t n_out, const void *sc_in0, int sc_c0, const void *sc_in1, int sc_c1,
+                     const void *sc_packed_w, const int32_t *sc_idx, void *out, int out_dtype, const float *bias,
+                     const void *residual, int relu, int num_sms_hint, int32_t *sched, tsg_stream_t stream) {
+  return tsg_conv_fwd_tc3(in0, c0, in1, c1, n_in, packed_w, k, c_out, nbr, nbr_stride, tile_mask, perm, n_out, nullptr, sc_in0,
+                          sc_c0, sc_in1, sc_c1, sc_packed_w, sc_idx, out, out_dtype, bias, residual, relu, num_sms_hint, sched,
+                          stream);
 }
 
 int tsg_conv_fwd_tc(const void *in0, int c0, const void *in1, int c1, int64_t n_in, const void *packed_w, int k,

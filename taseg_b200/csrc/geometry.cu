@@ -54,8 +54,9 @@ __global__ void table_insert_keys_kernel(const long long *__restrict__ keys, int
     table_insert(tab, mask, (unsigned long long)keys[i], (int)i);
 }
 
-__global__ void table_insert_coords_kernel(const int4 *__restrict__ coords, int64_t n, Slot *tab,
-                                           unsigned long long mask, int *status) {
+__global__ void table_insert_coords_kernel(const int4 *__restrict__ coords, int64_t n, const int *__restrict__ n_dev,
+                                           Slot *tab, unsigned long long mask, int *status) {
+  n = dev_count(n_dev, n);
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int4 c = __ldg(coords + i);
     if (!coord_in_range(c.x, c.y, c.z, c.w)) {
@@ -86,10 +87,12 @@ struct Offsets {
 // ballot, per-offset CTA totals go to blockcnt[k][cta].
 __global__ void __launch_bounds__(256) kmap_build_kernel(const Slot *__restrict__ tab, unsigned long long mask,
                                                          const int4 *__restrict__ out_coords, int64_t n_out,
+                                                         const int *__restrict__ n_dev, int64_t nbr_stride,
                                                          Offsets offs, int K, int ksplit, int *__restrict__ nbr,
                                                          int *__restrict__ nbsizes, int *__restrict__ blockcnt,
                                                          int64_t nblk) {
   __shared__ int s_cnt[32];
+  n_out = dev_count(n_dev, n_out);
   if (threadIdx.x < 32) s_cnt[threadIdx.x] = 0;
   __syncthreads();
   const int64_t base = (int64_t)blockIdx.x * KM_ROWS;
@@ -111,7 +114,7 @@ __global__ void __launch_bounds__(256) kmap_build_kernel(const Slot *__restrict_
       if (ok[r]) {
         const int x = c[r].x + dx, y = c[r].y + dy, z = c[r].z + dz;
         if (coord_in_range(x, y, z, c[r].w)) found = table_find_coord(tab, mask, pack_coord(x, y, z, c[r].w));
-        __stcs(nbr + (int64_t)k * n_out + base + r * 256 + threadIdx.x, found);
+        __stcs(nbr + (int64_t)k * nbr_stride + base + r * 256 + threadIdx.x, found);
       }
       hits += __popc(__ballot_sync(0xffffffffu, found >= 0));
     }
@@ -167,14 +170,15 @@ __global__ void fill_i32_kernel(int *p, int64_t n, int v) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
 }
 
-__global__ void kmap_transpose_kernel(const int *__restrict__ nbr, int64_t total, int64_t n_out, int64_t n_in,
-                                      int *__restrict__ nbr_t) {
+// nbr (K, in_stride) over n_out rows -> nbr_t (K, out_stride): nbr_t[k, nbr[k, o]] = o
+__global__ void kmap_transpose_kernel(const int *__restrict__ nbr, int K, int64_t n_out, const int *__restrict__ n_dev,
+                                      int64_t in_stride, int64_t out_stride, int *__restrict__ nbr_t) {
+  n_out = dev_count(n_dev, n_out);
+  const int64_t total = (int64_t)K * n_out;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-    const int i = nbr[t];
-    if (i >= 0) {
-      const int64_t k = t / n_out, o = t - k * n_out;
-      nbr_t[k * n_in + i] = (int)o;
-    }
+    const int64_t k = t / n_out, o = t - k * n_out;
+    const int i = nbr[k * in_stride + o];
+    if (i >= 0) nbr_t[k * out_stride + i] = (int)o;
   }
 }
 
@@ -267,16 +271,29 @@ int tsg_coord_table_build(const int32_t *coords, int64_t n, void *table, int64_t
   }
   table_clear_kernel<<<grid_for(slots, 256), 256, 0, stream>>>((Slot *)table, slots);
   if (n > 0)
-    table_insert_coords_kernel<<<grid_for(n, 256), 256, 0, stream>>>((const int4 *)coords, n, (Slot *)table,
+    table_insert_coords_kernel<<<grid_for(n, 256), 256, 0, stream>>>((const int4 *)coords, n, nullptr, (Slot *)table,
                                                                      (unsigned long long)(slots - 1), status);
   return check_launch("tsg_coord_table_build");
 }
 
+int tsg_coord_table_build_dev(const int32_t *coords, int64_t n_cap, const int32_t *n_dev, void *table, int64_t slots,
+                              int32_t *status, tsg_stream_t stream) {
+  if (!pow2(slots) || slots < 2 * n_cap) {
+    set_error("tsg_coord_table_build_dev: slots must be a power of two >= 2 n_cap");
+    return TSG_ERR_INVALID;
+  }
+  table_clear_kernel<<<grid_for(slots, 256), 256, 0, stream>>>((Slot *)table, slots);
+  if (n_cap > 0)
+    table_insert_coords_kernel<<<grid_for(n_cap, 256), 256, 0, stream>>>((const int4 *)coords, n_cap, n_dev, (Slot *)table,
+                                                                         (unsigned long long)(slots - 1), status);
+  return check_launch("tsg_coord_table_build_dev");
+}
+
 int64_t tsg_kmap_blocks(int64_t n_out) { return (n_out + KM_ROWS - 1) / KM_ROWS; }
 
-int tsg_kmap_build(const void *table, int64_t slots, const int32_t *out_coords, int64_t n_out,
-                   const int32_t *offsets_host, int k, int32_t *nbr, int32_t *nbsizes, int32_t *blockcnt,
-                   tsg_stream_t stream) {
+static int kmap_build_impl(const void *table, int64_t slots, const int32_t *out_coords, int64_t n_out, const int *n_dev,
+                           int64_t nbr_stride, const int32_t *offsets_host, int k, int32_t *nbr, int32_t *nbsizes,
+                           int32_t *blockcnt, cudaStream_t stream) {
   if (k <= 0 || k > 32 || !pow2(slots)) {
     set_error("tsg_kmap_build: need 1 <= K <= 32 and power-of-two slots");
     return TSG_ERR_INVALID;
@@ -290,9 +307,25 @@ int tsg_kmap_build(const void *table, int64_t slots, const int32_t *out_coords, 
   int ksplit = k;
   while (ksplit > 1 && nblk * ((k + ksplit - 1) / ksplit) < 4LL * num_sms()) ksplit = (ksplit + 2) / 3;
   kmap_build_kernel<<<dim3((unsigned)nblk, (unsigned)((k + ksplit - 1) / ksplit)), 256, 0, stream>>>(
-      (const Slot *)table, (unsigned long long)(slots - 1), (const int4 *)out_coords, n_out, offs, k, ksplit, nbr, nbsizes,
-      blockcnt, nblk);
+      (const Slot *)table, (unsigned long long)(slots - 1), (const int4 *)out_coords, n_out, n_dev, nbr_stride, offs, k, ksplit,
+      nbr, nbsizes, blockcnt, nblk);
   return check_launch("tsg_kmap_build");
+}
+
+int tsg_kmap_build(const void *table, int64_t slots, const int32_t *out_coords, int64_t n_out,
+                   const int32_t *offsets_host, int k, int32_t *nbr, int32_t *nbsizes, int32_t *blockcnt,
+                   tsg_stream_t stream) {
+  return kmap_build_impl(table, slots, out_coords, n_out, nullptr, n_out, offsets_host, k, nbr, nbsizes, blockcnt, stream);
+}
+
+int tsg_kmap_build_dev(const void *table, int64_t slots, const int32_t *out_coords, int64_t n_cap, const int32_t *n_dev,
+                       const int32_t *offsets_host, int k, int32_t *nbr, int32_t *nbsizes, int32_t *blockcnt,
+                       tsg_stream_t stream) {
+  if (!n_dev) {
+    set_error("tsg_kmap_build_dev: need the device row counter");
+    return TSG_ERR_INVALID;
+  }
+  return kmap_build_impl(table, slots, out_coords, n_cap, n_dev, n_cap, offsets_host, k, nbr, nbsizes, blockcnt, stream);
 }
 
 int tsg_kmap_pairs(const int32_t *nbr, int k, int64_t n_out, int32_t *blockcnt, int64_t *nbmaps,
@@ -309,8 +342,18 @@ int tsg_kmap_transpose(const int32_t *nbr, int k, int64_t n_out, int64_t n_in, i
   if (k <= 0) return TSG_OK;
   if (n_in > 0) fill_i32_kernel<<<grid_for(k * n_in, 256), 256, 0, stream>>>(nbr_t, (int64_t)k * n_in, -1);
   if (n_out > 0 && n_in > 0)
-    kmap_transpose_kernel<<<grid_for(k * n_out, 256), 256, 0, stream>>>(nbr, (int64_t)k * n_out, n_out, n_in, nbr_t);
+    kmap_transpose_kernel<<<grid_for(k * n_out, 256), 256, 0, stream>>>(nbr, k, n_out, nullptr, n_out, n_in, nbr_t);
   return check_launch("tsg_kmap_transpose");
+}
+
+int tsg_kmap_transpose_dev(const int32_t *nbr, int k, int64_t n_out_cap, const int32_t *n_out_dev, int64_t n_in_cap,
+                           int32_t *nbr_t, tsg_stream_t stream) {
+  if (k <= 0) return TSG_OK;
+  if (n_in_cap > 0) fill_i32_kernel<<<grid_for(k * n_in_cap, 256), 256, 0, stream>>>(nbr_t, (int64_t)k * n_in_cap, -1);
+  if (n_out_cap > 0 && n_in_cap > 0)
+    kmap_transpose_kernel<<<grid_for(k * n_out_cap, 256), 256, 0, stream>>>(nbr, k, n_out_cap, n_out_dev, n_out_cap, n_in_cap,
+                                                                           nbr_t);
+  return check_launch("tsg_kmap_transpose_dev");
 }
 
 int tsg_kmap_from_pairs(const int32_t *nbmaps, const int32_t *nbsizes_host, int k, int transposed,

@@ -247,7 +247,8 @@ __global__ void __launch_bounds__(256) cp_write_kernel(const uint8_t *__restrict
 }
 
 __global__ void gather_rows_kernel(const uint32_t *__restrict__ src, int width, const int *__restrict__ idx, int64_t n,
-                                   uint32_t *__restrict__ out) {
+                                   const int *__restrict__ n_dev, uint32_t *__restrict__ out) {
+  n = dev_count(n_dev, n);
   const int64_t total = n * width;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
     const int64_t i = t / width;
@@ -498,8 +499,9 @@ __global__ void rescale_coords_kernel(const float4 *__restrict__ pc, int64_t n, 
   }
 }
 
-__global__ void cast_pad_bf16_kernel(const float *__restrict__ in, int64_t n, int c, int c_pad,
-                                     __nv_bfloat16 *__restrict__ out) {
+__global__ void cast_pad_bf16_kernel(const float *__restrict__ in, int64_t n, const int *__restrict__ n_dev, int c,
+                                     int c_pad, __nv_bfloat16 *__restrict__ out) {
+  n = dev_count(n_dev, n);
   const int64_t total = n * c_pad;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
     const int64_t i = t / c_pad;
@@ -575,6 +577,26 @@ int tsg_aggregate_quantize(const float *pts, int c_in, const tsg_frame *frames_h
   return check_launch("tsg_aggregate_quantize");
 }
 
+/* Same passes with the frame table already on the device (graph-capturable: no host-to-device copy inside): frames_dev
+ * holds n_frames tsg_frame records, max_count >= every frame's count (sizes the grid). */
+int tsg_aggregate_quantize_dev(const float *pts, int c_in, const tsg_frame *frames_dev, int n_frames, int64_t max_count,
+                               int n_samples, const uint8_t *keep, float voxel_size, float *feats, int32_t *coords,
+                               uint8_t *flags, void *ws, size_t ws_bytes, tsg_stream_t stream) {
+  if (n_frames <= 0) return TSG_OK;
+  if (n_frames > 1024 || c_in < 3 || n_samples <= 0 || n_samples > 128 || max_count <= 0) {
+    set_error("tsg_aggregate_quantize_dev: need 1<=frames<=1024, c_in>=3, 1<=samples<=128, max_count>0");
+    return TSG_ERR_INVALID;
+  }
+  if (ws_bytes < align256(sizeof(AggWs) * (size_t)n_samples)) { set_error("tsg_aggregate_quantize_dev: workspace too small"); return TSG_ERR_WORKSPACE; }
+  AggWs *aw = (AggWs *)ws;
+  agg_init_kernel<<<1, 128, 0, stream>>>(aw, n_samples);
+  dim3 grid(grid_for(max_count, 256, 2), n_frames);
+  agg_warp_kernel<<<grid, 256, 0, stream>>>(pts, c_in, frames_dev, feats, aw);
+  agg_quant_kernel<<<grid, 256, 0, stream>>>(feats, c_in + 1, frames_dev, keep, voxel_size, (int4 *)coords, flags, aw);
+  agg_shift_kernel<<<grid, 256, 0, stream>>>(frames_dev, (int4 *)coords, aw);
+  return check_launch("tsg_aggregate_quantize_dev");
+}
+
 size_t tsg_compact_ws_bytes(int64_t n) { return align256((size_t)((n > 0 ? n : 1) / CP_ROWS + 2) * 4); }
 
 int tsg_compact_rows(const uint8_t *flags, int64_t n, const void *rows_a, int wa, void *out_a, const void *rows_b,
@@ -596,8 +618,16 @@ int tsg_compact_rows(const uint8_t *flags, int64_t n, const void *rows_a, int wa
 
 int tsg_gather_rows(const void *src, int width, const int32_t *idx, int64_t n, void *out, tsg_stream_t stream) {
   if (n <= 0 || width <= 0) return TSG_OK;
-  gather_rows_kernel<<<grid_for(n * width, 256), 256, 0, stream>>>((const uint32_t *)src, width, idx, n, (uint32_t *)out);
+  gather_rows_kernel<<<grid_for(n * width, 256), 256, 0, stream>>>((const uint32_t *)src, width, idx, n, nullptr, (uint32_t *)out);
   return check_launch("tsg_gather_rows");
+}
+
+int tsg_gather_rows_dev(const void *src, int width, const int32_t *idx, int64_t n_cap, const int32_t *n_dev, void *out,
+                        tsg_stream_t stream) {
+  if (n_cap <= 0 || width <= 0) return TSG_OK;
+  gather_rows_kernel<<<grid_for(n_cap * width, 256), 256, 0, stream>>>((const uint32_t *)src, width, idx, n_cap, n_dev,
+                                                                      (uint32_t *)out);
+  return check_launch("tsg_gather_rows_dev");
 }
 
 int tsg_count(const int32_t *idx, int64_t n, int32_t *out, int64_t m, tsg_stream_t stream) {
@@ -705,8 +735,16 @@ int tsg_rescale_coords(const float *pcoords, int64_t n, float init_res, float af
 int tsg_cast_pad_bf16(const float *in, int64_t n, int c, int c_pad, void *out, tsg_stream_t stream) {
   if (c_pad < c) { set_error("tsg_cast_pad_bf16: c_pad < c"); return TSG_ERR_INVALID; }
   if (n <= 0) return TSG_OK;
-  cast_pad_bf16_kernel<<<grid_for(n * c_pad, 256), 256, 0, stream>>>(in, n, c, c_pad, (__nv_bfloat16 *)out);
+  cast_pad_bf16_kernel<<<grid_for(n * c_pad, 256), 256, 0, stream>>>(in, n, nullptr, c, c_pad, (__nv_bfloat16 *)out);
   return check_launch("tsg_cast_pad_bf16");
+}
+
+int tsg_cast_pad_bf16_dev(const float *in, int64_t n_cap, const int32_t *n_dev, int c, int c_pad, void *out,
+                          tsg_stream_t stream) {
+  if (c_pad < c) { set_error("tsg_cast_pad_bf16_dev: c_pad < c"); return TSG_ERR_INVALID; }
+  if (n_cap <= 0) return TSG_OK;
+  cast_pad_bf16_kernel<<<grid_for(n_cap * c_pad, 256), 256, 0, stream>>>(in, n_cap, n_dev, c, c_pad, (__nv_bfloat16 *)out);
+  return check_launch("tsg_cast_pad_bf16_dev");
 }
 
 }  // extern "C"

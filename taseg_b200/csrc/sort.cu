@@ -26,8 +26,10 @@ struct RsPasses {
 
 // global digit histograms of every pass in one read of the keys: ghist[p][d]
 __global__ void __launch_bounds__(RS_THREADS) rs_global_hist_kernel(const unsigned long long *__restrict__ keys, int64_t n,
-                                                                    RsPasses ps, int *__restrict__ ghist) {
+                                                                    const int *__restrict__ n_dev, RsPasses ps,
+                                                                    int *__restrict__ ghist) {
   __shared__ int hist[RS_MAX_PASSES][RS_BINS];
+  n = dev_count(n_dev, n);
   for (int p = 0; p < ps.count; ++p) hist[p][threadIdx.x] = 0;
   __syncthreads();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -53,7 +55,8 @@ __device__ __forceinline__ void st_volatile_u32(unsigned *p, unsigned v) {
 }
 
 __global__ void __launch_bounds__(RS_THREADS) rs_pass_kernel(const unsigned long long *__restrict__ keys_in,
-                                                             const unsigned *__restrict__ vals_in, int64_t n, int bit,
+                                                             const unsigned *__restrict__ vals_in, int64_t n,
+                                                             const int *__restrict__ n_dev, int bit,
                                                              unsigned dmask, const int *__restrict__ ghist,
                                                              unsigned *__restrict__ look, int *__restrict__ tile_counter,
                                                              unsigned long long *__restrict__ keys_out,
@@ -67,6 +70,8 @@ __global__ void __launch_bounds__(RS_THREADS) rs_pass_kernel(const unsigned long
   for (int w = 0; w < RS_WARPS; ++w) wh[w][tid] = 0;
   __syncthreads();
   const int tile = s_tile;
+  n = dev_count(n_dev, n);
+  if ((int64_t)tile * RS_TILE >= n) return;  // capacity-sized grid: tiles past the device count have no keys and no successors
   const int64_t w0 = (int64_t)tile * RS_TILE + warp * (32 * RS_ITEMS);
   const unsigned lane_lt = (1u << lane) - 1;
   unsigned long long key[RS_ITEMS];
@@ -162,7 +167,7 @@ static size_t sort_ws_layout(int64_t n, char *base, SortWs *ws) {
 
 static int sort_pairs(const unsigned long long *keys_in, const unsigned *vals_in, int64_t n, int begin_bit,
                       int end_bit, unsigned long long *keys_out, unsigned *vals_out, void *ws_mem, size_t ws_bytes,
-                      cudaStream_t stream) {
+                      cudaStream_t stream, const int *n_dev = nullptr) {
   if (n <= 0) return TSG_OK;
   if (n >= (1ll << 30)) {
     set_error("tsg_sort_pairs: n must be < 2^30");
@@ -189,14 +194,14 @@ static int sort_pairs(const unsigned long long *keys_in, const unsigned *vals_in
   }
   TSG_CUDA(cudaMemsetAsync(ws.ghist, 0, ws.zero_bytes, stream));
   const int64_t hist_ctas = ntiles < 4 * num_sms() ? ntiles : 4 * num_sms();
-  rs_global_hist_kernel<<<(unsigned)hist_ctas, RS_THREADS, 0, stream>>>(keys_in, n, ps, ws.ghist);
+  rs_global_hist_kernel<<<(unsigned)hist_ctas, RS_THREADS, 0, stream>>>(keys_in, n, n_dev, ps, ws.ghist);
   const unsigned long long *src_k = keys_in;
   const unsigned *src_v = vals_in;
   for (int p = 0; p < passes; ++p) {
     const bool to_out = ((passes - 1 - p) & 1) == 0;
     unsigned long long *dst_k = to_out ? keys_out : ws.keys_tmp;
     unsigned *dst_v = to_out ? vals_out : ws.vals_tmp;
-    rs_pass_kernel<<<(unsigned)ntiles, RS_THREADS, 0, stream>>>(src_k, src_v, n, ps.bit[p], ps.mask[p],
+    rs_pass_kernel<<<(unsigned)ntiles, RS_THREADS, 0, stream>>>(src_k, src_v, n, n_dev, ps.bit[p], ps.mask[p],
                                                                ws.ghist + p * RS_BINS, ws.look + (size_t)p * ntiles * RS_BINS,
                                                                ws.tile_counter + p, dst_k, dst_v);
     src_k = dst_k;
@@ -225,21 +230,24 @@ static KeyBits key_bits_for(int K) {
   }
   return kb;
 }
-__global__ void row_mask_keys_kernel(const int *__restrict__ nbr, int K, int64_t n_out, KeyBits kb,
-                                     unsigned long long *__restrict__ keys) {
+__global__ void row_mask_keys_kernel(const int *__restrict__ nbr, int K, int64_t n_out, const int *__restrict__ n_dev,
+                                     int64_t in_stride, KeyBits kb, unsigned long long *__restrict__ keys) {
+  n_out = dev_count(n_dev, n_out);
   for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < n_out; o += (int64_t)gridDim.x * blockDim.x) {
     unsigned long long m = 0;
-    for (int k = 0; k < K; ++k) m |= (unsigned long long)(__ldg(nbr + (int64_t)k * n_out + o) >= 0) << kb.pos[k];
+    for (int k = 0; k < K; ++k) m |= (unsigned long long)(__ldg(nbr + (int64_t)k * in_stride + o) >= 0) << kb.pos[k];
     keys[o] = m;
   }
 }
 // nbr_sorted[k, r] = nbr[k, perm[r]] for r < n_out and -1 in the padding rows [n_out, out_stride)
 __global__ void permute_nbr_kernel(const int *__restrict__ nbr, const int *__restrict__ perm, int K, int64_t n_out,
-                                   int64_t out_stride, int *__restrict__ nbr_sorted) {
+                                   const int *__restrict__ n_dev, int64_t in_stride, int64_t out_stride,
+                                   int *__restrict__ nbr_sorted) {
+  n_out = dev_count(n_dev, n_out);
   for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < out_stride; r += (int64_t)gridDim.x * blockDim.x) {
     if (r < n_out) {
       const int o = __ldg(perm + r);
-      for (int k = 0; k < K; ++k) nbr_sorted[(int64_t)k * out_stride + r] = __ldg(nbr + (int64_t)k * n_out + o);
+      for (int k = 0; k < K; ++k) nbr_sorted[(int64_t)k * out_stride + r] = __ldg(nbr + (int64_t)k * in_stride + o);
     } else {
       for (int k = 0; k < K; ++k) nbr_sorted[(int64_t)k * out_stride + r] = -1;
     }
@@ -247,9 +255,10 @@ __global__ void permute_nbr_kernel(const int *__restrict__ nbr, const int *__res
 }
 // tile_mask[t] = which offsets occur in tile rows [128 t, 128 t + 128): OR of the SORTED keys, key bits mapped back to offsets
 __global__ void __launch_bounds__(128) tile_mask_from_keys_kernel(const unsigned long long *__restrict__ keys_sorted,
-                                                                  int64_t n_out, KeyBits kb, int K,
-                                                                  unsigned *__restrict__ tile_mask) {
+                                                                  int64_t n_out, const int *__restrict__ n_dev,
+                                                                  KeyBits kb, int K, unsigned *__restrict__ tile_mask) {
   __shared__ unsigned long long s_or[4];
+  n_out = dev_count(n_dev, n_out);
   const int64_t r = (int64_t)blockIdx.x * 128 + threadIdx.x;
   unsigned long long m = r < n_out ? keys_sorted[r] : 0ull;
 #pragma unroll
@@ -279,8 +288,9 @@ __device__ inline int4 unpack_dense(unsigned long long k, int4 fb) {
   return c;
 }
 
-__global__ void make_coord_keys_kernel(const int4 *__restrict__ coords, int64_t n, int trunc_stride, int4 fb,
-                                       unsigned long long *__restrict__ keys, int *status) {
+__global__ void make_coord_keys_kernel(const int4 *__restrict__ coords, int64_t n, const int *__restrict__ n_dev,
+                                       int trunc_stride, int4 fb, unsigned long long *__restrict__ keys, int *status) {
+  n = dev_count(n_dev, n);
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     int4 c = __ldg(coords + i);
     if (trunc_stride > 0) {  // torch.div(...).trunc() * stride: C integer division truncates toward zero as well
@@ -314,7 +324,8 @@ __global__ void make_hash_keys_kernel(const int4 *__restrict__ coords, int64_t n
 constexpr int UQ_ROWS = 1024;
 
 __global__ void __launch_bounds__(256) uq_count_kernel(const unsigned long long *__restrict__ skeys, int64_t n,
-                                                       int *__restrict__ blocksum) {
+                                                       const int *__restrict__ n_dev, int *__restrict__ blocksum) {
+  n = dev_count(n_dev, n);
   const int64_t base = (int64_t)blockIdx.x * UQ_ROWS + threadIdx.x * 4;
   int c = 0;
 #pragma unroll
@@ -327,7 +338,8 @@ __global__ void __launch_bounds__(256) uq_count_kernel(const unsigned long long 
   if (threadIdx.x == 0) blocksum[blockIdx.x] = tot;
 }
 
-__global__ void __launch_bounds__(1024) uq_scan_kernel(int *data, int64_t n, int *total_out) {
+// total_out = number of runs, clamped to out_cap (status bit 1 = the consumer's capacity was exceeded)
+__global__ void __launch_bounds__(1024) uq_scan_kernel(int *data, int64_t n, int *total_out, int64_t out_cap, int *status) {
   __shared__ int carry;
   if (threadIdx.x == 0) carry = 0;
   __syncthreads();
@@ -341,15 +353,23 @@ __global__ void __launch_bounds__(1024) uq_scan_kernel(int *data, int64_t n, int
     if (threadIdx.x == 0) carry += tot;
     __syncthreads();
   }
-  if (threadIdx.x == 0 && total_out) *total_out = carry;
+  if (threadIdx.x == 0 && total_out) {
+    if (out_cap > 0 && carry > out_cap) {
+      if (status) atomicOr(status, 2);
+      carry = (int)out_cap;
+    }
+    *total_out = carry;
+  }
 }
 
 // hash_mode: coordinates are not recoverable from the key -> copy them from the first member of the run
 __global__ void __launch_bounds__(256) uq_write_kernel(const unsigned long long *__restrict__ skeys,
                                                        const unsigned *__restrict__ sidx, int64_t n,
+                                                       const int *__restrict__ n_dev, int64_t out_cap,
                                                        const int *__restrict__ blockoff, int hash_mode, int4 fb,
                                                        const int4 *__restrict__ in_coords, int4 *__restrict__ out_coords,
                                                        int *__restrict__ first_idx, int *__restrict__ inverse) {
+  n = dev_count(n_dev, n);
   const int64_t base = (int64_t)blockIdx.x * UQ_ROWS + threadIdx.x * 4;
   bool head[4];
   int c = 0;
@@ -367,6 +387,7 @@ __global__ void __launch_bounds__(256) uq_write_kernel(const unsigned long long 
     const unsigned src = sidx[j];
     if (head[r]) {
       ++vid;
+      if (out_cap > 0 && vid >= out_cap) continue;   // capacity overflow (flagged by uq_scan_kernel): drop, stay in bounds
       if (out_coords)
         out_coords[vid] = hash_mode ? __ldg(in_coords + src) : (fb.x > 0 ? unpack_dense(skeys[j], fb) : unpack_coord(skeys[j]));
       if (first_idx) first_idx[vid] = (int)src;
@@ -404,7 +425,7 @@ static size_t unique_ws_layout(int64_t n, char *base, UniqueWs *ws) {
 
 static int unique_impl(const int32_t *in_coords, int64_t n, int trunc_stride, bool hash_mode, int4 fb, int32_t *out_coords,
                        int32_t *first_idx, int32_t *inverse, int32_t *m_dev, int32_t *status, void *ws_mem,
-                       size_t ws_bytes, cudaStream_t stream) {
+                       size_t ws_bytes, cudaStream_t stream, const int *n_dev = nullptr, int64_t out_cap = 0) {
   if (n <= 0) {
     if (m_dev) TSG_CUDA(cudaMemsetAsync(m_dev, 0, sizeof(int), stream));
     return TSG_OK;
@@ -417,15 +438,15 @@ static int unique_impl(const int32_t *in_coords, int64_t n, int trunc_stride, bo
   if (hash_mode)
     make_hash_keys_kernel<<<grid_for(n, 256), 256, 0, stream>>>((const int4 *)in_coords, n, ws.keys);
   else
-    make_coord_keys_kernel<<<grid_for(n, 256), 256, 0, stream>>>((const int4 *)in_coords, n, trunc_stride, fb, ws.keys,
+    make_coord_keys_kernel<<<grid_for(n, 256), 256, 0, stream>>>((const int4 *)in_coords, n, n_dev, trunc_stride, fb, ws.keys,
                                                                 status);
   const int key_bits = hash_mode ? 60 : (fb.x > 0 ? fb.x + fb.y + fb.z + fb.w : 64);
-  int rc = sort_pairs(ws.keys, nullptr, n, 0, key_bits, ws.skeys, ws.sidx, ws.sort_ws, ws.sort_bytes, stream);
+  int rc = sort_pairs(ws.keys, nullptr, n, 0, key_bits, ws.skeys, ws.sidx, ws.sort_ws, ws.sort_bytes, stream, n_dev);
   if (rc) return rc;
   const int64_t nblk = (n + UQ_ROWS - 1) / UQ_ROWS;
-  uq_count_kernel<<<(unsigned)nblk, 256, 0, stream>>>(ws.skeys, n, ws.blocksum);
-  uq_scan_kernel<<<1, 1024, 0, stream>>>(ws.blocksum, nblk, m_dev);
-  uq_write_kernel<<<(unsigned)nblk, 256, 0, stream>>>(ws.skeys, ws.sidx, n, ws.blocksum, hash_mode ? 1 : 0, fb,
+  uq_count_kernel<<<(unsigned)nblk, 256, 0, stream>>>(ws.skeys, n, n_dev, ws.blocksum);
+  uq_scan_kernel<<<1, 1024, 0, stream>>>(ws.blocksum, nblk, m_dev, out_cap, status);
+  uq_write_kernel<<<(unsigned)nblk, 256, 0, stream>>>(ws.skeys, ws.sidx, n, n_dev, out_cap, ws.blocksum, hash_mode ? 1 : 0, fb,
                                                       (const int4 *)in_coords, (int4 *)out_coords, first_idx, inverse);
   return check_launch("tsg_unique");
 }
@@ -451,8 +472,9 @@ size_t tsg_kmap_sort_ws_bytes(int64_t n_out) {
 
 int64_t tsg_kmap_sort_stride(int64_t n_out) { return (n_out + 255) / 256 * 256; }
 
-int tsg_kmap_sort_rows(const int32_t *nbr, int k, int64_t n_out, int32_t *perm, int32_t *nbr_sorted, int64_t out_stride,
-                       uint32_t *tile_mask, void *ws, size_t ws_bytes, tsg_stream_t stream) {
+static int kmap_sort_rows_impl(const int32_t *nbr, int k, int64_t n_out, const int *n_dev, int64_t in_stride, int32_t *perm,
+                               int32_t *nbr_sorted, int64_t out_stride, uint32_t *tile_mask, void *ws, size_t ws_bytes,
+                               cudaStream_t stream) {
   if (out_stride < n_out) {
     set_error("tsg_kmap_sort_rows: out_stride < n_out");
     return TSG_ERR_INVALID;
@@ -470,13 +492,24 @@ int tsg_kmap_sort_rows(const int32_t *nbr, int k, int64_t n_out, int32_t *perm, 
   unsigned long long *keys = (unsigned long long *)base;
   unsigned long long *keys_sorted = (unsigned long long *)(base + align256((size_t)n_out * 8));
   char *sort_ws = base + 2 * align256((size_t)n_out * 8);
-  row_mask_keys_kernel<<<grid_for(n_out, 256), 256, 0, stream>>>(nbr, k, n_out, key_bits_for(k), keys);
+  row_mask_keys_kernel<<<grid_for(n_out, 256), 256, 0, stream>>>(nbr, k, n_out, n_dev, in_stride, key_bits_for(k), keys);
   const int rc = sort_pairs(keys, nullptr, n_out, 0, k, keys_sorted, (unsigned *)perm, sort_ws,
-                            ws_bytes - 2 * align256((size_t)n_out * 8), stream);
+                            ws_bytes - 2 * align256((size_t)n_out * 8), stream, n_dev);
   if (rc != TSG_OK) return rc;
-  permute_nbr_kernel<<<grid_for(out_stride, 256), 256, 0, stream>>>(nbr, perm, k, n_out, out_stride, nbr_sorted);
-  tile_mask_from_keys_kernel<<<(unsigned)((n_out + 127) / 128), 128, 0, stream>>>(keys_sorted, n_out, key_bits_for(k), k, tile_mask);
+  permute_nbr_kernel<<<grid_for(out_stride, 256), 256, 0, stream>>>(nbr, perm, k, n_out, n_dev, in_stride, out_stride, nbr_sorted);
+  tile_mask_from_keys_kernel<<<(unsigned)((n_out + 127) / 128), 128, 0, stream>>>(keys_sorted, n_out, n_dev, key_bits_for(k), k, tile_mask);
   return check_launch("tsg_kmap_sort_rows");
+}
+
+int tsg_kmap_sort_rows(const int32_t *nbr, int k, int64_t n_out, int32_t *perm, int32_t *nbr_sorted, int64_t out_stride,
+                       uint32_t *tile_mask, void *ws, size_t ws_bytes, tsg_stream_t stream) {
+  return kmap_sort_rows_impl(nbr, k, n_out, nullptr, n_out, perm, nbr_sorted, out_stride, tile_mask, ws, ws_bytes, stream);
+}
+
+int tsg_kmap_sort_rows_dev(const int32_t *nbr, int k, int64_t n_cap, const int32_t *n_dev, int64_t in_stride, int32_t *perm,
+                           int32_t *nbr_sorted, int64_t out_stride, uint32_t *tile_mask, void *ws, size_t ws_bytes,
+                           tsg_stream_t stream) {
+  return kmap_sort_rows_impl(nbr, k, n_cap, n_dev, in_stride, perm, nbr_sorted, out_stride, tile_mask, ws, ws_bytes, stream);
 }
 
 size_t tsg_unique_ws_bytes(int64_t n) { return unique_ws_layout(n > 0 ? n : 1, nullptr, nullptr); }
@@ -494,6 +527,25 @@ int tsg_unique_coords(const int32_t *in_coords, int64_t n, int trunc_stride, con
   }
   return unique_impl(in_coords, n, trunc_stride, false, fb, out_coords, first_idx, inverse, m_dev, status, ws,
                      ws_bytes, stream);
+}
+
+int tsg_unique_coords_dev(const int32_t *in_coords, int64_t n_cap, const int32_t *n_dev, int trunc_stride,
+                          const int32_t *field_bits_host, int32_t *out_coords, int64_t out_cap, int32_t *first_idx,
+                          int32_t *inverse, int32_t *m_dev, int32_t *status, void *ws, size_t ws_bytes, tsg_stream_t stream) {
+  int4 fb = make_int4(0, 0, 0, 0);
+  if (field_bits_host) {
+    fb = make_int4(field_bits_host[0], field_bits_host[1], field_bits_host[2], field_bits_host[3]);
+    if (fb.x <= 0 || fb.y <= 0 || fb.z <= 0 || fb.w <= 0 || fb.x > 19 || fb.y > 19 || fb.z > 19 || fb.w > 7) {
+      set_error("tsg_unique_coords_dev: field bits must be in 1..19 (x,y,z) and 1..7 (b)");
+      return TSG_ERR_INVALID;
+    }
+  }
+  if (!n_dev || !m_dev || out_cap <= 0) {
+    set_error("tsg_unique_coords_dev: need the device counters and a positive output capacity");
+    return TSG_ERR_INVALID;
+  }
+  return unique_impl(in_coords, n_cap, trunc_stride, false, fb, out_coords, first_idx, inverse, m_dev, status, ws, ws_bytes,
+                     stream, n_dev, out_cap);
 }
 
 int tsg_unique_hash(const int32_t *in_coords, int64_t n, int32_t *out_coords, int32_t *first_idx, int32_t *inverse,

@@ -139,7 +139,8 @@ struct TcParams {
   int ksmax;   // most kernel offsets one K slice touches, over both phases (sizes the producers' index buffers)
   const unsigned *tile_mask;
   const int *perm;  // tile row r -> output row (NULL = identity); nbr / tile_mask are indexed by tile row
-  long long n_out;
+  long long n_out;        // output rows (capacity when n_out_dev is set)
+  const int *n_out_dev;   // sync-free pipeline: the row count lives on the device
   void *out;
   int out_f32;
   const float *bias;

@@ -84,16 +84,17 @@ class FusedConv:
             self.sc_packed, sc_shift, _, self.sc0, self.sc1 = _fold_pack(sk, sbn, s0, s1, self.c_out_pad)
             self.bias = self.bias + sc_shift
 
-    def __call__(self, x0, x1, m, n_out, residual=None, out_dtype=torch.bfloat16, sc_in=None):
+    def __call__(self, x0, x1, m, n_out, residual=None, out_dtype=torch.bfloat16, sc_in=None, n_dev=None):
         """m = (nbr, tile_mask, perm) from conv_map(), or None for the identity map (1x1x1 convolutions, point MLPs).
-        sc_in = (s0, s1 | None): the inputs of the folded shortcut."""
+        sc_in = (s0, s1 | None): the inputs of the folded shortcut.  n_dev: device row counter (n_out is then a capacity)."""
         nbr, tile_mask, perm = m if m is not None else (None, None, None)
         shortcut = None
         if self.sc_packed is not None:
             centre = nbr[self.k // 2] if perm is not None else None     # identity in tile-row order = the centre offset's line
             shortcut = (sc_in[0], sc_in[1], self.sc_packed, centre)
         return ops.conv_forward_tc(x0, x1, self.packed, self.k, self.c_out_pad, nbr, tile_mask, n_out, bias=self.bias,
-                                   residual=residual, relu=self.relu, out_dtype=out_dtype, perm=perm, shortcut=shortcut)
+                                   residual=residual, relu=self.relu, out_dtype=out_dtype, perm=perm, shortcut=shortcut,
+                                   n_dev=n_dev)
 
 
 class FusedBlock:
@@ -115,17 +116,30 @@ class FusedBlock:
             if has_sc:
                 self.shortcut = FusedConv(block.downsample[0].kernel, block.downsample[1], r0, r1, relu=False)
 
-    def __call__(self, x0, x1, km):
-        n, m = km.n_out, conv_map(km)
-        h = self.a(x0, x1, m, n)
+    def __call__(self, x0, x1, m, n, n_dev=None):
+        """m = (nbr, tile_mask, perm) of the level's 3x3x3 map, n rows (capacity when n_dev is given)."""
+        h = self.a(x0, x1, m, n, n_dev=n_dev)
         if self.folded:
-            return self.b(h, None, m, n, sc_in=(x0, x1))
-        res = self.shortcut(x0, x1, None, n) if self.shortcut is not None else x0
-        return self.b(h, None, m, n, residual=res)
+            return self.b(h, None, m, n, sc_in=(x0, x1), n_dev=n_dev)
+        res = self.shortcut(x0, x1, None, n, n_dev=n_dev) if self.shortcut is not None else x0
+        return self.b(h, None, m, n, residual=res, n_dev=n_dev)
 
 
 class Level:
-    __slots__ = ("stride", "coords", "n", "table", "km3", "km2")
+    """One pyramid level: n rows (exact, or the buffer capacity when the count lives on the device in n_dev)."""
+    __slots__ = ("stride", "coords", "n", "n_dev", "table", "km3", "km2", "m3", "m2", "m2t")
+
+    def map3(self):
+        """(nbr, tile_mask, perm) of the 3x3x3 stride-1 map at this level."""
+        return self.m3 if self.m3 is not None else conv_map(self.km3)
+
+    def map2(self):
+        """... of the 2x2x2 stride-2 map to the next coarser level (rows = coarse voxels)."""
+        return self.m2 if self.m2 is not None else conv_map(self.km2)
+
+    def map2t(self):
+        """... of its transpose (rows = this level's voxels): the transposed convolution of the decoder."""
+        return self.m2t if self.m2t is not None else conv_map(self.km2, True)
 
 
 class Geometry:
@@ -136,6 +150,7 @@ class Geometry:
         c = coords.contiguous()
         for l in range(n_levels):
             lv = Level()
+            lv.n_dev = lv.m3 = lv.m2 = lv.m2t = None
             lv.stride, lv.coords, lv.n = 2 ** l, c, c.shape[0]
             lv.table = ops.Table.from_coords(c)
             lv.km3 = ops.build_kmap(lv.table, lv.n, c, kernel_offsets_np(3, lv.stride))
@@ -213,12 +228,22 @@ class Engine:
         else:
             vox, x_f = coords.contiguous(), feats
         geo = Geometry(vox, field_bits=field_bits if not self.voxelize_input else None)
+        aux = dict(zc=zc, inv0=inv0, cnt0=cnt0) if self.voxelize_input else dict(zc=zc)
+        logits = self.run(geo, x_f, aux, out_rows)
+        return (logits, geo) if return_geometry else logits
+
+    @torch.no_grad()
+    def run(self, geo, x_f: torch.Tensor, aux: dict, out_rows: Optional[torch.Tensor] = None):
+        """The backbone over a built pyramid `geo` (Geometry, or pipeline.GeometryDev whose row counts stay on the device)."""
         L = geo.levels
-        x = ops.cast_pad_bf16(x_f, self.stem[0].c0)
+        zc = aux["zc"]
+        nd = [lv.n_dev for lv in L]
+        x = ops.cast_pad_bf16(x_f, self.stem[0].c0, n_dev=nd[0])
         for conv in self.stem:
-            x = conv(x, None, conv_map(L[0].km3), L[0].n)
+            x = conv(x, None, L[0].map3(), L[0].n, n_dev=nd[0])
         x0 = x
         if self.spv:
+            inv0, cnt0 = aux["inv0"], aux["cnt0"]
             q1 = ops.trilinear_query(L[0].table, zc, 1)
             q16 = ops.trilinear_query(L[4].table, zc, 16)
             q4 = ops.trilinear_query(L[2].table, zc, 4)
@@ -227,10 +252,10 @@ class Engine:
             x = ops.voxelize_forward(z0, *p2v1)
         skips = [x0]
         for i in range(4):
-            km2 = L[i].km2
-            x = self.down[i](x, None, conv_map(km2), km2.n_out)
+            x = self.down[i](x, None, L[i].map2(), L[i + 1].n, n_dev=nd[i + 1])
+            m3 = L[i + 1].map3()
             for blk in self.enc[i]:
-                x = blk(x, None, L[i + 1].km3)
+                x = blk(x, None, m3, L[i + 1].n, nd[i + 1])
             skips.append(x)
         x4 = x
         if self.spv:
@@ -240,11 +265,11 @@ class Engine:
         ys = []
         for i in range(4):
             lv = L[3 - i]
-            km2 = lv.km2
-            x = self.up[i](x, None, conv_map(km2, True), lv.n)
+            x = self.up[i](x, None, lv.map2t(), lv.n, n_dev=lv.n_dev)
             skip = skips[3 - i]
+            m3 = lv.map3()
             for j, blk in enumerate(self.dec[i]):
-                x = blk(x, skip if j == 0 else None, lv.km3)
+                x = blk(x, skip if j == 0 else None, m3, lv.n, lv.n_dev)
             ys.append(x)
             if self.spv and i == 1:
                 z2 = ops.devoxelize_forward(x, *q4) + self.mlps[1](z1, None, None, z1.shape[0])
@@ -258,16 +283,15 @@ class Engine:
                 cat = torch.nn.functional.pad(cat, (0, pad16(cat.shape[1]) - cat.shape[1]))
             logits = self.head(cat.contiguous(), None, None, cat.shape[0], out_dtype=torch.float32)
         else:
-            l16 = self.heads[0](x4, None, None, L[4].n, out_dtype=torch.float32)
-            l4 = self.heads[1](y2, None, None, L[2].n, out_dtype=torch.float32)
-            l1 = self.heads[2](y4, None, None, L[0].n, out_dtype=torch.float32)
-            logits = ops.devoxelize_multi([L[4].table, L[2].table, L[0].table], [16, 4, 1], [l16, l4, l1], zc,
-                                          self.num_class, rows=out_rows)
-            return (logits, geo) if return_geometry else logits
+            l16 = self.heads[0](x4, None, None, L[4].n, out_dtype=torch.float32, n_dev=nd[4])
+            l4 = self.heads[1](y2, None, None, L[2].n, out_dtype=torch.float32, n_dev=nd[2])
+            l1 = self.heads[2](y4, None, None, L[0].n, out_dtype=torch.float32, n_dev=nd[0])
+            return ops.devoxelize_multi([L[4].table, L[2].table, L[0].table], [16, 4, 1], [l16, l4, l1], zc,
+                                        self.num_class, rows=out_rows)
         logits = logits[:, :self.num_class]
         if out_rows is not None:
             logits = ops.gather_rows(logits.contiguous(), out_rows)
-        return (logits, geo) if return_geometry else logits
+        return logits
 
     @torch.no_grad()
     def forward_batch(self, batch_dict, return_logit=False, return_tta=False):

@@ -190,6 +190,86 @@ def kmap_from_pairs(nbmaps: torch.Tensor, nbsizes: torch.Tensor, k: int, transpo
     return nbr
 
 
+# ------------------------------------------------------------------------------- sync-free variants (pipeline.py)
+def table_from_coords_dev(coords: torch.Tensor, n_dev: torch.Tensor, status: torch.Tensor) -> Table:
+    """Table over the first *n_dev rows of a capacity-sized coordinate buffer."""
+    t = Table(coords.shape[0], coords.device)
+    t.status = status
+    call("tsg_coord_table_build_dev", ptr(coords), t.n, ptr(n_dev), ptr(t.buf), t.slots, ptr(status), stream())
+    return t
+
+
+def build_kmap_dev(table: Table, out_coords: torch.Tensor, n_dev: torch.Tensor, offsets: np.ndarray) -> torch.Tensor:
+    """nbr (K, cap) int32 of the first *n_dev output rows (rows beyond are left untouched)."""
+    cap = out_coords.shape[0]
+    offs = np.ascontiguousarray(offsets, dtype=np.int32)
+    k = offs.shape[0]
+    dev = out_coords.device
+    nbr = torch.empty((k, cap), dtype=torch.int32, device=dev)
+    nbsizes = torch.empty((k,), dtype=torch.int32, device=dev)
+    blockcnt = torch.empty((k * max(int(L.lib().tsg_kmap_blocks(cap)), 1),), dtype=torch.int32, device=dev)
+    call("tsg_kmap_build_dev", ptr(table.buf), table.slots, ptr(out_coords), cap, ptr(n_dev),
+         offs.ctypes.data_as(ctypes.c_void_p), k, ptr(nbr), ptr(nbsizes), ptr(blockcnt), stream())
+    return nbr
+
+
+def kmap_transpose_dev(nbr: torch.Tensor, n_out_dev: torch.Tensor, n_in_cap: int) -> torch.Tensor:
+    k, n_out_cap = nbr.shape
+    out = torch.empty((k, n_in_cap), dtype=torch.int32, device=nbr.device)
+    call("tsg_kmap_transpose_dev", ptr(nbr), k, n_out_cap, ptr(n_out_dev), n_in_cap, ptr(out), stream())
+    return out
+
+
+def kmap_sort_rows_dev(nbr: torch.Tensor, n_dev: torch.Tensor):
+    """(nbr_sorted (K, stride), tile_mask, perm) of a capacity-sized table, as KernelMap.sorted()."""
+    k, cap = nbr.shape
+    dev = nbr.device
+    perm = torch.empty((cap,), dtype=torch.int32, device=dev)
+    stride = int(L.lib().tsg_kmap_sort_stride(cap))
+    nbr_s = torch.empty((k, stride), dtype=torch.int32, device=dev)
+    mask = torch.empty(((cap + 127) // 128,), dtype=torch.int32, device=dev)
+    ws_bytes = int(L.lib().tsg_kmap_sort_ws_bytes(cap))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    call("tsg_kmap_sort_rows_dev", ptr(nbr), k, cap, ptr(n_dev), cap, ptr(perm), ptr(nbr_s), stride, ptr(mask), ptr(ws), ws_bytes,
+         stream())
+    return nbr_s, mask, perm
+
+
+def unique_coords_dev(coords: torch.Tensor, n_dev: torch.Tensor, out_cap: int, m_dev: torch.Tensor, status: torch.Tensor,
+                      trunc_stride: int = 0, field_bits: Optional[Sequence[int]] = None, want_index: bool = False,
+                      want_inverse: bool = False):
+    """unique_coords over the first *n_dev rows of a capacity-sized buffer; the number of voxels goes to the device
+    counter m_dev (clamped to out_cap, status bit 2 on overflow).  Returns (coords (out_cap,4)[, first][, inverse])."""
+    coords = _i32(coords).contiguous()
+    cap = coords.shape[0]
+    dev = coords.device
+    out_c = torch.empty((out_cap, 4), dtype=torch.int32, device=dev)
+    first = torch.empty((out_cap,), dtype=torch.int32, device=dev) if want_index else None
+    inv = torch.empty((cap,), dtype=torch.int32, device=dev) if want_inverse else None
+    ws_bytes = int(L.lib().tsg_unique_ws_bytes(cap))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    fb = (ctypes.c_int32 * 4)(*[int(b) for b in field_bits]) if field_bits is not None else None
+    call("tsg_unique_coords_dev", ptr(coords), cap, ptr(n_dev), int(trunc_stride), fb, ptr(out_c), int(out_cap), ptr(first),
+         ptr(inv), ptr(m_dev), ptr(status), ptr(ws), ws_bytes, stream())
+    res = [out_c]
+    if want_index:
+        res.append(first)
+    if want_inverse:
+        res.append(inv)
+    return res[0] if len(res) == 1 else tuple(res)
+
+
+def gather_rows_dev(src: torch.Tensor, idx: torch.Tensor, n_dev: torch.Tensor) -> torch.Tensor:
+    """out[i] = src[idx[i]] for i < *n_dev (rows of 4-byte elements); idx is capacity-sized."""
+    assert src.element_size() == 4
+    src = src.contiguous()
+    idx = _i32(idx).contiguous()
+    width = src.shape[1] if src.dim() > 1 else 1
+    out = torch.empty((idx.shape[0],) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
+    call("tsg_gather_rows_dev", ptr(src), width, ptr(idx), idx.shape[0], ptr(n_dev), ptr(out), stream())
+    return out
+
+
 # ------------------------------------------------------------------------------- unique voxels
 def unique_coords(coords: torch.Tensor, trunc_stride: int = 0, want_index: bool = False, want_inverse: bool = False,
                   by_hash: bool = False, field_bits: Optional[Sequence[int]] = None):
@@ -342,7 +422,7 @@ def gather_rows(src: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
 
 
 def compact_rows(flags: torch.Tensor, rows_a: Optional[torch.Tensor], rows_b: Optional[torch.Tensor] = None,
-                 want_pos: bool = False, sync: bool = True):
+                 want_pos: bool = False, sync: bool = True, m_dev: Optional[torch.Tensor] = None):
     """Stable compaction by a uint8 flag; returns (out_a, out_b, pos, m).  With sync=False the outputs keep their
     upper-bound length and m is the device counter (the caller slices after its own readback)."""
     n = flags.numel()
@@ -352,7 +432,8 @@ def compact_rows(flags: torch.Tensor, rows_a: Optional[torch.Tensor], rows_b: Op
     out_a = torch.empty_like(rows_a) if rows_a is not None else None
     out_b = torch.empty_like(rows_b) if rows_b is not None else None
     pos = torch.empty((n,), dtype=torch.int32, device=dev) if want_pos else None
-    m_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+    if m_dev is None:
+        m_dev = torch.zeros(1, dtype=torch.int32, device=dev)
     ws_bytes = int(L.lib().tsg_compact_ws_bytes(n))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     call("tsg_compact_rows", ptr(flags), n, ptr(rows_a), wa, ptr(out_a), ptr(rows_b), wb, ptr(out_b), ptr(pos), ptr(m_dev),
@@ -435,11 +516,14 @@ def pack_weights(weight: torch.Tensor, c0: int, c1: int = 0, out_scale: Optional
     return packed
 
 
-def cast_pad_bf16(feats: torch.Tensor, c_pad: int) -> torch.Tensor:
+def cast_pad_bf16(feats: torch.Tensor, c_pad: int, n_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
     feats = feats.float().contiguous()
     n, c = feats.shape
     out = torch.empty((n, c_pad), dtype=torch.bfloat16, device=feats.device)
-    call("tsg_cast_pad_bf16", ptr(feats), n, c, c_pad, ptr(out), stream())
+    if n_dev is not None:
+        call("tsg_cast_pad_bf16_dev", ptr(feats), n, ptr(n_dev), c, c_pad, ptr(out), stream())
+    else:
+        call("tsg_cast_pad_bf16", ptr(feats), n, c, c_pad, ptr(out), stream())
     return out
 
 
@@ -462,11 +546,13 @@ PROFILE = None   # set to a list to record (tag, start_event, end_event, pairs, 
 def conv_forward_tc(in0: torch.Tensor, in1: Optional[torch.Tensor], packed_w: torch.Tensor, k: int, c_out: int,
                     nbr: torch.Tensor, tile_mask: torch.Tensor, n_out: int, bias: Optional[torch.Tensor] = None,
                     residual: Optional[torch.Tensor] = None, relu: bool = False, out_dtype=torch.bfloat16,
-                    num_sms: int = 0, perm: Optional[torch.Tensor] = None, shortcut=None) -> torch.Tensor:
+                    num_sms: int = 0, perm: Optional[torch.Tensor] = None, shortcut=None,
+                    n_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
     """tcgen05/TMEM implicit GEMM; in0/in1 bf16 (n_in, c) with c % 16 == 0.  With `perm`, nbr/tile_mask are in the
     mask-sorted tile-row order of KernelMap.sorted() and tile row r is written to out[perm[r]].
     shortcut = (sc_in0, sc_in1 | None, sc_packed_w, sc_idx | None): a 1x1x1 convolution of (sc_in0 | sc_in1) (n_out rows)
-    accumulated into the same tile (tsg_conv_fwd_tc2); sc_idx = the centre offset's line of `nbr` for sorted maps."""
+    accumulated into the same tile (tsg_conv_fwd_tc2); sc_idx = the centre offset's line of `nbr` for sorted maps.
+    n_dev: int32 device counter — n_out is then the capacity of the buffers and min(*n_dev, n_out) rows are computed."""
     assert in0.dtype == torch.bfloat16 and in0.is_contiguous()
     c0 = in0.shape[1]
     c1 = 0
@@ -495,17 +581,24 @@ def conv_forward_tc(in0: torch.Tensor, in1: Optional[torch.Tensor], packed_w: to
         if sidx is not None:
             assert sidx.dtype == torch.int32 and sidx.is_contiguous() and sidx.numel() >= nbr_stride
     if PROFILE is not None:
-        pairs = (nbr >= 0).sum() if nbr is not None else torch.tensor(n_out * k, device=in0.device)
+        rows = n_dev[0].double() if n_dev is not None else float(n_out)
+        if nbr is None:
+            pairs = rows * k + torch.zeros((), dtype=torch.float64, device=in0.device)
+        elif n_dev is None:
+            pairs = (nbr >= 0).sum().double()
+        else:      # capacity-sized table: rows beyond the device count of a sorted table hold -1, of a raw table garbage
+            live = torch.arange(nbr.shape[1], device=nbr.device) < n_dev[0]
+            pairs = ((nbr >= 0) & live).sum().double()
         if shortcut is not None:     # the folded 1x1 convolution's MACs, expressed in pairs of the main phase's width
-            pairs = pairs.double() + n_out * (sc0 + sc1) / (c0 + c1)
+            pairs = pairs + rows * (sc0 + sc1) / (c0 + c1)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    call("tsg_conv_fwd_tc2", ptr(in0), c0, ptr(in1), c1, in0.shape[0], ptr(packed_w), k, c_out, ptr(nbr), nbr_stride,
-         ptr(tile_mask), ptr(perm), int(n_out), ptr(s0), sc0, ptr(s1), sc1, ptr(sw), ptr(sidx), ptr(out), L.DTYPES[out_dtype],
+    call("tsg_conv_fwd_tc3", ptr(in0), c0, ptr(in1), c1, in0.shape[0], ptr(packed_w), k, c_out, ptr(nbr), nbr_stride,
+         ptr(tile_mask), ptr(perm), int(n_out), ptr(n_dev), ptr(s0), sc0, ptr(s1), sc1, ptr(sw), ptr(sidx), ptr(out), L.DTYPES[out_dtype],
          ptr(bias), ptr(residual), int(relu), int(num_sms), ptr(_sched_ws(in0.device)) if DYNAMIC_TILES else None, stream())
     if PROFILE is not None:
         e1.record()
-        PROFILE.append((k, e0, e1, pairs, c0 + c1, c_out, n_out))
+        PROFILE.append((k, e0, e1, pairs, c0 + c1, c_out, rows if n_dev is not None else n_out))
     return out
 
 
@@ -556,3 +649,33 @@ def aggregate_quantize(points: torch.Tensor, frames: Sequence[dict], n_samples: 
          ptr(coords), ptr(flags), ptr(ws), ws_bytes, stream())
     extent = ws[:n_samples * 48].view(torch.int32).view(n_samples, 12)
     return feats, coords, flags, extent
+
+
+def frames_to_array(frames: Sequence[dict]):
+    """ctypes array of tsg_frame records from the dicts of frontend.MultiFrameBatch.frames."""
+    arr = (L.Frame * len(frames))()
+    ident = np.eye(4, dtype=np.float32).reshape(-1)
+    for i, f in enumerate(frames):
+        arr[i].offset, arr[i].count, arr[i].sample, arr[i].is_cur = int(f["offset"]), int(f["count"]), int(f["sample"]), int(f["is_cur"])
+        p0 = np.asarray(f.get("pose0", ident), np.float32).reshape(-1)
+        p1 = np.asarray(f.get("pose", ident), np.float32).reshape(-1)
+        for j in range(16):
+            arr[i].pose0[j] = float(p0[j])
+            arr[i].pose[j] = float(p1[j])
+    return arr
+
+
+def aggregate_quantize_dev(points: torch.Tensor, frames_dev: torch.Tensor, n_frames: int, max_count: int, n_samples: int,
+                           voxel_size: float, keep: Optional[torch.Tensor] = None):
+    """aggregate_quantize with the frame table already on the device (uint8 tensor holding n_frames tsg_frame records):
+    no host copy inside, so the call can be captured into a CUDA graph."""
+    pts = points.float().contiguous()
+    n, c_in = pts.shape
+    feats = torch.empty((n, c_in + 1), dtype=torch.float32, device=pts.device)
+    coords = torch.empty((n, 4), dtype=torch.int32, device=pts.device)
+    flags = torch.empty((n,), dtype=torch.uint8, device=pts.device)
+    ws_bytes = int(L.lib().tsg_aggregate_ws_bytes(n_samples))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=pts.device)
+    call("tsg_aggregate_quantize_dev", ptr(pts), c_in, ptr(frames_dev), int(n_frames), int(max_count), int(n_samples), ptr(keep),
+         float(voxel_size), ptr(feats), ptr(coords), ptr(flags), ptr(ws), ws_bytes, stream())
+    return feats, coords, flags
