@@ -5,7 +5,8 @@
 
 One "step" = one batch of B=4 three-frame SemanticKITTI-shaped samples per GPU through
   device front end (pose warp + time flag + clamp + quantise + dedup/collate)  ->  MinkUNetMs mk34 cr1.0 (63 sparse
-  convolutions, bf16 tcgen05 engine)  ->  per-point logits of the current scans.
+  convolutions, bf16 tcgen05 engine)  ->  per-point logits of the current scans,
+run as the sync-free pipeline captured into one CUDA graph per batch in flight (taseg_b200/pipeline.py).
 `value` times it with raw points resident in HBM; `e2e` includes the pinned-host -> device copy of the points and the
 device -> host copy of the logits every step.  `--impl reference` times the reference's own CPU implementation
 (oracle/_ref torchsparse backend + restated Python glue) on a bounded sample, rank 0 only.
@@ -30,7 +31,8 @@ BATCH = 4
 N_FRAMES = 3
 VOXEL = 0.05
 SECTOR = 1.0 / 16      # bounded sample for the CPU arms
-N_STREAMS = int(os.environ.get("TSG_BENCH_STREAMS", "2"))   # batches in flight (1 = strictly one batch at a time)
+N_STREAMS = int(os.environ.get("TSG_BENCH_STREAMS", "3"))   # batches in flight (1 = strictly one batch at a time)
+EAGER = os.environ.get("TSG_BENCH_EAGER", "0") == "1"        # A/B: round-1 eager path instead of the captured pipeline
 WORKLOAD = ("configs[1]: TASeg MinkUNetMs mk34 cr1.0 (IN_FEATURE_DIM 5, 20 classes), 3-frame temporal aggregation, "
             "SemanticKITTI shape (64x2048 rays/scan, 0.05 m voxels), batch 4 per GPU")
 
@@ -167,6 +169,7 @@ def main():
     import torch.distributed as dist
     from taseg_b200 import _lib, frontend, ops
     from taseg_b200.engine import Engine
+    from taseg_b200.pipeline import Pipeline
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
     torch.cuda.set_device(local_rank)
@@ -192,36 +195,58 @@ def main():
     cur_idx = torch.from_numpy(mfb.cur_idx).cuda()
     n_cur = int(sum(mfb.n_cur))
     host_out = torch.empty((n_cur, 20), dtype=torch.float32).pin_memory()
+    host_status = torch.zeros(N_STREAMS, dtype=torch.int32).pin_memory()
 
-    # Two batches in flight on two streams: while the host waits for a data-dependent size of batch i+1 (number of unique
-    # voxels per pyramid level), the GPU still has the queued convolutions of batch i, and the small geometry kernels of
-    # one batch fill the SMs that the tail of the other batch's persistent convolution kernels leaves idle.
+    # N_STREAMS batches in flight, each a captured CUDA graph of the sync-free pipeline (taseg_b200/pipeline.py) with its
+    # own static buffers: no data-dependent size returns to the host, one graph launch per batch.  While one batch runs
+    # its persistent convolution kernels the small geometry kernels of the other fill the SMs their tails leave idle.
+    # TSG_BENCH_EAGER=1 keeps the round-1 path (one C-ABI call per kernel, five size read-backs per step) for A/B runs.
     streams = [torch.cuda.Stream() for _ in range(N_STREAMS)]
+    pipes = []
+    if not EAGER:
+        for st in streams:
+            with torch.cuda.stream(st):
+                pipe = Pipeline(engine, mfb, VOXEL)
+                pipe.calibrate(pts)
+                pipe.points.copy_(pts)
+                l0 = _lib.launch_count
+                pipe()                                   # one eager sync-free pass: counts the kernels of a forward
+                launches_per_step = _lib.launch_count - l0
+                pipe.capture()
+                pipes.append(pipe)
+        torch.cuda.synchronize()
+        config["capacities"] = {"margin": pipes[0].margin, "levels": pipes[0].caps, "voxels": pipes[0].sizes["levels"]}
+    config["graph"] = not EAGER
     state = {"i": 0}
 
-    def forward(points):
+    def forward_eager(points):
         out = frontend.aggregate_voxelize(points, mfb, VOXEL, cur_idx)
         return engine(out["coords"], out["feats"], field_bits=out["field_bits"], out_rows=out["cur_rows"])
 
     def step():
-        st = streams[state["i"] % N_STREAMS]
+        k = state["i"] % N_STREAMS
         state["i"] += 1
-        with torch.cuda.stream(st):
-            return forward(pts)
+        with torch.cuda.stream(streams[k]):
+            return forward_eager(pts) if EAGER else pipes[k]()      # raw points already resident in the static input buffer
 
     def join_streams():
         for st in streams:
             torch.cuda.current_stream().wait_stream(st)
 
     # End to end through the public API with HOST buffers: every step copies its raw points pinned-host -> device and
-    # its logits device -> pinned-host.  Copies run on their own stream and are double buffered, so the transfer of
-    # step i+1's points and of step i-1's logits overlaps the kernels of step i (every byte still moves every step).
-    copy_stream = torch.cuda.Stream()
-    dev_pts = [torch.empty_like(pts), torch.empty_like(pts)]
-    dev_out = [torch.empty((n_cur, 20), dtype=torch.float32, device="cuda") for _ in range(2)]
-    h2d_done = [torch.cuda.Event(), torch.cuda.Event()]
-    out_ready = [torch.cuda.Event(), torch.cuda.Event()]
-    d2h_done = [torch.cuda.Event(), torch.cuda.Event()]
+    # its logits (+ the 4-byte status word) device -> pinned-host.  Uploads and downloads run on their own streams (PCIe
+    # is full duplex) and are buffered over the in-flight batches, so the transfer of step i+1's points and of step
+    # i-1's logits overlaps the kernels of step i (every byte still moves every step).
+    copy_stream = torch.cuda.Stream()       # host -> device
+    down_stream = torch.cuda.Stream()       # device -> host
+    nbuf = max(2, N_STREAMS) if EAGER else N_STREAMS      # graph mode: one input buffer per captured pipeline
+    dev_pts = [p.points for p in pipes] if not EAGER else [torch.empty_like(pts) for _ in range(nbuf)]
+    while len(dev_pts) < nbuf:
+        dev_pts.append(dev_pts[0])
+    dev_out = [torch.empty((n_cur, 20), dtype=torch.float32, device="cuda") for _ in range(nbuf)]
+    h2d_done = [torch.cuda.Event() for _ in range(nbuf)]
+    out_ready = [torch.cuda.Event() for _ in range(nbuf)]
+    d2h_done = [torch.cuda.Event() for _ in range(nbuf)]
     e2e_state = {"i": 0, "primed": False}
 
     def enqueue_h2d(slot):
@@ -232,26 +257,32 @@ def main():
 
     def step_e2e():
         i = e2e_state["i"]
-        slot = i & 1
+        slot = i % nbuf
         if not e2e_state["primed"]:
             enqueue_h2d(slot)
             e2e_state["primed"] = True
-        enqueue_h2d(slot ^ 1)                             # next step's input travels while this step computes
+        enqueue_h2d((i + 1) % nbuf)                       # next step's input travels while this step computes
         main = streams[slot % N_STREAMS]
         main.wait_event(h2d_done[slot])
-        main.wait_event(d2h_done[slot])                   # dev_out[slot] was drained two steps ago
+        main.wait_event(d2h_done[slot])                   # dev_out[slot] was drained nbuf steps ago
         with torch.cuda.stream(main):
-            dev_out[slot].copy_(forward(dev_pts[slot]))
+            if EAGER:
+                dev_out[slot].copy_(forward_eager(dev_pts[slot]))
+            else:
+                dev_out[slot].copy_(pipes[slot % N_STREAMS]())
         out_ready[slot].record(main)
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(out_ready[slot])
+        with torch.cuda.stream(down_stream):
+            down_stream.wait_event(out_ready[slot])
             host_out.copy_(dev_out[slot], non_blocking=True)
-            d2h_done[slot].record(copy_stream)
+            if not EAGER:
+                host_status[slot % N_STREAMS:slot % N_STREAMS + 1].copy_(pipes[slot % N_STREAMS].status, non_blocking=True)
+            d2h_done[slot].record(down_stream)
         e2e_state["i"] = i + 1
 
     def e2e_drain():
         join_streams()
         torch.cuda.current_stream().wait_stream(copy_stream)
+        torch.cuda.current_stream().wait_stream(down_stream)
 
     def barrier():
         if world > 1:
@@ -284,21 +315,30 @@ def main():
     time.sleep(0.3)
     launches0 = _lib.launch_count
     ms, w0, w1 = timed(step, args.steps)
-    launches = _lib.launch_count - launches0
+    launches = (_lib.launch_count - launches0) if EAGER else launches_per_step * args.steps
     for _ in range(2):
         step_e2e()
     ms_e2e, _, w2 = timed(step_e2e, args.steps)
     sampler.stop()
     clocks = sampler.summary(w0, w2)
+    if not EAGER:
+        bad = [p.check() for p in pipes] + host_status.tolist()
+        if any(bad):
+            raise SystemExit("bench.py: the sync-free pipeline flagged status %s (capacity overflow / coordinate range)" % bad)
 
-    # roofline of the dominant kernel (conv_tc_kernel): algorithmic FLOPs / CUDA-event time of its launches in one step
-    # (events on the launching stream around every launch; minimum over 3 instrumented steps, the instrumentation itself
-    # — pair counts, extra events — is outside the bracketed launches)
+    # roofline of the dominant kernel (conv_tc_kernel): algorithmic FLOPs / CUDA-event time of its launches in one step.
+    # Events on the launching stream around every launch of a sync-free forward issued kernel by kernel; a 40 ms device-side
+    # sleep in front lets the host enqueue the whole step first, so the events bracket back-to-back device execution and not
+    # the Python launch path (minimum over 3 instrumented steps; pair counts are computed outside the brackets).
     runs = []
     for _ in range(3):
         ops.PROFILE = []
         torch.cuda.synchronize()
-        forward(pts)          # on the current stream: the events of ops.PROFILE are recorded there
+        if EAGER:
+            forward_eager(pts)
+        else:
+            torch.cuda._sleep(int(0.04 * 1.9e9))
+            pipes[0]._forward()
         torch.cuda.synchronize()
         runs.append(ops.PROFILE)
         ops.PROFILE = None
@@ -307,13 +347,14 @@ def main():
     flops = sum(2.0 * float(p.item()) * cin * cout for _, _, _, p, cin, cout, _ in prof)
     pk = peaks()
     achieved = flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
-    traffic = None
+    traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("conv_tc_kernel_dram_bytes_per_step")
+        tj = json.load(open(tpath))
+        traffic, traffic_src = tj.get("conv_tc_kernel_dram_bytes_per_step"), tj.get("source")
     roofline = {"bound": "tensor", "kernel": "conv_tc_kernel (all %d launches of one step)" % len(prof),
                 "achieved": achieved, "peak": pk["bf16"], "unit": "TFLOP/s", "frac": achieved / pk["bf16"],
-                "peak_source": pk["source"] + " bf16_tflops_sustained", "traffic": traffic,
+                "peak_source": pk["source"] + " bf16_tflops_sustained", "traffic": traffic, "traffic_source": traffic_src,
                 "algorithmic_gflop_per_step": flops / 1e9, "kernel_ms_per_step": conv_ms,
                 "kernel_share_of_step": conv_ms / (ms / args.steps)}
 
@@ -327,7 +368,7 @@ def main():
                 "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
                 "points_per_step": int(mfb.total), "current_points_per_step": n_cur}
         if world == 1 and not args.no_cpu_baseline:
-            cb = cpu_arm(1, 0)
+            cb = cpu_arm(3, 0)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line))
     if world > 1:

@@ -528,10 +528,14 @@ def cast_pad_bf16(feats: torch.Tensor, c_pad: int, n_dev: Optional[torch.Tensor]
 
 
 _SCHED = {}
+SCHED_OVERRIDE = None   # a captured pipeline owns its scheduler counters (graphs replay on any stream, possibly concurrently)
 
 
 def _sched_ws(device) -> torch.Tensor:
-    """Two zeroed int32 per (device, stream) for the convolution's dynamic tile scheduler (the kernel re-zeroes them)."""
+    """Two zeroed int32 per (device, stream) for the convolution's dynamic tile scheduler (the kernel re-zeroes them).
+    Launches that may overlap need their own pair: eager launches get one per stream; a Pipeline passes its own."""
+    if SCHED_OVERRIDE is not None:
+        return SCHED_OVERRIDE
     key = (device, stream().value)
     t = _SCHED.get(key)
     if t is None:

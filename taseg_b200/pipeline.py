@@ -91,6 +91,7 @@ class Pipeline:
         self.set_poses(mfb.frames)
         self.counters = torch.zeros(self.N_COUNTERS, dtype=torch.int32, device=dev)
         self.status = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.sched = torch.zeros(2, dtype=torch.int32, device=dev)     # this pipeline's dynamic-tile-scheduler counters
         self.caps: Optional[List[int]] = None
         self.cap_pts = self.n_raw
         self.field_bits = None
@@ -124,6 +125,13 @@ class Pipeline:
 
     # -- the sync-free forward -------------------------------------------------------------------------------------
     def _forward(self) -> torch.Tensor:
+        prev, ops.SCHED_OVERRIDE = ops.SCHED_OVERRIDE, self.sched
+        try:
+            return self._forward_impl()
+        finally:
+            ops.SCHED_OVERRIDE = prev
+
+    def _forward_impl(self) -> torch.Tensor:
         cnt = self.counters
         ctr = [cnt[i:i + 1] for i in range(self.N_COUNTERS)]
         self.status.zero_()

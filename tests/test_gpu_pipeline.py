@@ -60,6 +60,32 @@ def test_pipeline_matches_eager_and_replays():
     assert torch.equal(pipe(pts), want)
 
 
+def test_two_pipelines_replay_concurrently():
+    """Two captured graphs in flight on two streams (the benchmark's configuration) must not share any state — each owns
+    its counters, status word and dynamic-tile-scheduler tickets."""
+    from taseg_b200.pipeline import Pipeline
+    mfb, engine = make(720, 2)
+    pts = cu(mfb.points)
+    want, _ = eager(engine, mfb, pts)
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    pipes = []
+    for st in streams:
+        with torch.cuda.stream(st):
+            p = Pipeline(engine, mfb, 0.05)
+            p.calibrate(pts)
+            p.points.copy_(pts)
+            p.capture()
+            pipes.append(p)
+    torch.cuda.synchronize()
+    for rep in range(6):
+        for p, st in zip(pipes, streams):
+            with torch.cuda.stream(st):
+                p()
+    torch.cuda.synchronize()
+    for p in pipes:
+        assert p.check() == 0 and torch.equal(p.logits, want)
+
+
 def test_pipeline_flags_capacity_overflow():
     from taseg_b200.pipeline import OVERFLOW, Pipeline
     mfb, engine = make(710, 1)

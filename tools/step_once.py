@@ -25,9 +25,20 @@ def main():
     pts = torch.from_numpy(mfb.points).cuda()
     cur_idx = torch.from_numpy(mfb.cur_idx).cuda()
 
-    def step():
-        out = frontend.aggregate_voxelize(pts, mfb, bench.VOXEL, cur_idx)
-        return engine(out["coords"], out["feats"], field_bits=out["field_bits"], out_rows=out["cur_rows"])
+    if os.environ.get("TSG_BENCH_EAGER") == "1":
+        def step():
+            out = frontend.aggregate_voxelize(pts, mfb, bench.VOXEL, cur_idx)
+            return engine(out["coords"], out["feats"], field_bits=out["field_bits"], out_rows=out["cur_rows"])
+    else:      # the shipped path: sync-free pipeline, captured graph (GRAPH=0: same kernels launched one by one)
+        from taseg_b200.pipeline import Pipeline
+        pipe = Pipeline(engine, mfb, bench.VOXEL)
+        pipe.calibrate(pts)
+        pipe.points.copy_(pts)
+        if os.environ.get("GRAPH", "1") == "1":
+            pipe.capture()
+
+        def step():
+            return pipe()
 
     for _ in range(int(os.environ.get("WARM", "2"))):
         step()
