@@ -153,6 +153,23 @@ size_t tsg_aggregate_ws_bytes(int n_samples);
 int tsg_aggregate_quantize(const float *pts, int c_in, const tsg_frame *frames_host, int n_frames, int n_samples,
                            const uint8_t *keep, float voxel_size, float *feats, int32_t *coords, uint8_t *flags,
                            void *ws, size_t ws_bytes, tsg_stream_t stream);
+/* nuScenes multi-sweep aggregation (BASELINE configs[3]) in the same three passes:
+ *   R/pcseg/data/dataset/nuscenes/nuscenes_ms.py:284-341  per sweep: drop the ego box |x| < 1 & |y| < 1.5 (tested on the
+ *                                                          RAW points), time lag into column 4, warp into the key frame
+ *   R/pcseg/data/dataset/nuscenes/nuscenes_ms.py:348-373  transform_point: float64 p @ R + T, stored back as float32
+ *   R/pcseg/data/dataset/nuscenes/nuscenes_voxel_ms.py:122-160  clamp to the key sweep's min corner, round, min-shift
+ * pts (sum count, c >= 5) rows [x, y, z, intensity, .]; sweeps_host: n_sweeps records (key sweep first within a sample).
+ * Outputs as tsg_aggregate_quantize: feats (sum count, c) with column 4 = dt, coords [x,y,z,sample], flags = kept. */
+typedef struct tsg_sweep {
+  int64_t offset, count;
+  int32_t sample, is_key;
+  double R[9], T[3];
+  float dt, pad_;
+} tsg_sweep;
+size_t tsg_aggregate_nus_ws_bytes(int n_samples);
+int tsg_aggregate_quantize_nus(const float *pts, int c, const tsg_sweep *sweeps_host, int n_sweeps, int n_samples,
+                               float voxel_size, float *feats, int32_t *coords, uint8_t *flags, void *ws, size_t ws_bytes,
+                               tsg_stream_t stream);
 /* Stable stream compaction of rows by a uint8 flag: used after tsg_aggregate_quantize.
  * rows_a (n, wa) and rows_b (n, wb) are 4-byte-element rows (either may be NULL); *m_dev = rows kept;
  * pos (n) int32 = destination row or -1.  ws: tsg_compact_ws_bytes(n). */

@@ -30,6 +30,12 @@ class Frame(ctypes.Structure):
                 ("is_cur", ctypes.c_int32), ("pose0", ctypes.c_float * 16), ("pose", ctypes.c_float * 16)]
 
 
+class Sweep(ctypes.Structure):
+    """tsg_sweep (include/taseg_b200.h)."""
+    _fields_ = [("offset", ctypes.c_int64), ("count", ctypes.c_int64), ("sample", ctypes.c_int32), ("is_key", ctypes.c_int32),
+                ("R", ctypes.c_double * 9), ("T", ctypes.c_double * 3), ("dt", ctypes.c_float), ("pad_", ctypes.c_float)]
+
+
 def parse_header(path: str = HEADER) -> Dict[str, Tuple[object, List[object]]]:
     """name -> (restype, argtypes) for every function declared in the header."""
     text = open(path).read()
@@ -99,7 +105,8 @@ def check(status: int, what: str = "") -> None:
 # + one kernel per 9-bit pass, counted here at their minimum for the key widths of the benchmark)
 KERNELS_PER_CALL = {"tsg_table_build": 2, "tsg_coord_table_build": 2, "tsg_kmap_pairs": 2, "tsg_kmap_transpose": 2,
                     "tsg_sort_pairs": 4, "tsg_unique_coords": 7, "tsg_unique_hash": 11, "tsg_aggregate_quantize": 4,
-                    "tsg_compact_rows": 3, "tsg_kmap_sort_rows": 5}
+                    "tsg_compact_rows": 3, "tsg_kmap_sort_rows": 5, "tsg_aggregate_quantize_nus": 4, "tsg_aggregate_quantize_dev": 4,
+                    "tsg_unique_coords_dev": 7, "tsg_coord_table_build_dev": 2, "tsg_kmap_sort_rows_dev": 5, "tsg_kmap_transpose_dev": 2}
 launch_count = 0
 
 

@@ -1,6 +1,8 @@
 // Multi-frame aggregation + quantisation front end and the point<->voxel transforms (a10-a14).
 // HBM-bound: every kernel is a single coalesced pass (float4 / int4 vectors where rows are 16 B), fp32 arithmetic
 // written with explicit round-to-nearest intrinsics wherever the reference's bit pattern must be reproduced.
+#include <cstring>
+
 #include "common.cuh"
 
 namespace tsg {
@@ -119,10 +121,55 @@ __global__ void agg_warp_kernel(const float *__restrict__ pts, int c_in, const t
   }
 }
 
+// nuScenes pass 1 (grid.y = sweep; nuscenes_ms.py:284-341, :348-373): per point of sweep k the ego-box test on the RAW
+// coordinates (|x| < 1 & |y| < 1.5 -> dropped), the sweep's time lag into column 4, the float64 warp into the key
+// frame (p @ R + T: products and sums rounded one by one, like numpy's matmul of a row by a 3x3 matrix), the min corner
+// of the key sweep's SURVIVING points.  flags = "outside the ego box"; pass 2 (agg_quant_kernel) ANDs the clamp.
+__global__ void agg_warp_nus_kernel(const float *__restrict__ pts, int c, const tsg_sweep *__restrict__ sweeps,
+                                    float *__restrict__ feats, uint8_t *__restrict__ flags, AggWs *ws) {
+  const tsg_sweep f = sweeps[blockIdx.y];
+  float mn[3] = {__int_as_float(0x7f800000), __int_as_float(0x7f800000), __int_as_float(0x7f800000)};
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < f.count; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = f.offset + t;
+    const float *r = pts + i * c;
+    const float x0 = r[0], y0 = r[1], z0 = r[2];
+    const bool keep = !(fabsf(x0) < 1.0f && fabsf(y0) < 1.5f);
+    float w[3] = {x0, y0, z0};
+    if (!f.is_key) {
+      const double x = x0, y = y0, z = z0;
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+        w[j] = (float)__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(x, f.R[j]), __dmul_rn(y, f.R[3 + j])), __dmul_rn(z, f.R[6 + j])), f.T[j]);
+    }
+    float *o = feats + i * c;
+    o[0] = w[0]; o[1] = w[1]; o[2] = w[2];
+    for (int j = 3; j < c; ++j) o[j] = j == 4 ? f.dt : r[j];
+    flags[i] = keep ? 1 : 0;
+    if (f.is_key && keep) {
+      mn[0] = fminf(mn[0], w[0]); mn[1] = fminf(mn[1], w[1]); mn[2] = fminf(mn[2], w[2]);
+    }
+  }
+  if (f.is_key) {
+    __shared__ float s_mn[8][3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      float v = mn[j];
+      for (int s = 16; s; s >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, s));
+      if ((threadIdx.x & 31) == 0) s_mn[threadIdx.x >> 5][j] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+      float v = s_mn[0][threadIdx.x];
+      for (int w2 = 1; w2 < (int)(blockDim.x >> 5); ++w2) v = fminf(v, s_mn[w2][threadIdx.x]);
+      if (v < __int_as_float(0x7f800000)) atomic_min_float(&ws[f.sample].cur_min[threadIdx.x], v);
+    }
+  }
+}
+
 // pass 2: keep mask (FSA & clamp to the current scan's min corner), quantise, per-sample min of kept voxels
 __global__ void agg_quant_kernel(const float *__restrict__ feats, int c_out, const tsg_frame *__restrict__ frames,
-                                 const uint8_t *__restrict__ keep, float voxel, int4 *__restrict__ coords,
-                                 uint8_t *__restrict__ flags, AggWs *ws) {
+                                 const uint8_t *keep, float voxel, int4 *__restrict__ coords, uint8_t *flags, AggWs *ws) {
+  // keep / flags may be the same array (nuScenes: the ego-box flags of pass 1 are refined in place)
   const tsg_frame f = frames[blockIdx.y];
   const float cx = ws[f.sample].cur_min[0], cy = ws[f.sample].cur_min[1], cz = ws[f.sample].cur_min[2];
   int mn[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff};
@@ -595,6 +642,45 @@ int tsg_aggregate_quantize_dev(const float *pts, int c_in, const tsg_frame *fram
   agg_quant_kernel<<<grid, 256, 0, stream>>>(feats, c_in + 1, frames_dev, keep, voxel_size, (int4 *)coords, flags, aw);
   agg_shift_kernel<<<grid, 256, 0, stream>>>(frames_dev, (int4 *)coords, aw);
   return check_launch("tsg_aggregate_quantize_dev");
+}
+
+size_t tsg_aggregate_nus_ws_bytes(int n_samples) {
+  return align256(sizeof(AggWs) * (size_t)(n_samples > 0 ? n_samples : 1)) + align256(sizeof(tsg_frame) * 1024) +
+         align256(sizeof(tsg_sweep) * 1024);
+}
+
+int tsg_aggregate_quantize_nus(const float *pts, int c, const tsg_sweep *sweeps_host, int n_sweeps, int n_samples,
+                               float voxel_size, float *feats, int32_t *coords, uint8_t *flags, void *ws, size_t ws_bytes,
+                               tsg_stream_t stream) {
+  if (n_sweeps <= 0) return TSG_OK;
+  if (n_sweeps > 1024 || c < 5 || n_samples <= 0 || n_samples > 128) {
+    set_error("tsg_aggregate_quantize_nus: need 1<=sweeps<=1024, c>=5 (x,y,z,intensity,dt), 1<=samples<=128");
+    return TSG_ERR_INVALID;
+  }
+  if (ws_bytes < tsg_aggregate_nus_ws_bytes(n_samples)) { set_error("tsg_aggregate_quantize_nus: workspace too small"); return TSG_ERR_WORKSPACE; }
+  AggWs *aw = (AggWs *)ws;
+  tsg_frame *fr = (tsg_frame *)((char *)ws + align256(sizeof(AggWs) * (size_t)n_samples));
+  tsg_sweep *sw = (tsg_sweep *)((char *)fr + align256(sizeof(tsg_frame) * 1024));
+  static thread_local tsg_frame frames_host[1024];   // (offset, count, sample) view of the sweeps for the shared passes 2 and 3
+  int64_t maxcount = 1;
+  for (int i = 0; i < n_sweeps; ++i) {
+    if (sweeps_host[i].sample < 0 || sweeps_host[i].sample >= n_samples) { set_error("tsg_aggregate_quantize_nus: bad sample id"); return TSG_ERR_INVALID; }
+    if (sweeps_host[i].count > maxcount) maxcount = sweeps_host[i].count;
+    memset(&frames_host[i], 0, sizeof(tsg_frame));
+    frames_host[i].offset = sweeps_host[i].offset;
+    frames_host[i].count = sweeps_host[i].count;
+    frames_host[i].sample = sweeps_host[i].sample;
+    frames_host[i].is_cur = 0;   // the ego-box mask applies to the key sweep too
+  }
+  TSG_CUDA(cudaMemcpyAsync(sw, sweeps_host, sizeof(tsg_sweep) * n_sweeps, cudaMemcpyHostToDevice, stream));
+  TSG_CUDA(cudaMemcpyAsync(fr, frames_host, sizeof(tsg_frame) * n_sweeps, cudaMemcpyHostToDevice, stream));
+  // (pageable sources: cudaMemcpyAsync returns once the data sits in the driver's staging buffer, so frames_host may be reused)
+  agg_init_kernel<<<1, 128, 0, stream>>>(aw, n_samples);
+  dim3 grid(grid_for(maxcount, 256, 2), n_sweeps);
+  agg_warp_nus_kernel<<<grid, 256, 0, stream>>>(pts, c, sw, feats, flags, aw);
+  agg_quant_kernel<<<grid, 256, 0, stream>>>(feats, c, fr, flags, voxel_size, (int4 *)coords, flags, aw);
+  agg_shift_kernel<<<grid, 256, 0, stream>>>(fr, (int4 *)coords, aw);
+  return check_launch("tsg_aggregate_quantize_nus");
 }
 
 size_t tsg_compact_ws_bytes(int64_t n) { return align256((size_t)((n > 0 ? n : 1) / CP_ROWS + 2) * 4); }

@@ -57,44 +57,69 @@ def aggregate_voxelize(points: torch.Tensor, batch: MultiFrameBatch, voxel_size:
                 pos=pos, field_bits=bits)
 
 
+class NusBatch:
+    """Host-side description of a nuScenes multi-sweep batch: sample b = [key sweep, sweep 1, ..., sweep S-1], each an
+    (N_k, >=5) array [x, y, z, intensity, .] in its own sensor frame, with p_key = p_k @ R_k + T_k (float64) and time
+    lag dt_k (nuscenes_ms.py:284-341).  One contiguous point buffer + one record per sweep, like MultiFrameBatch."""
+
+    def __init__(self, samples, Rs, Ts, dts):
+        self.sweeps: List[dict] = []
+        chunks, key_idx, self.n_key = [], [], []
+        off = 0
+        for b, sweeps in enumerate(samples):
+            for k, s in enumerate(sweeps):
+                n = int(s.shape[0])
+                self.sweeps.append(dict(offset=off, count=n, sample=b, is_key=int(k == 0), R=Rs[b][k], T=Ts[b][k], dt=dts[b][k]))
+                chunks.append(s)
+                if k == 0:
+                    key_idx.append(np.arange(off, off + n, dtype=np.int64))
+                    self.n_key.append(n)
+                off += n
+        self.n_samples = len(samples)
+        self.chunks = chunks
+        self.key_idx = np.concatenate(key_idx)
+        self.key_sample = np.concatenate([np.full(n, b, np.int64) for b, n in enumerate(self.n_key)])
+        self.total = off
+
+    def points(self, device="cuda") -> torch.Tensor:
+        """The batch's points as one (total, c) fp32 device tensor (chunks may be numpy arrays or device tensors)."""
+        parts = [c if isinstance(c, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(c, np.float32)).to(device) for c in self.chunks]
+        return torch.cat([p.float() for p in parts], 0).contiguous()
+
+
 def aggregate_voxelize_nus(samples: Sequence[Sequence[torch.Tensor]], Rs: Sequence[Sequence[np.ndarray]],
-                           Ts: Sequence[Sequence[np.ndarray]], dts: Sequence[Sequence[float]], voxel_size: float):
+                           Ts: Sequence[Sequence[np.ndarray]], dts: Sequence[Sequence[float]], voxel_size: float,
+                           batch: Optional[NusBatch] = None, points: Optional[torch.Tensor] = None):
     """nuScenes multi-sweep front end (BASELINE configs[3]) on the device, for a batch of samples.
     samples[b][k] (N_k, 5) fp32 device tensor [x, y, z, intensity, .] in sweep k's own frame (k = 0: key frame);
     Rs/Ts[b][k] float64 with p_key = p_k @ R + T; dts[b][k] seconds.  Per sweep, as
     R/pcseg/data/dataset/nuscenes/nuscenes_ms.py:284-341: the ego box |x| < 1 & |y| < 1.5 is tested on the RAW points,
     dt goes to column 4, the sweep is warped in fp64 (`transform_point`, :348-373), then filtered.  Then the loader's
     clamp / round / shift / sparse_quantize (nuscenes_voxel_ms.py:122-160 = the SemanticKITTI one) per sample, collated.
-    Returns the same dict as aggregate_voxelize (coords (M,4) [x,y,z,b], feats (M,5), inverse, cur_rows, point_ms, pc_ms, inds)."""
-    pts_all, pc_all, n_cur, cur_off = [], [], [], []
-    off = 0
-    for b, sweeps in enumerate(samples):
-        parts = []
-        for k, s in enumerate(sweeps):
-            s = s.float()
-            no_ego = ~((s[:, 0].abs() < 1.0) & (s[:, 1].abs() < 1.5))
-            s = s.clone()
-            s[:, 4] = float(dts[b][k])
-            if k > 0:
-                s = ops.transform_point(s, Rs[b][k], Ts[b][k])
-            parts.append(s[no_ego])
-        cur = parts[0]
-        ms = torch.cat(parts, 0)
-        mn = cur[:, :3].amin(dim=0)
-        ms = ms[(ms[:, 0] >= mn[0]) & (ms[:, 1] >= mn[1]) & (ms[:, 2] >= mn[2])]      # clamp to the key frame's min corner
-        pc = torch.round(ms[:, :3] / voxel_size).to(torch.int32)                       # fp32 divide, round half to even
-        pc = pc - pc.amin(dim=0, keepdim=True)
-        pts_all.append(ms)
-        pc_all.append(torch.cat([pc, torch.full((pc.shape[0], 1), b, dtype=torch.int32, device=pc.device)], 1))
-        n_cur.append(int(cur.shape[0]))                                                # key-frame points come first and all survive the clamp
-        cur_off.append(off)
-        off += ms.shape[0]
-    point_ms, pc_ms = torch.cat(pts_all, 0).contiguous(), torch.cat(pc_all, 0).contiguous()
-    vox, first, inverse = ops.unique_coords(pc_ms, want_index=True, want_inverse=True)
+    All of it is three fused passes over the batch (tsg_aggregate_quantize_nus), one compaction and one radix sort — no
+    per-sweep Python loop, one host read-back (kept points, key points per sample, voxel extent) + the voxel count.
+    Returns the same dict as aggregate_voxelize (coords (M,4) [x,y,z,b], feats (M,5), inverse, cur_rows, point_ms, pc_ms, inds)
+    plus n_cur (key-frame points per sample that survive the ego-box filter)."""
+    if batch is None:
+        batch = NusBatch(samples, Rs, Ts, dts)
+    if points is None:
+        points = batch.points()
+    dev = points.device
+    feats, coords, flags, extent = ops.aggregate_quantize_nus(points, batch.sweeps, batch.n_samples, voxel_size)
+    point_ms, pc_ms, pos, m_dev = ops.compact_rows(flags, feats, coords, want_pos=True, sync=False)
+    key_pos = pos[torch.from_numpy(batch.key_idx).to(dev)]                     # -1 for key points inside the ego box
+    per_sample = torch.zeros(batch.n_samples, dtype=torch.int32, device=dev)
+    per_sample.index_add_(0, torch.from_numpy(batch.key_sample).to(dev), (key_pos >= 0).to(torch.int32))
+    span = (extent[:, 8:11] - extent[:, 4:7]).amax(dim=0)
+    host = torch.cat([m_dev, span, per_sample]).tolist()                       # the one host sync of the front end
+    m, (sx, sy, sz), n_cur = host[0], host[1:4], host[4:]
+    point_ms, pc_ms = point_ms[:m], pc_ms[:m]
+    bits = [max(1, int(v).bit_length()) for v in (sx, sy, sz, batch.n_samples - 1)]
+    vox, first, inverse = ops.unique_coords(pc_ms, want_index=True, want_inverse=True, field_bits=bits)
     vfeat = ops.gather_rows(point_ms, first)
-    cur_idx = torch.cat([torch.arange(o, o + n, device=pc_ms.device) for o, n in zip(cur_off, n_cur)])
-    return dict(coords=vox, feats=vfeat, inverse=inverse, cur_rows=inverse[cur_idx], point_ms=point_ms, pc_ms=pc_ms, inds=first,
-                n_cur=n_cur)
+    cur_rows = inverse[key_pos[key_pos >= 0].long()]
+    return dict(coords=vox, feats=vfeat, inverse=inverse, cur_rows=cur_rows, point_ms=point_ms, pc_ms=pc_ms, inds=first,
+                n_cur=[int(v) for v in n_cur], field_bits=bits)
 
 
 def as_lidar_ms(out: dict) -> SparseTensor:

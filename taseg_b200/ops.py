@@ -683,3 +683,32 @@ def aggregate_quantize_dev(points: torch.Tensor, frames_dev: torch.Tensor, n_fra
     call("tsg_aggregate_quantize_dev", ptr(pts), c_in, ptr(frames_dev), int(n_frames), int(max_count), int(n_samples), ptr(keep),
          float(voxel_size), ptr(feats), ptr(coords), ptr(flags), ptr(ws), ws_bytes, stream())
     return feats, coords, flags
+
+
+def aggregate_quantize_nus(points: torch.Tensor, sweeps: Sequence[dict], n_samples: int, voxel_size: float):
+    """nuScenes multi-sweep aggregation in three fused passes (tsg_aggregate_quantize_nus).  points (sum n, c >= 5) fp32,
+    sweeps: dicts(offset, count, sample, is_key, R (3,3) float64, T (3,) float64, dt) — p_key = p @ R + T.
+    Returns feats (sum n, c) [x', y', z', intensity, dt, ...], coords (sum n, 4) int32, flags (sum n) uint8 (kept),
+    extent (n_samples, 12) int32 view of [cur_min(4 f32 bits), ms_min(4), ms_max(4)]."""
+    L.require_cuda(points)
+    pts = points.float().contiguous()
+    n, c = pts.shape
+    arr = (L.Sweep * len(sweeps))()
+    for i, f in enumerate(sweeps):
+        arr[i].offset, arr[i].count, arr[i].sample, arr[i].is_key = int(f["offset"]), int(f["count"]), int(f["sample"]), int(f["is_key"])
+        R = np.asarray(f["R"], np.float64).reshape(-1)
+        T = np.asarray(f["T"], np.float64).reshape(-1)
+        for j in range(9):
+            arr[i].R[j] = float(R[j])
+        for j in range(3):
+            arr[i].T[j] = float(T[j])
+        arr[i].dt = float(f["dt"])
+    feats = torch.empty((n, c), dtype=torch.float32, device=pts.device)
+    coords = torch.empty((n, 4), dtype=torch.int32, device=pts.device)
+    flags = torch.empty((n,), dtype=torch.uint8, device=pts.device)
+    ws_bytes = int(L.lib().tsg_aggregate_nus_ws_bytes(n_samples))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=pts.device)
+    call("tsg_aggregate_quantize_nus", ptr(pts), c, arr, len(sweeps), n_samples, float(voxel_size), ptr(feats), ptr(coords),
+         ptr(flags), ptr(ws), ws_bytes, stream())
+    extent = ws[:n_samples * 48].view(torch.int32).view(n_samples, 12)
+    return feats, coords, flags, extent
