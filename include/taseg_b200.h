@@ -186,6 +186,29 @@ int tsg_gather_rows(const void *src, int width, const int32_t *idx, int64_t n, v
  * tsg_devoxelize_fwd/bwd replace devoxelize_forward_cuda / _backward_cuda        TS/backend/devoxelize/devoxelize_cuda.h:5-11
  * feats are (rows, c) of `dtype`; accumulation is fp32. */
 int tsg_count(const int32_t *idx, int64_t n, int32_t *out, int64_t m, tsg_stream_t stream);
+/* B200-first versions of the same four transforms (taseg_b200/csrc/pointvoxel.cu): 16-byte vector access with a lane
+ * group per row, index / weight words read once per row, and — for the scatter-mean of
+ * TS/backend/voxelize/voxelize_cuda.cu:12-25 — a deterministic SEGMENTED REDUCTION instead of fp32 atomics:
+ *   tsg_voxelize_plan     sorts the point ids by voxel (stable radix sort): order (n) uint32 = point ids grouped by voxel
+ *                         in point order, skeys (n) uint64 = their voxel ids (scratch), seg (m, 2) int32 = [first, one past
+ *                         last] sorted position of every voxel ({0, 0}: empty).  One plan serves every voxelize over `idx`.
+ *   tsg_voxelize_fwd_seg  out[v] = sum_{i in voxel v, point order} feats[i] / counts[v], written once, any dtype, no
+ *                         accumulation workspace; run-to-run bit-identical.
+ *   tsg_voxelize_bwd_vec / tsg_devoxelize_fwd_vec / tsg_devoxelize_bwd_vec: vectorised gather / trilinear gather / vector
+ *                         atomic scatter (TS/backend/voxelize/voxelize_cuda.cu:28-42, devoxelize_cuda.cu:11-57).
+ * All need rows of a multiple of 16 bytes, 16-byte aligned (tsg_pv_vector_ok); the scalar entry points above remain. */
+int tsg_pv_vector_ok(const void *a, const void *b, int c, int dtype);
+size_t tsg_voxelize_plan_ws_bytes(int64_t n);
+int tsg_voxelize_plan(const int32_t *idx, int64_t n, int64_t m, uint32_t *order, uint64_t *skeys, int32_t *seg,
+                      void *ws, size_t ws_bytes, tsg_stream_t stream);
+int tsg_voxelize_fwd_seg(const void *feats, int dtype, const uint32_t *order, const int32_t *seg, const int32_t *counts,
+                         int64_t n, int c, int64_t m, void *out, tsg_stream_t stream);
+int tsg_voxelize_bwd_vec(const void *top_grad, int dtype, const int32_t *idx, const int32_t *counts, int64_t n, int c,
+                         void *bottom_grad, tsg_stream_t stream);
+int tsg_devoxelize_fwd_vec(const void *feats, int dtype, const int32_t *idx8, const float *w8, int64_t n, int c, void *out,
+                           tsg_stream_t stream);
+int tsg_devoxelize_bwd_vec(const void *top_grad, int dtype, const int32_t *idx8, const float *w8, int64_t n, int c,
+                           int64_t m, void *bottom_grad, float *acc_ws, tsg_stream_t stream);
 int tsg_voxelize_fwd(const void *feats, int dtype, const int32_t *idx, const int32_t *counts, int64_t n, int c,
                      int64_t m, void *out, float *acc_ws, tsg_stream_t stream);
 int tsg_voxelize_bwd(const void *top_grad, int dtype, const int32_t *idx, const int32_t *counts, int64_t n, int c,

@@ -20,7 +20,7 @@ TSG_OK, TSG_ERR_INVALID, TSG_ERR_CUDA, TSG_ERR_WORKSPACE, TSG_ERR_RANGE, TSG_ERR
 TSG_F32, TSG_BF16, TSG_F16 = 0, 1, 2
 DTYPES = {torch.float32: TSG_F32, torch.bfloat16: TSG_BF16, torch.float16: TSG_F16}
 
-_SCALARS = {"int": ctypes.c_int, "int32_t": ctypes.c_int32, "int64_t": ctypes.c_int64, "size_t": ctypes.c_size_t,
+_SCALARS = {"uint64_t": ctypes.c_uint64, "int": ctypes.c_int, "int32_t": ctypes.c_int32, "int64_t": ctypes.c_int64, "size_t": ctypes.c_size_t,
             "float": ctypes.c_float, "uint32_t": ctypes.c_uint32, "tsg_stream_t": ctypes.c_void_p}
 
 
@@ -106,7 +106,7 @@ def check(status: int, what: str = "") -> None:
 KERNELS_PER_CALL = {"tsg_table_build": 2, "tsg_coord_table_build": 2, "tsg_kmap_pairs": 2, "tsg_kmap_transpose": 2,
                     "tsg_sort_pairs": 4, "tsg_unique_coords": 7, "tsg_unique_hash": 11, "tsg_aggregate_quantize": 4,
                     "tsg_compact_rows": 3, "tsg_kmap_sort_rows": 5, "tsg_aggregate_quantize_nus": 4, "tsg_aggregate_quantize_dev": 4,
-                    "tsg_unique_coords_dev": 7, "tsg_coord_table_build_dev": 2, "tsg_kmap_sort_rows_dev": 5, "tsg_kmap_transpose_dev": 2}
+                    "tsg_unique_coords_dev": 7, "tsg_coord_table_build_dev": 2, "tsg_kmap_sort_rows_dev": 5, "tsg_kmap_transpose_dev": 2, "tsg_voxelize_plan": 5}
 launch_count = 0
 
 

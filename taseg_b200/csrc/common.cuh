@@ -161,6 +161,12 @@ __device__ inline int table_find(const Slot *__restrict__ tab, unsigned long lon
   }
 }
 
+// stable LSD radix sort of (64-bit key, 32-bit payload) pairs over key bits [begin_bit, end_bit) (sort.cu); vals_in NULL =
+// the payload is the input position; workspace tsg_sort_ws_bytes(n); n_dev: optional device row counter (n = capacity)
+int sort_pairs(const unsigned long long *keys_in, const unsigned *vals_in, int64_t n, int begin_bit, int end_bit,
+               unsigned long long *keys_out, unsigned *vals_out, void *ws_mem, size_t ws_bytes, cudaStream_t stream,
+               const int *n_dev = nullptr);
+
 // ------------------------------------------------------------------ block scan (power-of-two block sizes, <=1024)
 template <int THREADS>
 __device__ inline int block_exclusive_scan(int v, int *total) {

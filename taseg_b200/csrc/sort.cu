@@ -165,9 +165,9 @@ static size_t sort_ws_layout(int64_t n, char *base, SortWs *ws) {
   return off;
 }
 
-static int sort_pairs(const unsigned long long *keys_in, const unsigned *vals_in, int64_t n, int begin_bit,
-                      int end_bit, unsigned long long *keys_out, unsigned *vals_out, void *ws_mem, size_t ws_bytes,
-                      cudaStream_t stream, const int *n_dev = nullptr) {
+int sort_pairs(const unsigned long long *keys_in, const unsigned *vals_in, int64_t n, int begin_bit,
+               int end_bit, unsigned long long *keys_out, unsigned *vals_out, void *ws_mem, size_t ws_bytes,
+               cudaStream_t stream, const int *n_dev) {
   if (n <= 0) return TSG_OK;
   if (n >= (1ll << 30)) {
     set_error("tsg_sort_pairs: n must be < 2^30");

@@ -325,13 +325,52 @@ def spcount(idx: torch.Tensor, num: int) -> torch.Tensor:
     return out
 
 
-def voxelize_forward(feats: torch.Tensor, idx: torch.Tensor, counts: torch.Tensor) -> torch.Tensor:
+class VoxelizePlan:
+    """Points grouped by voxel (stable radix sort of the point ids by `idx`): what the segmented scatter-mean walks.
+    Built once per index tensor and cached on it, so SPVCNN's repeated point_to_voxel over the same points sorts once."""
+
+    def __init__(self, idx: torch.Tensor, m: int):
+        idx = _i32(idx).contiguous()
+        n, dev = idx.numel(), idx.device
+        self.n, self.m = n, int(m)
+        self.order = torch.empty((max(n, 1),), dtype=torch.int32, device=dev)
+        skeys = torch.empty((max(n, 1),), dtype=torch.int64, device=dev)      # scratch: the sorted voxel ids
+        self.seg = torch.empty((max(self.m, 1), 2), dtype=torch.int32, device=dev)
+        ws_bytes = int(L.lib().tsg_voxelize_plan_ws_bytes(n))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        call("tsg_voxelize_plan", ptr(idx), n, self.m, ptr(self.order), ptr(skeys), ptr(self.seg), ptr(ws), ws_bytes, stream())
+
+    @staticmethod
+    def of(idx: torch.Tensor, m: int) -> "VoxelizePlan":
+        key = (idx.data_ptr(), idx._version, int(m), idx.numel())
+        cached = getattr(idx, "_tsg_plan", None)
+        if cached is None or cached[0] != key:
+            cached = (key, VoxelizePlan(idx, m))
+            try:
+                idx._tsg_plan = cached
+            except AttributeError:
+                pass
+        return cached[1]
+
+
+def _vec_ok(a: torch.Tensor, b: torch.Tensor, c: int) -> bool:
+    return bool(L.lib().tsg_pv_vector_ok(ptr(a), ptr(b), int(c), L.DTYPES[a.dtype]))
+
+
+def voxelize_forward(feats: torch.Tensor, idx: torch.Tensor, counts: torch.Tensor, plan: Optional[VoxelizePlan] = None) -> torch.Tensor:
+    """Scatter-mean of point rows into voxel rows: deterministic segmented reduction over a VoxelizePlan (vector rows),
+    or the reference-style atomic kernel for rows that are not a multiple of 16 bytes."""
     L.require_cuda(feats, idx, counts)
     feats = feats.contiguous()
     idx, counts = _i32(idx).contiguous(), _i32(counts).contiguous()
     n, c = feats.shape
     m = counts.shape[0]
     out = torch.empty((m, c), dtype=feats.dtype, device=feats.device)
+    if m and c and _vec_ok(feats, out, c):
+        plan = plan or VoxelizePlan.of(idx, m)
+        call("tsg_voxelize_fwd_seg", ptr(feats), L.DTYPES[feats.dtype], ptr(plan.order), ptr(plan.seg), ptr(counts), n, c, m,
+             ptr(out), stream())
+        return out
     acc = None if feats.dtype == torch.float32 else torch.empty((m, c), dtype=torch.float32, device=feats.device)
     call("tsg_voxelize_fwd", ptr(feats), L.DTYPES[feats.dtype], ptr(idx), ptr(counts), n, c, m, ptr(out), ptr(acc), stream())
     return out
@@ -342,7 +381,8 @@ def voxelize_backward(top_grad: torch.Tensor, idx: torch.Tensor, counts: torch.T
     idx, counts = _i32(idx).contiguous(), _i32(counts).contiguous()
     c = top_grad.shape[1]
     out = torch.empty((n, c), dtype=top_grad.dtype, device=top_grad.device)
-    call("tsg_voxelize_bwd", ptr(top_grad), L.DTYPES[top_grad.dtype], ptr(idx), ptr(counts), n, c, ptr(out), stream())
+    name = "tsg_voxelize_bwd_vec" if (n and c and _vec_ok(top_grad, out, c)) else "tsg_voxelize_bwd"
+    call(name, ptr(top_grad), L.DTYPES[top_grad.dtype], ptr(idx), ptr(counts), n, c, ptr(out), stream())
     return out
 
 
@@ -352,7 +392,8 @@ def devoxelize_forward(feats: torch.Tensor, idx8: torch.Tensor, w8: torch.Tensor
     idx8, w8 = _i32(idx8).contiguous(), w8.float().contiguous()
     n, c = idx8.shape[0], feats.shape[1]
     out = torch.empty((n, c), dtype=feats.dtype, device=feats.device)
-    call("tsg_devoxelize_fwd", ptr(feats), L.DTYPES[feats.dtype], ptr(idx8), ptr(w8), n, c, ptr(out), stream())
+    name = "tsg_devoxelize_fwd_vec" if (n and c and _vec_ok(feats, out, c)) else "tsg_devoxelize_fwd"
+    call(name, ptr(feats), L.DTYPES[feats.dtype], ptr(idx8), ptr(w8), n, c, ptr(out), stream())
     return out
 
 
@@ -362,7 +403,8 @@ def devoxelize_backward(top_grad: torch.Tensor, idx8: torch.Tensor, w8: torch.Te
     n, c = top_grad.shape
     out = torch.empty((m, c), dtype=top_grad.dtype, device=top_grad.device)
     acc = None if top_grad.dtype == torch.float32 else torch.empty((m, c), dtype=torch.float32, device=top_grad.device)
-    call("tsg_devoxelize_bwd", ptr(top_grad), L.DTYPES[top_grad.dtype], ptr(idx8), ptr(w8), n, c, m, ptr(out), ptr(acc), stream())
+    name = "tsg_devoxelize_bwd_vec" if (m and c and c % 4 == 0 and _vec_ok(top_grad, out, c)) else "tsg_devoxelize_bwd"
+    call(name, ptr(top_grad), L.DTYPES[top_grad.dtype], ptr(idx8), ptr(w8), n, c, m, ptr(out), ptr(acc), stream())
     return out
 
 

@@ -238,6 +238,45 @@ def test_point_voxel_ops(ts, golden):
     assert hf.dtype == torch.bfloat16 and rel_err(npy(hf), g["dv1_out"]) < 2e-2
 
 
+@pytest.mark.parametrize("c,dtype", [(32, torch.float32), (96, torch.float32), (4, torch.float32), (64, torch.bfloat16),
+                                     (48, torch.float16), (5, torch.float32)])
+def test_point_voxel_vector_kernels(ts, c, dtype):
+    """The lane-group / segmented-reduction kernels of pointvoxel.cu against the numpy oracle (TS voxelize / devoxelize
+    semantics) on random maps with empty voxels, unmatched points (-1) and missing corners; the scatter-mean must be
+    bit-identical run to run (no atomics).  c = 5 exercises the scalar fall-back (rows not a multiple of 16 bytes)."""
+    from taseg_b200 import ops
+    rng = np.random.default_rng(c)
+    n, m = 50000, 9000
+    idx = rng.integers(-1, m - 50, n).astype(np.int32)          # -1 = unmatched; the last 50 voxels stay empty
+    counts = T.spcount(idx, m)
+    feats = rng.normal(size=(n, c)).astype(np.float32)
+    tol = 1e-5 if dtype == torch.float32 else 2e-2
+    f_t = cu(feats).to(dtype)
+    f_ref = f_t.float().cpu().numpy()
+    got = ops.voxelize_forward(f_t, cu(idx), cu(counts))
+    again = ops.voxelize_forward(f_t, cu(idx), cu(counts))
+    assert got.dtype == dtype
+    if (c * f_t.element_size()) % 16 == 0:      # segmented reduction (the scalar fall-back keeps the reference's atomics)
+        assert torch.equal(got, again), "scatter-mean is not deterministic"
+    ok = idx >= 0                                               # the numpy oracle has no "unmatched point" branch
+    assert rel_err(npy(got.float()), T.spvoxelize(f_ref[ok], idx[ok], np.maximum(counts, 1))) < tol
+    gy = rng.normal(size=(m, c)).astype(np.float32)
+    g_t = cu(gy).to(dtype)
+    gb = ops.voxelize_backward(g_t, cu(idx), cu(counts), n)
+    want_gb = T.spvoxelize_backward(g_t.float().cpu().numpy(), np.where(ok, idx, 0), np.maximum(counts, 1), n)
+    want_gb[~ok] = 0
+    assert rel_err(npy(gb.float()), want_gb) < tol
+    idx8 = rng.integers(-1, m, (n, 8)).astype(np.int32)
+    w8 = rng.random((n, 8)).astype(np.float32)
+    w8[idx8 < 0] = 0
+    vf = cu(gy).to(dtype)
+    dv = ops.devoxelize_forward(vf, cu(idx8), cu(w8))
+    assert rel_err(npy(dv.float()), T.spdevoxelize(vf.float().cpu().numpy(), idx8, w8)) < tol
+    top = cu(feats).to(dtype)
+    db = ops.devoxelize_backward(top, cu(idx8), cu(w8), m)
+    assert rel_err(npy(db.float()), T.spdevoxelize_backward(top.float().cpu().numpy(), idx8, w8, m)) < (1e-4 if dtype == torch.float32 else 2e-2)
+
+
 def test_fuse_and_aggregate(ts, golden):
     from taseg_b200 import ops
     g = golden("fuse_kat")
