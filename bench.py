@@ -68,6 +68,22 @@ def make_samples(first_seed, count):
         return list(ex.map(synth.kitti_sample, [first_seed + i for i in range(count)], [N_FRAMES] * count))
 
 
+def _kitti1(seed):
+    from taseg_b200 import synth
+    return synth.kitti_sample(seed, 1)
+
+
+def _nus10(seed):
+    from taseg_b200 import synth
+    return synth.nus_sample(seed, 10)
+
+
+def pool_map(fn, seeds):
+    from concurrent.futures import ProcessPoolExecutor
+    with ProcessPoolExecutor(max_workers=min(len(seeds), os.cpu_count() or 1)) as ex:
+        return list(ex.map(fn, seeds))
+
+
 class ClockSampler(threading.Thread):
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -138,6 +154,127 @@ def cpu_arm(steps, warmup, seed=2000):
     return dict(value=SECTOR / t, unit=UNIT, cores=cores, kind=kind, sample=sample, seconds_per_sample=t)
 
 
+def other_configs(rank, world, steps=6, warmup=2):
+    """Short measurements of BASELINE.json configs[2], [3] and [4] in the same run and with the same rules as the headline
+    (warm-up, barrier + synchronize on both sides, CUDA events, max over ranks), so that they reach the driver's BENCH /
+    SCALE records: the global batch of configs[2] (8 scans) and configs[3] (16 samples) is SHARDED over the ranks
+    ("scaling": "strong"); configs[4] trains on 4 scans per GPU with the NCCL gradient all-reduce ("weak")."""
+    import torch
+    import torch.distributed as dist
+    import taseg_b200 as ts
+    from taseg_b200 import frontend, parallel, synth
+    from taseg_b200.engine import Engine
+    from taseg_b200.segmentor import SPVCNN, MinkUNetMs, ModelCfg
+
+    def randomize_bn(model):
+        g = torch.Generator().manual_seed(1)
+        for m in model.modules():
+            if isinstance(m, torch.nn.modules.batchnorm._BatchNorm):
+                m.running_mean.copy_(torch.randn(m.num_features, generator=g) * 0.1)
+                m.running_var.copy_(torch.rand(m.num_features, generator=g) + 0.5)
+        return model.cuda().eval()
+
+    def timed(step, n_streams=2):
+        streams = [torch.cuda.Stream() for _ in range(n_streams)]
+        for i in range(warmup):
+            with torch.cuda.stream(streams[i % n_streams]):
+                step()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            with torch.cuda.stream(streams[i % n_streams]):
+                step()
+        for st in streams:
+            torch.cuda.current_stream().wait_stream(st)
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        return parallel.max_over_ranks(e0.elapsed_time(e1) / steps, "cuda")
+
+    out = {}
+    planes = [32, 32, 64, 128, 256, 256, 128, 96, 96]
+    # ---- configs[2]: SPVCNN point-voxel backbone, single SemanticKITTI-shaped scans, global batch 8
+    try:
+        per = max(1, 8 // world)
+        torch.manual_seed(0)
+        cfg = ModelCfg(IN_FEATURE_DIM=4, BLOCK="ResBlock", NUM_LAYER=[2, 2, 2, 2, 2, 2, 2, 2], cr=1.0, PLANES=planes, pres=0.05,
+                       vres=0.05, IF_DIST=False, IGNORE_LABEL=0, DROPOUT_P=0.0)
+        eng = Engine(randomize_bn(SPVCNN(cfg, 20)))
+        smp = pool_map(_kitti1, [3000 + rank * per + i for i in range(per)])
+        mfb = frontend.MultiFrameBatch([s[0] for s in smp], [s[1] for s in smp])
+        pts, cur_idx = torch.from_numpy(mfb.points).cuda(), torch.from_numpy(mfb.cur_idx).cuda()
+
+        def step_spv():
+            o = frontend.aggregate_voxelize(pts, mfb, 0.05, cur_idx)
+            return eng(o["coords"], o["feats"][:, :4].contiguous())
+
+        ms = timed(step_spv)
+        out["configs[2]"] = {"workload": "SPVCNN cr1.0 (voxelize / devoxelize point branch), single SemanticKITTI-shaped scans, "
+                             "global batch 8 sharded over the GPUs", "value": per * world / (ms * 1e-3), "unit": UNIT,
+                             "ms_per_step": ms, "scans_per_gpu": per, "points_per_gpu": int(mfb.total), "scaling": "strong"}
+        del eng
+    except Exception as e:      # an auxiliary line must never take the headline down
+        out["configs[2]"] = {"error": repr(e)[:300]}
+    # ---- configs[3]: nuScenes shape, 10 sweeps, global batch 16
+    try:
+        per = max(1, 16 // world)
+        torch.manual_seed(0)
+        cfg = ModelCfg(IN_FEATURE_DIM=4, BLOCK="ResBlock", NUM_LAYER=[2, 3, 4, 6, 2, 2, 2, 2], cr=1.0, PLANES=planes, pres=0.1,
+                       vres=0.1, IF_DIST=False, IGNORE_LABEL=0, DROPOUT_P=0.0)
+        eng = Engine(randomize_bn(MinkUNetMs(cfg, 17)))
+        smp = pool_map(_nus10, [4000 + rank * per + i for i in range(per)])
+        nb = frontend.NusBatch([s[0] for s in smp], [s[1] for s in smp], [s[2] for s in smp], [s[3] for s in smp])
+        npts = nb.points()
+
+        def step_nus():
+            o = frontend.aggregate_voxelize_nus(None, None, None, None, 0.1, batch=nb, points=npts)
+            return eng(o["coords"], o["feats"], field_bits=o["field_bits"], out_rows=o["cur_rows"])
+
+        ms = timed(step_nus)
+        out["configs[3]"] = {"workload": "TASeg MinkUNetMs mk34 cr1.0 (IN_FEATURE_DIM 4, 17 classes), nuScenes shape: 10-sweep "
+                             "aggregation, 0.1 m voxels, global batch 16 sharded over the GPUs", "value": per * world / (ms * 1e-3),
+                             "unit": UNIT, "ms_per_step": ms, "samples_per_gpu": per, "points_per_sample": int(nb.total // per),
+                             "scaling": "strong"}
+        del eng, npts
+    except Exception as e:
+        out["configs[3]"] = {"error": repr(e)[:300]}
+    # ---- configs[4]: training step, bf16 autocast, SGD, NCCL weight-gradient all-reduce
+    try:
+        torch.cuda.empty_cache()
+        model = make_model().train()
+        smp = make_samples(5000 + rank * BATCH, BATCH)
+        mfb = frontend.MultiFrameBatch([s[0] for s in smp], [s[1] for s in smp])
+        o = frontend.aggregate_voxelize(torch.from_numpy(mfb.points).cuda(), mfb, VOXEL, torch.from_numpy(mfb.cur_idx).cuda())
+        coords, feats = o["coords"], o["feats"]
+        g = torch.Generator(device="cuda").manual_seed(rank)
+        labels = torch.randint(1, 20, (coords.shape[0],), device="cuda", generator=g)
+        opt = torch.optim.SGD(model.parameters(), lr=0.02, momentum=0.9, weight_decay=1e-4)
+        reducer = parallel.GradientReducer(model.parameters(), bucket_mb=25.0)
+        comm = []
+
+        def step_train():
+            batch = {"lidar_ms": ts.SparseTensor(feats.clone(), coords), "targets_ms": ts.SparseTensor(labels, coords)}
+            return parallel.train_step(model, batch, opt, reducer, amp_dtype=torch.bfloat16, comm_events=comm)
+
+        ms = timed(step_train, n_streams=1)
+        exposed = [a.elapsed_time(b) for a, b in comm[-steps:]] if comm else [0.0]
+        out["configs[4]"] = {"workload": "TASeg MinkUNetMs mk34 cr1.0 training step (forward, loss, backward, clip, SGD), bf16 "
+                             "autocast, 3-frame SemanticKITTI shape, 4 scans per GPU, bucketed NCCL gradient all-reduce "
+                             "overlapped with backward", "value": BATCH * world / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
+                             "scans_per_gpu": BATCH, "voxels_per_gpu": int(coords.shape[0]), "scaling": "weak",
+                             "allreduce_bytes_per_step": reducer.bytes_per_step() if world > 1 else 0,
+                             "allreduce_exposed_ms": parallel.max_over_ranks(sum(exposed) / len(exposed), "cuda"),
+                             "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
+        reducer.remove()
+    except Exception as e:
+        out["configs[4]"] = {"error": repr(e)[:300]}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -145,6 +282,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the short configs[2]/[3]/[4] measurements")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
@@ -358,6 +496,12 @@ def main():
                 "algorithmic_gflop_per_step": flops / 1e9, "kernel_ms_per_step": conv_ms,
                 "kernel_share_of_step": conv_ms / (ms / args.steps)}
 
+    others = None
+    if not args.no_other_configs:
+        del pipes, dev_pts, dev_out
+        torch.cuda.empty_cache()
+        others = other_configs(rank, world)
+
     if rank == 0:
         scans = BATCH * world * args.steps
         line = {"metric": METRIC, "value": scans / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -367,6 +511,8 @@ def main():
                         "d2h_bytes_per_step": host_out.numel() * 4, "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
                 "points_per_step": int(mfb.total), "current_points_per_step": n_cur}
+        if others is not None:
+            line["other_configs"] = others
         if world == 1 and not args.no_cpu_baseline:
             cb = cpu_arm(3, 0)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}

@@ -41,10 +41,29 @@ def _tc_ok(feats: torch.Tensor, c_in: int, c_out: int) -> bool:
     return feats.dtype == torch.bfloat16 and c_in % 16 == 0 and c_out % 16 == 0 and c_out <= 256
 
 
+# Packed tensor-core images of a layer's weights, W[k] for the forward and W[k]^T for the data gradient, cached per
+# PARAMETER VERSION: the optimizer's in-place update bumps `_version`, so a step packs each layer once instead of on every
+# forward and backward call (and an evaluation loop never re-packs).
+_PACKS = {}
+
+
+def packed_weights(param: torch.Tensor, transposed_w: bool) -> torch.Tensor:
+    key = (id(param), transposed_w)
+    hit = _PACKS.get(key)
+    if hit is not None and hit[0] == param._version and hit[1] == param.data_ptr():
+        return hit[2]
+    w = param.detach().float()
+    k, c_in, c_out = w.shape
+    packed = ops.pack_weights(w.transpose(1, 2).contiguous(), c_out) if transposed_w else ops.pack_weights(w, c_in)
+    _PACKS[key] = (param._version, param.data_ptr(), packed)
+    return packed
+
+
 class ConvolutionFunction(Function):
 
     @staticmethod
-    def forward(ctx, input: torch.Tensor, weight: torch.Tensor, kmap: ops.KernelMap, transposed: bool = False):
+    def forward(ctx, input: torch.Tensor, weight: torch.Tensor, kmap: ops.KernelMap, transposed: bool = False, param=None):
+        """param: the fp32 parameter `weight` was cast from (autocast), the key of the packed-weight cache."""
         input = input.contiguous()
         weight = weight.contiguous()
         if input.shape[1] != weight.shape[1]:
@@ -53,16 +72,17 @@ class ConvolutionFunction(Function):
         n_out = kmap.n_in if transposed else kmap.n_out
         k, c_in, c_out = weight.shape
         if _tc_ok(input, c_in, c_out):
-            packed = ops.pack_weights(weight, c_in)
-            out = ops.conv_forward_tc(input, None, packed, k, c_out, nbr, kmap.tile_mask(transposed), n_out)
+            packed = packed_weights(param, False) if param is not None else ops.pack_weights(weight, c_in)
+            nbr_s, mask_s, perm = kmap.sorted(transposed)      # mask-sorted tile rows: empty (tile, offset) pairs are skipped
+            out = ops.conv_forward_tc(input, None, packed, k, c_out, nbr_s, mask_s, n_out, perm=perm)
         else:
             out = ops.conv_forward(input, weight, nbr, n_out)
-        ctx.for_backwards = (input, weight, kmap, transposed)
+        ctx.for_backwards = (input, weight, kmap, transposed, param)
         return out
 
     @staticmethod
     def backward(ctx, grad_output: torch.Tensor):
-        input, weight, kmap, transposed = ctx.for_backwards
+        input, weight, kmap, transposed, param = ctx.for_backwards
         k = weight.shape[0]
         # pairs (in i, out o, k): dX[i] += dY[o] W[k]^T ; dW[k] += X[i]^T dY[o]
         tab_in_of_out = kmap.nbr_t if transposed else kmap.nbr       # rows = outputs of the forward, values = inputs
@@ -70,9 +90,11 @@ class ConvolutionFunction(Function):
         c_in, c_out = weight.shape[1], weight.shape[2]
         if ctx.needs_input_grad[0] and _tc_ok(input, c_out, c_in):
             # dgrad = the same tensor-core kernel over the transposed table with W[k]^T (bf16 operands, fp32 accumulate)
-            packed_t = ops.pack_weights(weight.transpose(1, 2).contiguous(), c_out)
+            packed_t = (packed_weights(param, True) if param is not None
+                        else ops.pack_weights(weight.transpose(1, 2).contiguous(), c_out))
+            nbr_s, mask_s, perm = kmap.sorted(not transposed)
             grad_input = ops.conv_forward_tc(grad_output.contiguous().to(torch.bfloat16), None, packed_t, k, c_in,
-                                             tab_out_of_in, kmap.tile_mask(not transposed), input.shape[0])
+                                             nbr_s, mask_s, input.shape[0], perm=perm)
         elif ctx.needs_input_grad[0]:
             grad_input = ops.conv_dgrad(grad_output, weight, tab_out_of_in, input.shape[0]).to(input.dtype)
         else:
@@ -81,7 +103,7 @@ class ConvolutionFunction(Function):
             grad_weight = ops.conv_wgrad_bf16(input, grad_output, tab_in_of_out, k).to(weight.dtype)
         else:
             grad_weight = ops.conv_wgrad(input, grad_output, tab_in_of_out, k).to(weight.dtype)
-        return grad_input, grad_weight, None, None
+        return grad_input, grad_weight, None, None, None
 
 
 def conv3d(input: SparseTensor, weight: torch.Tensor, kernel_size: Union[int, List[int], Tuple[int, ...]],
@@ -89,6 +111,7 @@ def conv3d(input: SparseTensor, weight: torch.Tensor, kernel_size: Union[int, Li
            dilation: Union[int, Tuple[int, ...]] = 1, transposed: bool = False) -> SparseTensor:
     kernel_size, stride, dilation = make_ntuple(kernel_size, 3), make_ntuple(stride, 3), make_ntuple(dilation, 3)
     feats = input.feats
+    param = weight if (weight.dim() == 3 and weight.is_leaf) else None
     if torch.is_autocast_enabled():        # reference: custom_fwd(cast_inputs=torch.half) (conv.py:19)
         dt = torch.get_autocast_dtype('cuda')
         feats, weight = feats.to(dt), weight.to(dt)
@@ -110,12 +133,12 @@ def conv3d(input: SparseTensor, weight: torch.Tensor, kernel_size: Union[int, Li
             table = coord_table(input, input.coords, input.stride)
             input.kmaps[key] = ops.build_kmap(table, input.coords.shape[0], out_coords, offsets)
         kmap = as_kernel_map(input.kmaps[key], weight.shape[0])
-        out_feats = ConvolutionFunction.apply(feats, weight, kmap, False)
+        out_feats = ConvolutionFunction.apply(feats, weight, kmap, False, param)
     else:
         out_stride = tuple(input.stride[k] // stride[k] for k in range(3))
         out_coords = input.cmaps[out_stride]                                   # KeyError like the reference (conv.py:186)
         kmap = as_kernel_map(input.kmaps[(out_stride, kernel_size, stride, dilation)], weight.shape[0])
-        out_feats = ConvolutionFunction.apply(feats, weight, kmap, True)
+        out_feats = ConvolutionFunction.apply(feats, weight, kmap, True, param)
 
     if bias is not None:
         out_feats = out_feats + bias.to(out_feats.dtype)

@@ -74,10 +74,10 @@ class GradientReducer:
             self._launch(b)
 
     def _launch(self, b: int) -> None:
-        ps = [p for p in self.buckets[b] if p.grad is not None]
-        if not ps:
-            return
-        flat = torch.cat([p.grad.reshape(-1).to(torch.float32) for p in ps])
+        # bucket membership is FIXED (every rank exchanges the same number of elements whatever it used this step): a
+        # parameter without a gradient on this rank contributes zeros, as DistributedDataParallel does for unused ones
+        ps = self.buckets[b]
+        flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).to(torch.float32) for p in ps])
         work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
         self._inflight.append((work, flat, ps))
 
@@ -94,6 +94,8 @@ class GradientReducer:
             off = 0
             for p in ps:
                 n = p.numel()
+                if p.grad is None:
+                    p.grad = torch.empty_like(p)
                 p.grad.copy_(flat[off:off + n].view_as(p.grad))
                 off += n
         self._inflight.clear()
@@ -110,9 +112,10 @@ class GradientReducer:
 
 def train_step(model: torch.nn.Module, batch_dict: dict, optimizer: torch.optim.Optimizer,
                reducer: Optional[GradientReducer] = None, amp_dtype: Optional[torch.dtype] = torch.bfloat16,
-               clip_grad_norm: Optional[float] = 10.0) -> float:
+               clip_grad_norm: Optional[float] = 10.0, comm_events: Optional[list] = None) -> float:
     """One training step of the reference loop (R/train.py:399-417) with bf16 autocast instead of fp16 + GradScaler:
-    forward -> loss -> backward (gradient buckets all-reduced while backward runs) -> clip -> optimizer step."""
+    forward -> loss -> backward (gradient buckets all-reduced while backward runs) -> clip -> optimizer step.
+    comm_events: optional list that receives one (start, end) CUDA event pair per step around `reducer.finish()`."""
     model.train()
     optimizer.zero_grad(set_to_none=True)
     dev_type = next(model.parameters()).device.type
@@ -121,7 +124,13 @@ def train_step(model: torch.nn.Module, batch_dict: dict, optimizer: torch.optim.
         loss = ret_dict['loss']
     loss.backward()
     if reducer is not None:
+        if comm_events is not None:     # device time between "backward has been issued" and "averaged gradients are in place":
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)   # the EXPOSED part of the exchange
+            e0.record()
         reducer.finish()
+        if comm_events is not None:
+            e1.record()
+            comm_events.append((e0, e1))
     if clip_grad_norm:
         torch.nn.utils.clip_grad_norm_(model.parameters(), clip_grad_norm)
     optimizer.step()
