@@ -59,6 +59,7 @@ class Table:
 
     @classmethod
     def from_keys(cls, keys: torch.Tensor) -> "Table":
+        L.require_cuda(keys)
         keys = keys.contiguous()
         t = cls(keys.numel(), keys.device)
         call("tsg_table_build", ptr(keys), t.n, ptr(t.buf), t.slots, stream())
@@ -66,6 +67,7 @@ class Table:
 
     @classmethod
     def from_coords(cls, coords: torch.Tensor, status: Optional[torch.Tensor] = None) -> "Table":
+        L.require_cuda(coords)
         coords = coords.contiguous()
         t = cls(coords.shape[0], coords.device)
         t.status = status if status is not None else _status(coords.device)
@@ -167,6 +169,7 @@ class KernelMap:
 
 
 def build_kmap(table: Table, n_in: int, out_coords: torch.Tensor, offsets: np.ndarray) -> KernelMap:
+    L.require_cuda(out_coords)
     out_coords = out_coords.contiguous()
     n_out = out_coords.shape[0]
     offs = np.ascontiguousarray(offsets, dtype=np.int32)
@@ -599,6 +602,7 @@ def conv_forward_tc(in0: torch.Tensor, in1: Optional[torch.Tensor], packed_w: to
     shortcut = (sc_in0, sc_in1 | None, sc_packed_w, sc_idx | None): a 1x1x1 convolution of (sc_in0 | sc_in1) (n_out rows)
     accumulated into the same tile (tsg_conv_fwd_tc2); sc_idx = the centre offset's line of `nbr` for sorted maps.
     n_dev: int32 device counter — n_out is then the capacity of the buffers and min(*n_dev, n_out) rows are computed."""
+    L.require_cuda(in0, in1, packed_w)
     assert in0.dtype == torch.bfloat16 and in0.is_contiguous()
     c0 = in0.shape[1]
     c1 = 0
