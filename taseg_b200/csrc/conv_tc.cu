@@ -57,11 +57,16 @@ constexpr int V8_MAX_STAGES = 8;
 constexpr int V8_PLAN_SLOTS = 4;
 constexpr int V8_PLAN_MAX = 512;                                  // stages of one super tile: <= 32 virtual offsets x 16 slices
 constexpr int V8_CONSUMER_WARPS = V8_PROD_WARPS + V8_EPI_WARPS + 3;  // producers + epilogue + 2 MMA + weights
-// Epilogue staging: per epilogue warp 32 rows x (64 B of output + 16 B pad).  The pad makes both access patterns
-// conflict-free: a thread walking its own row in 16-byte steps (pitch 80 B = 20 banks) and a warp reading
-// consecutive 16-byte chunks of consecutive rows.
-constexpr int V8_STG_PITCH = 80;
-constexpr int V8_STG_BYTES = 32 * V8_STG_PITCH;  // 2560
+// Epilogue staging: per epilogue warp 32 rows x 64 B of output; 16-byte chunk c of row r sits at chunk position
+// c ^ ((r >> 1) & 3).  Both access patterns are then conflict-free: eight threads walking their own rows write the same
+// chunk c of rows r..r+7 into eight different 16-byte bank groups ((r & 1) * 4 + (c ^ (r >> 1 & 3))), and eight lanes reading
+// the four chunks of two consecutive rows cover one 128-byte wavefront.  (v16 padded rows to 80 B instead: the row-pair
+// reads were 2-way conflicted, 8 wavefronts per LDS.128 in the ncu source view.)
+constexpr int V8_STG_PITCH = 64;
+constexpr int V8_STG_BYTES = 32 * V8_STG_PITCH;  // 2048
+__device__ __forceinline__ uint32_t stg_chunk(uint32_t stg, int r, int c) {
+  return stg + (uint32_t)r * V8_STG_PITCH + (uint32_t)((c ^ ((r >> 1) & 3)) << 4);
+}
 constexpr int V8_DYN_SMEM = 221 * 1024;          // dynamic shared memory requested per CTA
 
 // What the planner publishes per super tile: the tile, the offset masks of its G tiles and the list of pipeline stages
@@ -70,6 +75,7 @@ constexpr int V8_DYN_SMEM = 221 * 1024;          // dynamic shared memory reques
 struct __align__(16) Plan {
   int tile, n;      // n: bits 0-15 number of stages, bit 16 column half of the work item (N split)
   unsigned mask[2];
+  int split, slot;  // K split (work-item lists): bits 0-7 part of the tile's offsets this item sums, 8-15 number of parts; partial-sum slot
   unsigned short stage[V8_PLAN_MAX];
 };
 
@@ -91,7 +97,13 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
 constexpr int TRACE_N = 96;
 __device__ long long g_trace[13][TRACE_N];  // 0 producer group 0 got empty, 1 it arrived on full, 2 MMA got full, 3 MMA committed,
                                            // 4 weights got empty, 5 MMA starts waiting for full, 6 copies issued, 7 next indices requested
+__device__ long long g_life[8];             // trace build: CTA 0's clock64 at kernel entry, after the prologue barrier, first plan
+                                            // published, first plan seen by producers, last epilogue done, before exit
 #ifdef TSG_TC_TRACE  // profiling build (TSG_TC_TRACE=1 python -m taseg_b200.build): knock-outs and traces cost nothing otherwise
+#define TSG_LIFE(i)                                                        \
+  do {                                                                     \
+    if ((p.dbg & 128) && blockIdx.x == 0) g_life[i] = clock64();           \
+  } while (0)
 #define TSG_DBG(bit) (p.dbg & (bit))
 #define TSG_TRACE(role, idx)                                                              \
   do {                                                                                    \
@@ -100,6 +112,7 @@ __device__ long long g_trace[13][TRACE_N];  // 0 producer group 0 got empty, 1 i
 #else
 #define TSG_DBG(bit) 0
 #define TSG_TRACE(role, idx) do { } while (0)
+#define TSG_LIFE(i) do { } while (0)
 #endif
 
 // ---- epilogue building blocks: NCOLS accumulator columns of 32 tile rows (one per lane) through the warp's staging buffer
@@ -110,14 +123,47 @@ __device__ __forceinline__ void epi_prefetch_res(uint32_t stg, const char *res_c
   for (int it = 0; it < CPR; ++it) {
     const int r = it * (32 / CPR) + lane / CPR, q = lane % CPR;
     const int orow = __shfl_sync(0xffffffffu, rows_g, r);
-    cp_async16(stg + r * V8_STG_PITCH + q * 16, res_c0 + (long long)max(orow, 0) * pitch + q * 16, orow >= 0 ? 16u : 0u);
+    cp_async16(stg_chunk(stg, r, q), res_c0 + (long long)max(orow, 0) * pitch + q * 16, orow >= 0 ? 16u : 0u);
   }
 }
 
+// Wait until *flag == want (set by a warp of another, already running CTA); same watchdog policy as mbar_wait.
+__device__ __forceinline__ void spin_until(const int *flag, int want) {
+  long long t0 = 0;
+  for (uint32_t spin = 1; *reinterpret_cast<const volatile int *>(flag) != want; ++spin) {
+    __nanosleep(64);
+    if ((spin & 0x3ffu) == 0) {
+      const long long now = clock64();
+      if (!t0) t0 = now;
+      else if (now - t0 > (1ll << 33)) __trap();
+    }
+  }
+}
+
+// K split: the first of a tile's two work items to finish parks its fp32 accumulators in global memory ...
+template <int NCOLS>
+__device__ __forceinline__ void epi_store_partial(uint32_t taddr, float *part_row) {
+#pragma unroll
+  for (int cc = 0; cc < NCOLS; cc += 16) {
+    uint32_t v[16];
+    tmem_ld16(taddr + cc, v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      __stcg(reinterpret_cast<float4 *>(part_row + cc + 4 * j),
+             make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                         __uint_as_float(v[4 * j + 3])));
+  }
+}
+
+// ... and the second adds them to its own (part_row != nullptr) before bias / residual / ReLU.  a + b is commutative, so
+// the result does not depend on which item finished first.
 template <int NCOLS, bool F32>
 __device__ __forceinline__ void epi_block(const TcParams &p, uint32_t taddr, bool have_acc, const float *bias_c, uint32_t stg,
-                                          int lane, int rows_g, int c0, bool res_staged, bool no_store) {
+                                          int lane, int rows_g, int c0, bool res_staged, bool no_store,
+                                          const float *part_row = nullptr) {
   const uint32_t my_row = stg + lane * V8_STG_PITCH;
+  const int my_x = (lane >> 1) & 3;                       // chunk c of this thread's row sits at my_row + ((c ^ my_x) << 4)
+  auto my_chunk = [&](int c) -> uint32_t { return my_row + (uint32_t)((c ^ my_x) << 4); };
   // (A) every thread finishes NCOLS columns of its own row: accumulator + bias (+ residual), ReLU, convert, into staging
 #pragma unroll
   for (int cc = 0; cc < NCOLS; cc += 16) {
@@ -127,6 +173,16 @@ __device__ __forceinline__ void epi_block(const TcParams &p, uint32_t taddr, boo
     } else {
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] = 0u;
+    }
+    if (part_row) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 o = __ldcg(reinterpret_cast<const float4 *>(part_row + cc + 4 * j));
+        v[4 * j] = __float_as_uint(__uint_as_float(v[4 * j]) + o.x);
+        v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + o.y);
+        v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + o.z);
+        v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + o.w);
+      }
     }
     float f[16];
 #pragma unroll
@@ -140,8 +196,8 @@ __device__ __forceinline__ void epi_block(const TcParams &p, uint32_t taddr, boo
     if (p.residual) {
       uint4 r0, r1;
       if (res_staged) {
-        r0 = lds128(my_row + cc * 2);
-        r1 = lds128(my_row + cc * 2 + 16);
+        r0 = lds128(my_chunk(cc >> 3));
+        r1 = lds128(my_chunk((cc >> 3) + 1));
       } else if (rows_g >= 0) {  // fp32 output with a residual (not on the engine's path): direct loads
         const uint4 *rp = reinterpret_cast<const uint4 *>(p.residual + (long long)rows_g * p.c_out + c0 + cc);
         r0 = __ldg(rp);
@@ -163,8 +219,8 @@ __device__ __forceinline__ void epi_block(const TcParams &p, uint32_t taddr, boo
     if (F32) {
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        sts128(my_row + cc * 4 + 16 * j, make_uint4(__float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]),
-                                                    __float_as_uint(f[4 * j + 2]), __float_as_uint(f[4 * j + 3])));
+        sts128(my_chunk((cc >> 2) + j), make_uint4(__float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]),
+                                                   __float_as_uint(f[4 * j + 2]), __float_as_uint(f[4 * j + 3])));
     } else {
       uint32_t w[8];
 #pragma unroll
@@ -172,8 +228,8 @@ __device__ __forceinline__ void epi_block(const TcParams &p, uint32_t taddr, boo
         const __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
         w[j] = *reinterpret_cast<const uint32_t *>(&h);
       }
-      sts128(my_row + cc * 2, make_uint4(w[0], w[1], w[2], w[3]));
-      sts128(my_row + cc * 2 + 16, make_uint4(w[4], w[5], w[6], w[7]));
+      sts128(my_chunk(cc >> 3), make_uint4(w[0], w[1], w[2], w[3]));
+      sts128(my_chunk((cc >> 3) + 1), make_uint4(w[4], w[5], w[6], w[7]));
     }
   }
   __syncwarp();
@@ -186,7 +242,7 @@ __device__ __forceinline__ void epi_block(const TcParams &p, uint32_t taddr, boo
   for (int it = 0; it < CPR; ++it) {
     const int r = it * (32 / CPR) + lane / CPR, q = lane % CPR;
     const int orow = __shfl_sync(0xffffffffu, rows_g, r);
-    const uint4 val = lds128(stg + r * V8_STG_PITCH + q * 16);
+    const uint4 val = lds128(stg_chunk(stg, r, q));
     if (orow >= 0 && !no_store) *reinterpret_cast<uint4 *>(out_c0 + (long long)orow * pitch + q * 16) = val;
   }
   __syncwarp();
@@ -221,6 +277,7 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
   const uint32_t sfull0 = tfull0 + 32, sempty0 = sfull0 + 8 * V8_PLAN_SLOTS;
   const uint32_t obar0 = sempty0 + 8 * V8_PLAN_SLOTS;                // issue-order hand-off between the two MMA issuers (G == 1)
 
+  if (threadIdx.x == 0) TSG_LIFE(0);
   // programmatic dependent launch: the next kernel of the stream may start its prologue while this grid drains
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (threadIdx.x == 0) {
@@ -266,6 +323,7 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
+  if (threadIdx.x == 0) TSG_LIFE(1);
 
   auto need_of = [&](unsigned phi, int j) -> unsigned { return (unsigned)((phi ? need1 : need0) >> (4 * j)) & 15u; };
   // Plan ring, consumer side: wait for the next plan; release it when the role is done with the super tile.
@@ -316,34 +374,72 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
       const int st = pl->tile;
       const unsigned mask_g = pl->mask[g];
       const int cbase = (pl->n >> 16) * n_eff;              // first output channel of this work item
+      const int split = pl->split, pslot = pl->slot;
       plan_release_warp();
       if (st < 0) break;
       const uint32_t buf = it & 1, ph = (it >> 1) & 1;
       const long long r = (long long)(st * G + g) * TC_BM + quad * 32 + lane;  // destination row: fetched before the long wait
       const int rows_g = r < n_rows ? (p.perm ? __ldg(p.perm + r) : (int)r) : -1;
       const bool live = st * G + g < num_tiles && cfirst < n_eff;
-      if (res_staged && live) prefetch_res(rows_g, cbase + cfirst, blk_cols(cfirst));  // lands while the main loop still runs
+      const bool is_split = G == 1 && (split >> 8) > 1;                // one of the two work items of a K-split tile
+      if (res_staged && live && !is_split) prefetch_res(rows_g, cbase + cfirst, blk_cols(cfirst));  // lands while the main loop still runs
       mbar_wait_sleep(tfull0 + 8 * buf, ph);
       tc_fence_after();
       if (threadIdx.x == 0) TSG_TRACE(10, it);
       if (live) {
         const bool have_acc = mask_g != 0u || NPH > 1;   // a folded shortcut multiplies every live tile
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (buf * G + g) * (uint32_t)n_eff;
-        for (int lc = cfirst; lc < n_eff; lc += cstep) {     // lc: column inside the work item, c0: output channel
-          const int ncols = blk_cols(lc), c0 = cbase + lc;
-          if (res_staged) {
-            if (lc != cfirst) prefetch_res(rows_g, c0, ncols);
-            asm volatile("cp.async.wait_all;" ::: "memory");
+        // K split: this warp and the warp with the same number in the tile's other work item own the same rows and
+        // columns.  Whichever arrives first (state 0 -> 1) stores its accumulators and raises the state again when they
+        // are visible; the other waits for that (state 3), adds them to its own and runs the real epilogue.
+        int role = -1;
+        float *part = nullptr;
+        int *state = nullptr;
+        if (is_split) {
+          state = p.split_state + (size_t)pslot * V8_EPI_WARPS + warp;
+          part = p.split_scratch + ((size_t)pslot * TC_BM + quad * 32 + lane) * n_eff;
+          int a = 0;
+          if (lane == 0) a = atomicAdd(state, 1);
+          a = __shfl_sync(0xffffffffu, a, 0);
+          role = a == 0 ? 0 : 1;
+          if (role == 1) {
+            if (a == 1 && lane == 0) spin_until(state, 3);
             __syncwarp();
+            __threadfence();
+            if (res_staged) prefetch_res(rows_g, cbase + cfirst, blk_cols(cfirst));
           }
-          if (f32) epi_block<16, true>(p, taddr + lc, have_acc, bias_s + c0, stg, lane, rows_g, c0, res_staged, no_store);
-          else if (ncols == 32) epi_block<32, false>(p, taddr + lc, have_acc, bias_s + c0, stg, lane, rows_g, c0, res_staged, no_store);
-          else epi_block<16, false>(p, taddr + lc, have_acc, bias_s + c0, stg, lane, rows_g, c0, res_staged, no_store);
+        }
+        if (role == 0) {
+          for (int lc = cfirst; lc < n_eff; lc += cstep) {
+            if (blk_cols(lc) == 32 && !f32) epi_store_partial<32>(taddr + lc, part + lc);
+            else epi_store_partial<16>(taddr + lc, part + lc);
+          }
+          __threadfence();
+          __syncwarp();
+          if (lane == 0) atomicAdd(state, 1);
+        } else {
+          for (int lc = cfirst; lc < n_eff; lc += cstep) {     // lc: column inside the work item, c0: output channel
+            const int ncols = blk_cols(lc), c0 = cbase + lc;
+            if (res_staged) {
+              if (lc != cfirst) prefetch_res(rows_g, c0, ncols);
+              asm volatile("cp.async.wait_all;" ::: "memory");
+              __syncwarp();
+            }
+            const float *pr_ = role == 1 ? part + lc : nullptr;
+            if (f32) epi_block<16, true>(p, taddr + lc, have_acc, bias_s + c0, stg, lane, rows_g, c0, res_staged, no_store, pr_);
+            else if (ncols == 32) epi_block<32, false>(p, taddr + lc, have_acc, bias_s + c0, stg, lane, rows_g, c0, res_staged, no_store, pr_);
+            else epi_block<16, false>(p, taddr + lc, have_acc, bias_s + c0, stg, lane, rows_g, c0, res_staged, no_store, pr_);
+          }
+          if (role == 1) {   // both parts are in: re-arm the pair's state for the next launch
+            __syncwarp();
+            if (lane == 0) *state = 0;
+          }
         }
       }
       tc_fence_before();
       mbar_arrive(tempty0 + 8 * buf);
       if (threadIdx.x == 0) TSG_TRACE(11, it);
+      if (threadIdx.x == 0) TSG_LIFE(4);
     }
   } else if (warp == V8_MMA_WARP || warp == V8_MMA_WARP + 1) {
     // ================================================================= MMA issuers
@@ -479,28 +575,49 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
     // the bottleneck of the whole kernel — profiles/README.md.)
     Ring w;
     int static_next = blockIdx.x;
+    bool first_ticket = true;
+    // work-item list (K split, G == 1): the list replaces the tile enumeration; its length is a device value
+    const bool use_items = G == 1 && p.items != nullptr;
+    const int n_work = use_items ? __ldg(p.n_items) : num_super * NS;
     for (;;) {
       mbar_wait(sempty0 + 8 * w.slot, w.phase ^ 1);
       int t = 0;
       if (lane == 0) {
         if (p.sched) {
-          t = atomicAdd(p.sched, 1);
+          // the first ticket of a CTA is its block index (no round trip to the L2 before the first plan); the shared
+          // counter hands out the tickets from gridDim.x on
+          t = first_ticket ? (int)blockIdx.x : (int)gridDim.x + atomicAdd(p.sched, 1);
         } else {
           t = static_next;
           static_next += gridDim.x;
         }
       }
+      first_ticket = false;
       t = __shfl_sync(0xffffffffu, t, 0);
-      const int st = t < num_super * NS ? num_super - 1 - t / NS : -1;  // heavy (high-key) tiles first; NS column blocks each
-      const int half = t < num_super * NS ? t % NS : 0;
+      int st, half = 0, split = 1 << 8, pslot = 0;
       unsigned mm = 0, lv = 0;
-      if (st >= 0 && lane < G) {
-        const int tile = st * G + lane;
-        lv = tile < num_tiles ? 1u : 0u;
-        mm = lv ? ((p.tile_mask ? __ldg(p.tile_mask + tile) : 0xffffffffu) & kmask) : 0u;
+      if (use_items) {
+        int4 it = make_int4(-1, 0, 1 << 8, 0);
+        if (t < n_work) it = __ldg(p.items + t);
+        st = it.x;
+        split = it.z;
+        pslot = it.w;
+        if (st >= 0 && lane == 0) {
+          lv = st < num_tiles ? 1u : 0u;
+          mm = lv ? ((unsigned)it.y & kmask) : 0u;
+        }
+      } else {
+        st = t < n_work ? num_super - 1 - t / NS : -1;  // heavy (high-key) tiles first; NS column blocks each
+        half = t < n_work ? t % NS : 0;
+        if (st >= 0 && lane < G) {
+          const int tile = st * G + lane;
+          lv = tile < num_tiles ? 1u : 0u;
+          mm = lv ? ((p.tile_mask ? __ldg(p.tile_mask + tile) : 0xffffffffu) & kmask) : 0u;
+        }
       }
       const unsigned m0 = __shfl_sync(0xffffffffu, mm, 0), m1 = G > 1 ? __shfl_sync(0xffffffffu, mm, 1) : 0u;
-      const unsigned l0 = __shfl_sync(0xffffffffu, lv, 0), l1 = G > 1 ? __shfl_sync(0xffffffffu, lv, 1) : 0u;
+      // a folded shortcut (phase 1) is summed by part 0 of a split tile only
+      const unsigned l0 = (split & 0xff) ? 0u : __shfl_sync(0xffffffffu, lv, 0), l1 = G > 1 ? __shfl_sync(0xffffffffu, lv, 1) : 0u;
       Plan *pl = &plans[w.slot];
       // per phase: the slices of virtual offset `lane` that some tile of the super tile needs, and their positions in
       // the stage list (phase 0 first); f0 / f1 = first stage that multiplies sub-tile 0 / 1 (its first MMA overwrites
@@ -563,10 +680,13 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
         pl->n = n_total | (half << 16);
         pl->mask[0] = m0;
         pl->mask[1] = m1;
+        pl->split = split;
+        pl->slot = pslot;
       }
       __threadfence_block();  // every lane's stage entries are performed before lane 0 publishes the plan
       __syncwarp();
       if (lane == 0) mbar_arrive(sfull0 + 8 * w.slot);  // release: the plan is visible to the waiters
+      if (lane == 0 && w.slot == 0 && w.phase == 0) TSG_LIFE(2);
       w.advance(V8_PLAN_SLOTS);
       if (st < 0) break;
     }
@@ -704,6 +824,7 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
       uint32_t ib = 0;                           // which half of the warp's index buffer holds the current stage
       View cur, nxt;
       bool have = advance_mine(true) == 1;
+      if (pw == 0 && lane == 0) TSG_LIFE(3);
       if (have) {
         locate(cur);
         prefetch_idx(ibuf);
@@ -784,6 +905,7 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) TSG_LIFE(5);
   if (warp == V8_MMA_WARP) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
   }
@@ -837,6 +959,64 @@ __global__ void pack_weights_kernel(const float *__restrict__ w, int K, int c_in
   }
 }
 
+// Work-item list of a K-split launch.  One block; tiles are listed heaviest first (descending tile index of a mask-sorted
+// map).  A tile with more than `cap` active offsets becomes two items that sum the lower / upper half of its offsets —
+// the serial stage chain of the heaviest tile is what a launch with fewer tiles than SMs waits for (stride-16 level of the
+// benchmark: 120 tiles, 9.2 active offsets per SM on average but 27 on the critical path).  At most max_slots tiles are split.
+__global__ void __launch_bounds__(1024, 1) conv_split_items_kernel(const unsigned *__restrict__ tile_mask, long long n_out,
+                                                                 const int *__restrict__ n_out_dev, int K, int cap, int max_slots,
+                                                                 int4 *__restrict__ items, int *__restrict__ n_items) {
+  __shared__ int scan_a[1024], scan_b[1024];
+  const long long n_rows = dev_count(n_out_dev, n_out);
+  const int num_tiles = (int)((n_rows + TC_BM - 1) / TC_BM);
+  const unsigned kmask = K >= 32 ? 0xffffffffu : ((1u << K) - 1u);
+  const int per = (num_tiles + 1023) / 1024;
+  const int i0 = threadIdx.x * per, i1 = min(num_tiles, i0 + per);   // positions in heavy-first order: tile = num_tiles - 1 - i
+  int nsplit = 0;
+  for (int i = i0; i < i1; ++i) nsplit += __popc(tile_mask[num_tiles - 1 - i] & kmask) > cap ? 1 : 0;
+  // exclusive block scans (Hillis-Steele over 1024 partial sums): split tiles before this thread, then items
+  auto block_scan = [&](int *buf, int v) -> int {
+    buf[threadIdx.x] = v;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {
+      const int o = threadIdx.x >= d ? buf[threadIdx.x - d] : 0;
+      __syncthreads();
+      buf[threadIdx.x] += o;
+      __syncthreads();
+    }
+    return buf[threadIdx.x] - v;
+  };
+  int sbase = block_scan(scan_a, nsplit);
+  int nitems = 0;
+  {
+    int sb = sbase;
+    for (int i = i0; i < i1; ++i) {
+      const bool sp = __popc(tile_mask[num_tiles - 1 - i] & kmask) > cap && sb < max_slots;
+      if (__popc(tile_mask[num_tiles - 1 - i] & kmask) > cap) ++sb;
+      nitems += sp ? 2 : 1;
+    }
+  }
+  int ibase = block_scan(scan_b, nitems);
+  for (int i = i0; i < i1; ++i) {
+    const int tile = num_tiles - 1 - i;
+    const unsigned m = tile_mask[tile] & kmask;
+    const int x = __popc(m);
+    if (x > cap && sbase < max_slots) {
+      unsigned lo = 0, rest = m;
+      for (int b = 0; b < (x + 1) / 2; ++b) {   // lower half of the active offsets
+        lo |= rest & (0u - rest);
+        rest &= rest - 1;
+      }
+      items[ibase++] = make_int4(tile, (int)lo, 0 | (2 << 8), sbase);
+      items[ibase++] = make_int4(tile, (int)rest, 1 | (2 << 8), sbase);
+    } else {
+      items[ibase++] = make_int4(tile, (int)m, 0 | (1 << 8), 0);
+    }
+    if (x > cap) ++sbase;
+  }
+  if (threadIdx.x == 1023) *n_items = scan_b[1023];
+}
+
 }  // namespace tsg
 
 using namespace tsg;
@@ -872,6 +1052,13 @@ int tsg_debug_conv_trace(long long *host) {
   return TSG_OK;
 }
 
+/* ... and CTA 0's life-cycle stamps of the same launch (8 int64) */
+int tsg_debug_conv_life(long long *host) {
+  TSG_CUDA(cudaDeviceSynchronize());
+  TSG_CUDA(cudaMemcpyFromSymbol(host, g_life, sizeof(long long) * 8));
+  return TSG_OK;
+}
+
 static int fill_phase(TcPhase &h, const void *in0, int c0, const void *in1, int c1, const void *packed_w, int k,
                       const int32_t *nbr, int64_t nbr_stride, int *ksmax, const char *what) {
   const SlicePlan sp = slice_plan(c0, c1);
@@ -895,11 +1082,23 @@ static int fill_phase(TcPhase &h, const void *in0, int c0, const void *in1, int 
   return TSG_OK;
 }
 
-int tsg_conv_fwd_tc3(const void *in0, int c0, const void *in1, int c1, int64_t n_in, const void *packed_w, int k,
+int tsg_conv_split_items(const uint32_t *tile_mask, int64_t n_out, const int32_t *n_out_dev, int k, int cap, int max_slots,
+                         int32_t *items, int32_t *n_items, tsg_stream_t stream) {
+  if (!tile_mask || !items || !n_items || k <= 0 || k > 32 || cap < 1 || max_slots < 0 || n_out <= 0 ||
+      (n_out + TC_BM - 1) / TC_BM > 4096) {
+    set_error("tsg_conv_split_items: need tile_mask, items, n_items, 0 < K <= 32, cap >= 1 and at most 4096 tiles");
+    return TSG_ERR_INVALID;
+  }
+  conv_split_items_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(tile_mask, n_out, n_out_dev, k, cap, max_slots, (int4 *)items, n_items);
+  return check_launch("tsg_conv_split_items");
+}
+
+int tsg_conv_fwd_tc4(const void *in0, int c0, const void *in1, int c1, int64_t n_in, const void *packed_w, int k,
                      int c_out, const int32_t *nbr, int64_t nbr_stride, const uint32_t *tile_mask, const int32_t *perm,
                      int64_t n_out, const int32_t *n_out_dev, const void *sc_in0, int sc_c0, const void *sc_in1, int sc_c1,
                      const void *sc_packed_w, const int32_t *sc_idx, void *out, int out_dtype, const float *bias,
-                     const void *residual, int relu, int num_sms_hint, int32_t *sched, tsg_stream_t stream) {
+                     const void *residual, int relu, int num_sms_hint, int32_t *sched, const int32_t *items,
+                     const int32_t *n_items, int max_slots, float *split_scratch, int32_t *split_state, tsg_stream_t stream) {
   if (c0 % 16 || c1 % 16 || c_out % 16 || c_out > 256 || c_out <= 0 || c0 <= 0 || k <= 0 || k > 32 ||
       (out_dtype != TSG_BF16 && out_dtype != TSG_F32)) {
     set_error("tsg_conv_fwd_tc: need c0,c1,c_out multiples of 16, c_out<=256, K<=32, out bf16/f32");
@@ -946,6 +1145,16 @@ int tsg_conv_fwd_tc3(const void *in0, int c0, const void *in1, int c1, int64_t n
   p.residual = (const __nv_bfloat16 *)residual;
   p.relu = relu;
   p.sched = sched;
+  if (items) {
+    if (!n_items || !sched || (max_slots > 0 && (!split_scratch || !split_state))) {
+      set_error("tsg_conv_fwd_tc: a work-item list needs n_items, the scheduler counters and (max_slots > 0) scratch + state");
+      return TSG_ERR_INVALID;
+    }
+    p.items = (const int4 *)items;
+    p.n_items = n_items;
+    p.split_scratch = split_scratch;
+    p.split_state = split_state;
+  }
 #ifdef TSG_TC_TRACE  // profiling knock-outs (trace build only, wrong results): 1 no gathers, 2 no weight copies,
   const char *dbg_env = getenv("TSG_TC_DEBUG");  // 4 no MMAs, 8 no epilogue stores, 128 trace; re-read on every launch
   p.dbg = dbg_env ? atoi(dbg_env) : 0;
@@ -962,13 +1171,14 @@ int tsg_conv_fwd_tc3(const void *in0, int c0, const void *in1, int c1, int64_t n
   // 52 -> 63 us — a stage costs about the same whatever its width (the pipeline is hand-shake bound, profiles/README.md), so
   // twice the stages on 148 instead of 120 SMs is a loss.  Kept as a tested switch for wider / shallower launches.
   const char *ns_env = getenv("TSG_TC_NSPLIT");
-  const int ns = (ns_env && atoi(ns_env) == 2 && c_out >= 64 && c_out % 32 == 0 && num_tiles <= sms) ? 2 : 1;
+  const int ns = (!items && ns_env && atoi(ns_env) == 2 && c_out >= 64 && c_out % 32 == 0 && num_tiles <= sms) ? 2 : 1;
   p.ns = ns;
   p.n_eff = c_out / ns;
   // G sub-tiles share every weight slice; bounded by TMEM (2 buffers x G x n_eff fp32 columns <= 512) and by the
   // number of super tiles needed to keep every SM busy
   int G = p.n_eff <= 128 ? 2 : 1;  // (G = 4 spills the producers' index registers at 768 threads per CTA)
   while (G > 1 && (num_tiles + G - 1) / G * ns < 2LL * sms) G >>= 1;
+  if (items) G = 1;   // work items address single tiles
 #ifdef TSG_TC_TRACE
   if (getenv("TSG_TC_G1")) G = 1;
 #endif
@@ -996,7 +1206,7 @@ int tsg_conv_fwd_tc3(const void *in0, int c0, const void *in1, int c1, int64_t n
     TSG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, V8_DYN_SMEM));
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
-  const long long items = (num_tiles + G - 1) / G * ns;
+  const long long work = items ? num_tiles + max_slots : (num_tiles + G - 1) / G * ns;
   // programmatic dependent launch (TSG_TC_PDL=1, off by default): this grid's CTAs may be scheduled while the previous
   // kernel of the stream drains; the kernel executes griddepcontrol.wait before it reads anything.  Measured: +1 % with one
   // batch in flight, -8 % with two (early CTAs of one stream's next convolution hold the SMs the other stream's small
@@ -1004,7 +1214,7 @@ int tsg_conv_fwd_tc3(const void *in0, int c0, const void *in1, int c1, int64_t n
   static const bool pdl = getenv("TSG_TC_PDL") && atoi(getenv("TSG_TC_PDL")) == 1;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3((unsigned)(items < sms ? items : sms));
+  cfg.gridDim = dim3((unsigned)(work < sms ? work : sms));
   cfg.blockDim = dim3(V8_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = (cudaStream_t)stream;
@@ -1016,6 +1226,16 @@ int tsg_conv_fwd_tc3(const void *in0, int c0, const void *in1, int c1, int64_t n
   if (G == 2) TSG_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<2>, p));
   else TSG_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<1>, p));
   return check_launch("tsg_conv_fwd_tc");
+}
+
+int tsg_conv_fwd_tc3(const void *in0, int c0, const void *in1, int c1, int64_t n_in, const void *packed_w, int k,
+                     int c_out, const int32_t *nbr, int64_t nbr_stride, const uint32_t *tile_mask, const int32_t *perm,
+                     int64_t n_out, const int32_t *n_out_dev, const void *sc_in0, int sc_c0, const void *sc_in1, int sc_c1,
+                     const void *sc_packed_w, const int32_t *sc_idx, void *out, int out_dtype, const float *bias,
+                     const void *residual, int relu, int num_sms_hint, int32_t *sched, tsg_stream_t stream) {
+  return tsg_conv_fwd_tc4(in0, c0, in1, c1, n_in, packed_w, k, c_out, nbr, nbr_stride, tile_mask, perm, n_out, n_out_dev, sc_in0,
+                          sc_c0, sc_in1, sc_c1, sc_packed_w, sc_idx, out, out_dtype, bias, residual, relu, num_sms_hint, sched,
+                          nullptr, nullptr, 0, nullptr, nullptr, stream);
 }
 
 int tsg_conv_fwd_tc2(const void *in0, int c0, const void *in1, int c1, int64_t n_in, const void *packed_w, int k,

@@ -149,6 +149,12 @@ struct TcParams {
   uint32_t tmem_cols;
   int dbg;     // profiling knock-out bits (TSG_TC_DEBUG), 0 in production
   int *sched;  // {next ticket, finished CTAs}, zero between launches; NULL = static round-robin tile assignment
+  // K split (tsg_conv_split_items): work items {tile, offset mask, part | parts << 8, partial-sum slot} replace the tile
+  // enumeration; tiles with many active offsets are summed by two items (on two SMs) and combined in the epilogue
+  const int4 *items;
+  const int *n_items;    // device: number of work items
+  float *split_scratch;  // slots x 128 x n_eff fp32 partial sums
+  int *split_state;      // slots x 8 hand-off words, zero between launches
 };
 
 struct Ring {  // slot + phase of a circular mbarrier pipeline

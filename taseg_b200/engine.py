@@ -38,10 +38,11 @@ SORT_ROWS = os.environ.get("TSG_SORT_ROWS", "1") != "0"   # mask-sorted tile row
 
 
 def conv_map(km, transposed: bool = False):
-    """(nbr, tile_mask, perm) the tensor-core convolution consumes for kernel map `km`."""
+    """(nbr, tile_mask, perm, split) the tensor-core convolution consumes for kernel map `km` (split: K-split work items
+    of launches with about as many tiles as SMs, or None)."""
     if SORT_ROWS:
-        return km.sorted(transposed)
-    return (km.nbr_t if transposed else km.nbr, km.tile_mask(transposed), None)
+        return km.sorted(transposed) + (km.split_items(transposed),)
+    return (km.nbr_t if transposed else km.nbr, km.tile_mask(transposed), None, None)
 
 
 FOLD_SHORTCUT = os.environ.get("TSG_FOLD_SHORTCUT", "1") != "0"   # A/B switch: 1x1 shortcut as a second K phase of conv 2
@@ -87,14 +88,15 @@ class FusedConv:
     def __call__(self, x0, x1, m, n_out, residual=None, out_dtype=torch.bfloat16, sc_in=None, n_dev=None):
         """m = (nbr, tile_mask, perm) from conv_map(), or None for the identity map (1x1x1 convolutions, point MLPs).
         sc_in = (s0, s1 | None): the inputs of the folded shortcut.  n_dev: device row counter (n_out is then a capacity)."""
-        nbr, tile_mask, perm = m if m is not None else (None, None, None)
+        nbr, tile_mask, perm = m[:3] if m is not None else (None, None, None)
+        split = m[3] if m is not None and len(m) > 3 else None
         shortcut = None
         if self.sc_packed is not None:
             centre = nbr[self.k // 2] if perm is not None else None     # identity in tile-row order = the centre offset's line
             shortcut = (sc_in[0], sc_in[1], self.sc_packed, centre)
         return ops.conv_forward_tc(x0, x1, self.packed, self.k, self.c_out_pad, nbr, tile_mask, n_out, bias=self.bias,
                                    residual=residual, relu=self.relu, out_dtype=out_dtype, perm=perm, shortcut=shortcut,
-                                   n_dev=n_dev)
+                                   n_dev=n_dev, split=split)
 
 
 class FusedBlock:

@@ -158,6 +158,16 @@ class KernelMap:
             setattr(self, attr, (nbr_s, mask, perm))
         return getattr(self, attr)
 
+    def split_items(self, transposed: bool = False):
+        """SplitItems of the mask-sorted map when the launch has few enough tiles to want a K split, else None."""
+        rows = self.n_in if transposed else self.n_out
+        if not SplitItems.wanted(rows, self.k):
+            return None
+        attr = "_split_t" if transposed else "_split"
+        if getattr(self, attr, None) is None:
+            setattr(self, attr, SplitItems(self.sorted(transposed)[1], rows, self.k))
+        return getattr(self, attr)
+
     def __getitem__(self, i):
         return (self.nbmaps, self.nbsizes, self.sizes)[i]
 
@@ -589,6 +599,29 @@ def _sched_ws(device) -> torch.Tensor:
 
 
 DYNAMIC_TILES = os.environ.get("TSG_DYNAMIC_TILES", "1") != "0"   # A/B switch: in-kernel dynamic tile scheduler
+SPLIT_K = os.environ.get("TSG_SPLIT_K", "1") != "0"               # A/B switch: K-split work items for launches with few tiles
+SPLIT_MAX_TILES = int(os.environ.get("TSG_SPLIT_MAX_TILES", "222"))   # ... up to 1.5 tiles per SM of a B200
+SPLIT_CAP = int(os.environ.get("TSG_SPLIT_CAP", "14"))             # a tile with more active offsets becomes two work items
+
+
+class SplitItems:
+    """Work-item list of a K-split tensor-core launch (tsg_conv_split_items) for one (mask-sorted) kernel map."""
+
+    def __init__(self, tile_mask: torch.Tensor, n_out: int, k: int, n_dev: Optional[torch.Tensor] = None,
+                 cap: int = 0, max_slots: int = 0):
+        tiles = (int(n_out) + 127) // 128
+        self.max_slots = int(max_slots) if max_slots else min(tiles, 128)
+        dev = tile_mask.device
+        self.items = torch.empty((tiles + self.max_slots, 4), dtype=torch.int32, device=dev)
+        self.n_items = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.state = torch.zeros(self.max_slots * 8, dtype=torch.int32, device=dev)
+        call("tsg_conv_split_items", ptr(tile_mask), int(n_out), ptr(n_dev), int(k), int(cap or SPLIT_CAP), self.max_slots,
+             ptr(self.items), ptr(self.n_items), stream())
+
+    @staticmethod
+    def wanted(n_out: int, k: int) -> bool:
+        return SPLIT_K and DYNAMIC_TILES and k > SPLIT_CAP and (int(n_out) + 127) // 128 <= SPLIT_MAX_TILES
+
 PROFILE = None   # set to a list to record (tag, start_event, end_event, pairs, c_in, c_out) per tensor-core launch
 
 
@@ -596,12 +629,13 @@ def conv_forward_tc(in0: torch.Tensor, in1: Optional[torch.Tensor], packed_w: to
                     nbr: torch.Tensor, tile_mask: torch.Tensor, n_out: int, bias: Optional[torch.Tensor] = None,
                     residual: Optional[torch.Tensor] = None, relu: bool = False, out_dtype=torch.bfloat16,
                     num_sms: int = 0, perm: Optional[torch.Tensor] = None, shortcut=None,
-                    n_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
+                    n_dev: Optional[torch.Tensor] = None, split: Optional["SplitItems"] = None) -> torch.Tensor:
     """tcgen05/TMEM implicit GEMM; in0/in1 bf16 (n_in, c) with c % 16 == 0.  With `perm`, nbr/tile_mask are in the
     mask-sorted tile-row order of KernelMap.sorted() and tile row r is written to out[perm[r]].
     shortcut = (sc_in0, sc_in1 | None, sc_packed_w, sc_idx | None): a 1x1x1 convolution of (sc_in0 | sc_in1) (n_out rows)
     accumulated into the same tile (tsg_conv_fwd_tc2); sc_idx = the centre offset's line of `nbr` for sorted maps.
-    n_dev: int32 device counter — n_out is then the capacity of the buffers and min(*n_dev, n_out) rows are computed."""
+    n_dev: int32 device counter — n_out is then the capacity of the buffers and min(*n_dev, n_out) rows are computed.
+    split: SplitItems of this map (K-split work items; launches with about as many tiles as SMs)."""
     L.require_cuda(in0, in1, packed_w)
     assert in0.dtype == torch.bfloat16 and in0.is_contiguous()
     c0 = in0.shape[1]
@@ -643,9 +677,16 @@ def conv_forward_tc(in0: torch.Tensor, in1: Optional[torch.Tensor], packed_w: to
             pairs = pairs + rows * (sc0 + sc1) / (c0 + c1)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    call("tsg_conv_fwd_tc3", ptr(in0), c0, ptr(in1), c1, in0.shape[0], ptr(packed_w), k, c_out, ptr(nbr), nbr_stride,
-         ptr(tile_mask), ptr(perm), int(n_out), ptr(n_dev), ptr(s0), sc0, ptr(s1), sc1, ptr(sw), ptr(sidx), ptr(out), L.DTYPES[out_dtype],
-         ptr(bias), ptr(residual), int(relu), int(num_sms), ptr(_sched_ws(in0.device)) if DYNAMIC_TILES else None, stream())
+    if split is not None and DYNAMIC_TILES:
+        scratch = torch.empty((split.max_slots * 128 * c_out,), dtype=torch.float32, device=in0.device)
+        call("tsg_conv_fwd_tc4", ptr(in0), c0, ptr(in1), c1, in0.shape[0], ptr(packed_w), k, c_out, ptr(nbr), nbr_stride,
+             ptr(tile_mask), ptr(perm), int(n_out), ptr(n_dev), ptr(s0), sc0, ptr(s1), sc1, ptr(sw), ptr(sidx), ptr(out),
+             L.DTYPES[out_dtype], ptr(bias), ptr(residual), int(relu), int(num_sms), ptr(_sched_ws(in0.device)),
+             ptr(split.items), ptr(split.n_items), split.max_slots, ptr(scratch), ptr(split.state), stream())
+    else:
+        call("tsg_conv_fwd_tc3", ptr(in0), c0, ptr(in1), c1, in0.shape[0], ptr(packed_w), k, c_out, ptr(nbr), nbr_stride,
+             ptr(tile_mask), ptr(perm), int(n_out), ptr(n_dev), ptr(s0), sc0, ptr(s1), sc1, ptr(sw), ptr(sidx), ptr(out), L.DTYPES[out_dtype],
+             ptr(bias), ptr(residual), int(relu), int(num_sms), ptr(_sched_ws(in0.device)) if DYNAMIC_TILES else None, stream())
     if PROFILE is not None:
         e1.record()
         PROFILE.append((k, e0, e1, pairs, c0 + c1, c_out, rows if n_dev is not None else n_out))

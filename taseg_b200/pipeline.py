@@ -54,6 +54,8 @@ class GeometryDev:
             lv.table = ops.table_from_coords_dev(coords[l], counters[l], status)
             nbr3 = ops.build_kmap_dev(lv.table, coords[l], counters[l], kernel_offsets_np(3, lv.stride))
             lv.m3 = ops.kmap_sort_rows_dev(nbr3, counters[l])
+            if ops.SplitItems.wanted(caps[l], 27):      # few tiles per SM: K-split work items balance the launch
+                lv.m3 = lv.m3 + (ops.SplitItems(lv.m3[1], caps[l], 27, n_dev=counters[l]),)
             if l + 1 < n_levels:
                 nbr2 = ops.build_kmap_dev(lv.table, coords[l + 1], counters[l + 1], kernel_offsets_np(2, lv.stride))
                 lv.m2 = ops.kmap_sort_rows_dev(nbr2, counters[l + 1])

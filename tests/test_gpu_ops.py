@@ -455,6 +455,66 @@ def test_conv_tensor_core_column_split(ts, monkeypatch):
         assert torch.equal(outs[0], outs[1]), (c_in, c_out)
 
 
+def test_conv_tensor_core_k_split(ts):
+    """K-split work items (tsg_conv_split_items + tsg_conv_fwd_tc4): launches with about as many tiles as SMs sum heavy
+    tiles with two work items on two SMs.  The list must cover every (tile, offset) exactly once; the result must match the
+    oracle, must not depend on which item finishes first (run-to-run torch.equal) and must stay within fp32 summation-order
+    round-off of the unsplit launch; folded shortcut, residual, ReLU and fp32 output ride along."""
+    from taseg_b200 import ops
+    rng = np.random.default_rng(11)
+    c = np.unique(rng.integers(0, 28, (14000, 3)).astype(np.int32), axis=0)      # dense block: most rows see all 27 offsets
+    c = np.concatenate([c, np.zeros((len(c), 1), np.int32)], 1)
+    n = len(c)
+    assert 64 * 128 < n <= ops.SPLIT_MAX_TILES * 128
+    km = ops.build_kmap(ops.Table.from_coords(cu(c)), n, cu(c), T.get_kernel_offsets(3, 1))
+    nbr_s, mask_s, perm = km.sorted()
+    sp = km.split_items()
+    assert sp is not None
+    n_items = int(sp.n_items.item())
+    items = npy(sp.items[:n_items])
+    tiles = (n + 127) // 128
+    cover = np.zeros(tiles, np.int64)
+    for tile, m, part, slot in items:
+        assert 0 <= tile < tiles and (cover[tile] & (int(m) & 0x7ffffff)) == 0
+        cover[tile] |= int(m) & 0x7ffffff
+        parts = part >> 8
+        assert parts in (1, 2) and (part & 0xff) < parts and 0 <= slot < sp.max_slots
+        if parts == 1:
+            assert bin(int(m) & 0x7ffffff).count("1") <= ops.SPLIT_CAP or slot == 0
+    assert np.array_equal(cover, npy(mask_s).astype(np.int64) & 0x7ffffff), "work items do not cover the tile masks"
+    assert n_items > tiles, "no tile was split: the case does not exercise the partial-sum path"
+    nbmaps, nbsizes = npy(km.nbmaps), npy(km.nbsizes)
+    for c_in, c_out, od in [(256, 256, torch.bfloat16), (64, 128, torch.float32), (96, 96, torch.bfloat16)]:
+        x = torch.randn(n, c_in, device="cuda").bfloat16()
+        w = (torch.randn(27, c_in, c_out, device="cuda") * 0.05).bfloat16()
+        packed = ops.pack_weights(w.float(), c_in)
+        bias = torch.randn(c_out, device="cuda")
+        res = torch.randn(n, c_out, device="cuda").bfloat16() if od == torch.bfloat16 else None
+        ref = ops.conv_forward_tc(x, None, packed, 27, c_out, nbr_s, mask_s, n, bias=bias, residual=res, relu=True, perm=perm, out_dtype=od)
+        outs = [ops.conv_forward_tc(x, None, packed, 27, c_out, nbr_s, mask_s, n, bias=bias, residual=res, relu=True, perm=perm,
+                                    out_dtype=od, split=sp) for _ in range(4)]
+        torch.cuda.synchronize()
+        assert all(torch.equal(outs[0], o) for o in outs[1:]), "K-split result depends on the arrival order"
+        assert rel_err(npy(outs[0].float()), npy(ref.float())) < (1e-5 if od == torch.float32 else 4e-3)
+        want = T.conv_forward(npy(x.float()), npy(w.float()), nbmaps, nbsizes, (n, n), False) + npy(bias)
+        if res is not None:
+            want = want + npy(res.float())
+        assert rel_err(npy(outs[0].float()), np.maximum(want, 0)) < (1e-3 if od == torch.float32 else 1e-2)
+    assert int(sp.state.abs().sum().item()) == 0, "hand-off words were not re-armed"
+    # folded shortcut: summed by part 0 only
+    h = torch.randn(n, 128, device="cuda").bfloat16()
+    x0 = torch.randn(n, 64, device="cuda").bfloat16()
+    w = torch.randn(27, 128, 128, device="cuda") * 0.05
+    ws = torch.randn(1, 64, 128, device="cuda") * 0.1
+    packed, packed_s = ops.pack_weights(w, 128), ops.pack_weights(ws, 64)
+    ref = ops.conv_forward_tc(h, None, packed, 27, 128, nbr_s, mask_s, n, relu=True, perm=perm, shortcut=(x0, None, packed_s, nbr_s[13]),
+                              out_dtype=torch.float32)
+    got = ops.conv_forward_tc(h, None, packed, 27, 128, nbr_s, mask_s, n, relu=True, perm=perm, shortcut=(x0, None, packed_s, nbr_s[13]),
+                              out_dtype=torch.float32, split=sp)
+    torch.cuda.synchronize()
+    assert rel_err(npy(got), npy(ref)) < 1e-5
+
+
 def test_conv_tensor_core_vs_oracle(ts):
     """The tensor-core forward and the bf16 weight gradient directly against the numpy oracle (TS conv semantics,
     oracle/ts_oracle.py conv_forward / conv_backward) on bf16-representable inputs — no detour through our own fp32 kernel."""

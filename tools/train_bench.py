@@ -54,6 +54,11 @@ def main():
     for _ in range(args.warmup):
         loss = step()
     torch.cuda.synchronize()
+    if os.environ.get("PROFILE_STEP"):     # ncu --profile-from-start off: the launch list of exactly one training step
+        torch.cuda.cudart().cudaProfilerStart()
+        loss = step()
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
     if world > 1:
         dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
