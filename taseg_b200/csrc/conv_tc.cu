@@ -97,9 +97,19 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
 constexpr int TRACE_N = 96;
 __device__ long long g_trace[13][TRACE_N];  // 0 producer group 0 got empty, 1 it arrived on full, 2 MMA got full, 3 MMA committed,
                                            // 4 weights got empty, 5 MMA starts waiting for full, 6 copies issued, 7 next indices requested
+__device__ long long g_cta[160][4];         // trace build: per CTA {globaltimer at entry, at exit, stages issued by MMA warp 0, tiles}
 __device__ long long g_life[8];             // trace build: CTA 0's clock64 at kernel entry, after the prologue barrier, first plan
                                             // published, first plan seen by producers, last epilogue done, before exit
 #ifdef TSG_TC_TRACE  // profiling build (TSG_TC_TRACE=1 python -m taseg_b200.build): knock-outs and traces cost nothing otherwise
+#define TSG_CTA(j, v)                                                      \
+  do {                                                                     \
+    if ((p.dbg & 128) && blockIdx.x < 160) g_cta[blockIdx.x][j] = (v);     \
+  } while (0)
+__device__ __forceinline__ long long gtime() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 #define TSG_LIFE(i)                                                        \
   do {                                                                     \
     if ((p.dbg & 128) && blockIdx.x == 0) g_life[i] = clock64();           \
@@ -113,6 +123,7 @@ __device__ long long g_life[8];             // trace build: CTA 0's clock64 at k
 #define TSG_DBG(bit) 0
 #define TSG_TRACE(role, idx) do { } while (0)
 #define TSG_LIFE(i) do { } while (0)
+#define TSG_CTA(j, v) do { } while (0)
 #endif
 
 // ---- epilogue building blocks: NCOLS accumulator columns of 32 tile rows (one per lane) through the warp's staging buffer
@@ -248,14 +259,30 @@ __device__ __forceinline__ void epi_block(const TcParams &p, uint32_t taddr, boo
   __syncwarp();
 }
 
-template <int G>
+// PAIR (v18): a cluster of two CTAs on the two SMs of a TPC computes TWO tiles with tcgen05.mma.cta_group::2 (M = 256:
+// rows 0-127 = the leader CTA's tile, in the leader's TMEM; rows 128-255 = the peer's).  Every CTA gathers its own A
+// tile and stages HALF of the weight slice (output channels [rank N/2, rank N/2 + N/2)): the weight bytes an SM pulls
+// from the L2, writes to and reads from shared memory are halved — the bound of the c_out >= 128 layers (L2 -> SM
+// traffic is two thirds weights at c_out = 256) — and the stage shrinks, so more stages are in flight.  Protocol:
+//   * both CTAs plan the same unit (tiles 2u, 2u + 1; static round-robin over clusters, heaviest first) and derive the
+//     same stage list = union of the two tiles' needs; a tile that does not need a stage presents zero rows;
+//   * full barriers stay CTA-local (cp.async / bulk completions signal only the own CTA); the peer's first MMA warp is a
+//     RELAY: wait local full, proxy fence, mbarrier.arrive on the leader's pfull[slot] through the cluster window;
+//   * only the leader issues MMAs (two alternating issuers as before) after full + pfull; tcgen05.commit ... multicast
+//     arrives on empty[slot] / tfull[buf] of BOTH CTAs;
+//   * the peer's epilogue threads release the accumulator buffer on the LEADER's tempty (remote arrive).
+// THR: the planner's look-ahead throttle (heaviest-first list scheduling for launches with few tiles per CTA) is compiled in.
+template <int G, bool PAIR, bool THR>
 __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p) {
+  static_assert(!PAIR || G == 1, "a pair CTA holds one tile");
+  constexpr int GP = PAIR ? 2 : G;   // tiles per plan (unit of scheduling)
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[2 * V8_MAX_STAGES + 4 + 2 * V8_PLAN_SLOTS + 2];
+  __shared__ __align__(8) uint64_t bars[3 * V8_MAX_STAGES + 4 + 2 * V8_PLAN_SLOTS + 2];
   __shared__ Plan plans[V8_PLAN_SLOTS];
   __shared__ uint32_t tmem_base_slot;
   __shared__ __align__(16) float bias_s[256];
   __shared__ uint16_t lut[256];  // per (phase, slice j, 16-byte chunk c of the slice): which offset / source tensor / source chunk
+  __shared__ int issued_s;       // global stage number the first MMA issuer has reached (the planner's look-ahead throttle)
 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -263,7 +290,10 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
   const int P0 = p.ph[0].pk, Q0 = p.ph[0].kq, P1 = p.ph[1].pk, Q1 = p.ph[1].kq;  // offsets / slices per virtual offset
   const unsigned long long need0 = p.ph[0].slice_need, need1 = p.ph[1].slice_need;
   const int NS = p.ns, n_eff = p.n_eff;
-  const uint32_t b_bytes = (uint32_t)n_eff * 128u;                   // weight slice of one work item; multiple of 2048
+  uint32_t rank = 0;                                                 // CTA rank in the pair
+  if (PAIR) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  const int my_g = PAIR ? (int)rank : 0;                             // this CTA's tile among the plan's tiles (PAIR)
+  const uint32_t b_bytes = (uint32_t)n_eff * (PAIR ? 64u : 128u);    // weight rows this CTA stages; multiple of 1024
   const uint32_t b_full = (uint32_t)p.c_out * 128u;                  // ... of all output channels (block pitch of packed_w)
   const uint32_t stage_bytes = b_bytes + (uint32_t)G * TC_A_BYTES;   // [W slice][A tile 0]..[A tile G-1]
   const uint32_t nst = (uint32_t)p.na;                               // stages
@@ -273,21 +303,24 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
   const unsigned kmask = p.ph[0].K >= 32 ? 0xffffffffu : ((1u << p.ph[0].K) - 1u);
   const int KV0 = (p.ph[0].K + P0 - 1) / P0, KV1 = NPH > 1 ? (p.ph[1].K + P1 - 1) / P1 : 0;  // virtual offsets
   const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[V8_MAX_STAGES]);
-  const uint32_t tfull0 = smem_u32(&bars[2 * V8_MAX_STAGES]), tempty0 = tfull0 + 16;
+  const uint32_t pfull0 = smem_u32(&bars[2 * V8_MAX_STAGES]);       // PAIR, leader: "the peer's half of the stage is full"
+  const uint32_t tfull0 = smem_u32(&bars[3 * V8_MAX_STAGES]), tempty0 = tfull0 + 16;
   const uint32_t sfull0 = tfull0 + 32, sempty0 = sfull0 + 8 * V8_PLAN_SLOTS;
   const uint32_t obar0 = sempty0 + 8 * V8_PLAN_SLOTS;                // issue-order hand-off between the two MMA issuers (G == 1)
 
   if (threadIdx.x == 0) TSG_LIFE(0);
+  if (threadIdx.x == 0) TSG_CTA(0, gtime());
   // programmatic dependent launch: the next kernel of the stream may start its prologue while this grid drains
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (threadIdx.x == 0) {
     for (uint32_t s = 0; s < nst; ++s) {
       mbar_init(full0 + 8 * s, V8_GROUP_WARPS * 32 + 1);  // every thread of the owning producer group (async, when its copies land) + the weight thread
       mbar_init(empty0 + 8 * s, 1);                  // one tcgen05.commit, from the issuer that owns the stage
+      mbar_init(pfull0 + 8 * s, 1);                  // the peer's relay thread
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull0 + 8 * b, 2);                  // both MMA warps commit once per super tile
-      mbar_init(tempty0 + 8 * b, V8_EPI_WARPS * 32);
+      mbar_init(tempty0 + 8 * b, V8_EPI_WARPS * 32 * (PAIR ? 2 : 1));   // PAIR: the epilogue threads of both CTAs
       mbar_init(obar0 + 8 * b, 1);
     }
     for (int s = 0; s < V8_PLAN_SLOTS; ++s) {
@@ -300,7 +333,8 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
   asm volatile("griddepcontrol.wait;" ::: "memory");
   const long long n_rows = dev_count(p.n_out_dev, p.n_out);   // host value, or the device counter of the sync-free pipeline
   const int num_tiles = (int)((n_rows + TC_BM - 1) / TC_BM);
-  const int num_super = (num_tiles + G - 1) / G;
+  const int num_super = (num_tiles + GP - 1) / GP;
+  if (threadIdx.x == 0) issued_s = 0;
   if (threadIdx.x < 256) bias_s[threadIdx.x] = (p.bias && (int)threadIdx.x < p.c_out) ? __ldg(p.bias + threadIdx.x) : 0.f;
   if (threadIdx.x >= 256 && threadIdx.x < 256 + 256) {
     const int t = threadIdx.x - 256, phi = t >> 7, j = (t >> 3) & 15, c = t & 7;
@@ -313,14 +347,25 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
     }
     lut[t] = (uint16_t)e;
   }
-  if (warp == V8_MMA_WARP) {  // TMEM allocation by the MMA warp
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
-                 "r"(p.tmem_cols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  if (warp == V8_MMA_WARP) {  // TMEM allocation by the MMA warp (PAIR: the same warp of both CTAs, same shared-memory slot)
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                   "r"(p.tmem_cols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                   "r"(p.tmem_cols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) {   // both CTAs' barriers are initialised before anything arrives on them through the cluster window
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  }
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
   if (threadIdx.x == 0) TSG_LIFE(1);
@@ -372,16 +417,17 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
     for (;; ++it) {
       const volatile Plan *pl = plan_wait();
       const int st = pl->tile;
-      const unsigned mask_g = pl->mask[g];
+      const unsigned mask_g = PAIR ? (pl->mask[0] | pl->mask[1]) : pl->mask[g];   // PAIR: one MMA writes both tiles' accumulators
       const int cbase = (pl->n >> 16) * n_eff;              // first output channel of this work item
       const int split = pl->split, pslot = pl->slot;
       plan_release_warp();
       if (st < 0) break;
       const uint32_t buf = it & 1, ph = (it >> 1) & 1;
-      const long long r = (long long)(st * G + g) * TC_BM + quad * 32 + lane;  // destination row: fetched before the long wait
+      const int my_tile = st * GP + (PAIR ? my_g : g);
+      const long long r = (long long)my_tile * TC_BM + quad * 32 + lane;  // destination row: fetched before the long wait
       const int rows_g = r < n_rows ? (p.perm ? __ldg(p.perm + r) : (int)r) : -1;
-      const bool live = st * G + g < num_tiles && cfirst < n_eff;
-      const bool is_split = G == 1 && (split >> 8) > 1;                // one of the two work items of a K-split tile
+      const bool live = my_tile < num_tiles && cfirst < n_eff;
+      const bool is_split = G == 1 && !PAIR && (split >> 8) > 1;       // one of the two work items of a K-split tile
       if (res_staged && live && !is_split) prefetch_res(rows_g, cbase + cfirst, blk_cols(cfirst));  // lands while the main loop still runs
       mbar_wait_sleep(tfull0 + 8 * buf, ph);
       tc_fence_after();
@@ -437,7 +483,8 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
         }
       }
       tc_fence_before();
-      mbar_arrive(tempty0 + 8 * buf);
+      if (PAIR && rank) mbar_arrive_remote(tempty0 + 8 * buf, 0);   // the leader's MMA warps wait for both CTAs' epilogues
+      else mbar_arrive(tempty0 + 8 * buf);
       if (threadIdx.x == 0) TSG_TRACE(11, it);
       if (threadIdx.x == 0) TSG_LIFE(4);
     }
@@ -450,8 +497,31 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
     // executes tcgen05.fence::before_thread_sync and arrives on an mbarrier, the issuer of s + 1 waits for it and
     // executes tcgen05.fence::after_thread_sync — accumulation order, and the result, are those of a single issuer.
     const int mw = warp - V8_MMA_WARP;
-    if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n_eff >> 3) << 17) | ((TC_BM >> 4) << 24);
+    if (PAIR && rank != 0) {
+      // peer CTA of a pair: no MMA issue.  Warp 8 relays "my half of stage s is full" to the leader, warp 9 only keeps
+      // the plan ring moving.
+      if (lane == 0) {
+        Ring r;
+        for (;;) {
+          const volatile Plan *pl = plan_wait();
+          if (pl->tile < 0) {
+            plan_release_lane();
+            break;
+          }
+          const int n = pl->n & 0xffff;
+          if (mw == 0) {
+            for (int i = 0; i < n; ++i) {
+              mbar_wait(full0 + 8 * r.slot, r.phase);   // this CTA's rows (cp.async) and weight half (bulk copy) have landed
+              fence_async_proxy();                      // ... ordered before the tensor cores' (async proxy) reads
+              mbar_arrive_remote(pfull0 + 8 * r.slot, 0);
+              r.advance(nst);
+            }
+          }
+          plan_release_lane();
+        }
+      }
+    } else if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n_eff >> 3) << 17) | (((PAIR ? 2 * TC_BM : TC_BM) >> 4) << 24);
       const uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);   // SBO 1024 B, version 1, SWIZZLE_128B
       const uint32_t desc_lo_stage = stage_bytes >> 4;
       const uint32_t b_lo0 = ((smem_base & 0x3FFFFu) >> 4) | (1u << 16);          // LBO field = 1 (ignored for swizzled K-major)
@@ -469,7 +539,7 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
         }
         const int n = pl->n & 0xffff;
         const uint32_t buf = it & 1, ph = (it >> 1) & 1;
-        mbar_wait(tempty0 + 8 * buf, ph ^ 1);
+        mbar_wait<PAIR>(tempty0 + 8 * buf, ph ^ 1);
         tc_fence_after();
         if (tracer) TSG_TRACE(8, it);
         const uint32_t d_tmem = tmem_base + buf * G * (uint32_t)n_eff;
@@ -486,6 +556,7 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
           if (tracer) TSG_TRACE(5, n_mma);
           TSG_STATE(pl->tile, n, i, n_mma);
           mbar_wait(full0 + 8 * slot, phase);  // the gathered rows (cp.async, generic proxy) and the weight slice have landed
+          if (PAIR) mbar_wait<true>(pfull0 + 8 * slot, phase);   // ... and so has the peer's half (fenced and relayed by the peer)
           fence_async_proxy();                 // ... order them before this thread's tensor-core (async proxy) reads
           if (mine | mw) {                     // every stage but global stage 0 follows the other issuer's previous stage
             const uint32_t k = mw ? mine : mine - 1;
@@ -496,10 +567,18 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
           const uint32_t b_lo = b_lo0 + slot * desc_lo_stage;
 #pragma unroll
           for (int g = 0; g < G; ++g) {
-            if (!((d >> (9 + g)) & 1u) || TSG_DBG(4)) continue;
             // every slice is a full 64-channel block: four K = 16 MMAs per sub-tile
             const uint32_t a_lo = a_lo0 + slot * desc_lo_stage + g * (TC_A_BYTES >> 4);
             const uint32_t dt = d_tmem + g * (uint32_t)n_eff;
+            if (PAIR) {   // every stage of the list multiplies the pair (a tile that does not need it holds zero rows)
+              if (TSG_DBG(4)) continue;
+              umma_bf16_pair(dt, make_desc(a_lo, desc_hi), make_desc(b_lo, desc_hi), idesc, i == 0 ? 0u : 1u);
+              umma_bf16_pair(dt, make_desc(a_lo + 2, desc_hi), make_desc(b_lo + 2, desc_hi), idesc, 1u);
+              umma_bf16_pair(dt, make_desc(a_lo + 4, desc_hi), make_desc(b_lo + 4, desc_hi), idesc, 1u);
+              umma_bf16_pair(dt, make_desc(a_lo + 6, desc_hi), make_desc(b_lo + 6, desc_hi), idesc, 1u);
+              continue;
+            }
+            if (!((d >> (9 + g)) & 1u) || TSG_DBG(4)) continue;
             umma_bf16(dt, make_desc(a_lo, desc_hi), make_desc(b_lo, desc_hi), idesc, ((d >> (11 + g)) & 1u) ^ 1u);
             umma_bf16(dt, make_desc(a_lo + 2, desc_hi), make_desc(b_lo + 2, desc_hi), idesc, 1u);
             umma_bf16(dt, make_desc(a_lo + 4, desc_hi), make_desc(b_lo + 4, desc_hi), idesc, 1u);
@@ -507,17 +586,20 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
           }
           tc_fence_before();
           mbar_arrive(obar0 + 8 * mw);         // the other issuer may issue the next stage
-          umma_commit(empty0 + 8 * slot);      // "stage consumed" (arrives once the MMAs have read it)
+          if (PAIR) umma_commit_pair(empty0 + 8 * slot);   // "stage consumed", in both CTAs
+          else umma_commit(empty0 + 8 * slot);             // "stage consumed" (arrives once the MMAs have read it)
           if (tracer) TSG_TRACE(3, n_mma);
           ++n_mma;
           ++mine;
+          if (THR && mw == 0) *reinterpret_cast<volatile int *>(&issued_s) = 2 * (int)mine;   // progress for the planner's throttle
           slot += 2;
           if (slot >= nst) {
             slot -= nst;
             phase ^= 1;
           }
         }
-        umma_commit(tfull0 + 8 * buf);  // this issuer's share of the accumulators is complete (immediately if it had no stage)
+        if (PAIR) umma_commit_pair(tfull0 + 8 * buf);
+        else umma_commit(tfull0 + 8 * buf);  // this issuer's share of the accumulators is complete (immediately if it had no stage)
         if (tracer) TSG_TRACE(9, it);
 #ifdef TSG_TC_TRACE
         if (tracer && (p.dbg & 128) && blockIdx.x == 0 && it < TRACE_N) g_trace[12][it] = n;
@@ -530,6 +612,10 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
           phase0 ^= 1;
         }
         plan_release_lane();
+      }
+      if (tracer) {
+        TSG_CTA(2, (long long)n_mma);
+        TSG_CTA(3, (long long)it);
       }
     }
     __syncwarp();
@@ -545,7 +631,7 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
           break;
         }
         const int n = pl->n & 0xffff;
-        const size_t hoff = (size_t)(pl->n >> 16) * b_bytes;   // this work item's rows of every [c_out][64] block
+        const size_t hoff = (size_t)((pl->n >> 16) + my_g) * b_bytes;   // this work item's (PAIR: this CTA's) rows of every [c_out][64] block
         for (int i = 0; i < n; ++i) {
           const unsigned d = pl->stage[i];
           const unsigned phi = (d >> 13) & 1u;
@@ -579,11 +665,39 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
     // work-item list (K split, G == 1): the list replaces the tile enumeration; its length is a device value
     const bool use_items = G == 1 && p.items != nullptr;
     const int n_work = use_items ? __ldg(p.n_items) : num_super * NS;
+    // Look-ahead throttle (v18).  The plan ring lets the planner run up to four tiles ahead — and at kernel start it
+    // did: every CTA drew four tickets in its first microsecond, so a launch with 2-3 tiles per SM was assigned
+    // statically, in launch order, and the CTAs holding the heaviest tiles ended up with the most tiles (per-CTA
+    // timeline, profiles/r02: stride-8 layers finished between 21 and 50 us).  A ticket is now drawn only when fewer
+    // than LOOKAHEAD planned stages are left in front of the MMA issuers: long tiles take their next ticket shortly before
+    // they finish (true heaviest-first list scheduling), short tiles still keep several plans in flight.
+    // With many tiles per CTA the imbalance averages out and a stalled planner only costs (measured: +7 % on the
+    // stride-1 layers), so the throttle is applied to launches with at most eight work items per CTA.
+    const int LOOKAHEAD = 3 * (int)nst + 4;   // progress is published by the MMA issuer, up to nst stages behind the producers
+    // A template switch, chosen by the host from the tile count: the two-tile kernel's hot loops are sensitive to every
+    // KB of code (75 KB of SASS against the instruction cache) — the throttle, compiled in but never taken, cost the
+    // stride-1 layers 6 %.
+    const bool throttle = THR && !PAIR && p.sched;
+    int planned = 0;
     for (;;) {
       mbar_wait(sempty0 + 8 * w.slot, w.phase ^ 1);
+      if (throttle) {
+        long long t0 = 0;
+        for (uint32_t spin = 1; planned - *reinterpret_cast<volatile int *>(&issued_s) >= LOOKAHEAD; ++spin) {
+          __nanosleep(64);
+          if ((spin & 0x3fffu) == 0) {   // same watchdog policy as mbar_wait
+            const long long now = clock64();
+            if (!t0) t0 = now;
+            else if (now - t0 > (1ll << 33)) __trap();
+          }
+        }
+      }
       int t = 0;
       if (lane == 0) {
-        if (p.sched) {
+        if (PAIR) {          // both CTAs of a pair must plan the same unit: static round-robin over the clusters
+          t = static_next >> 1;
+          static_next += gridDim.x;
+        } else if (p.sched) {
           // the first ticket of a CTA is its block index (no round trip to the L2 before the first plan); the shared
           // counter hands out the tickets from gridDim.x on
           t = first_ticket ? (int)blockIdx.x : (int)gridDim.x + atomicAdd(p.sched, 1);
@@ -609,15 +723,15 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
       } else {
         st = t < n_work ? num_super - 1 - t / NS : -1;  // heavy (high-key) tiles first; NS column blocks each
         half = t < n_work ? t % NS : 0;
-        if (st >= 0 && lane < G) {
-          const int tile = st * G + lane;
+        if (st >= 0 && lane < GP) {
+          const int tile = st * GP + lane;
           lv = tile < num_tiles ? 1u : 0u;
           mm = lv ? ((p.tile_mask ? __ldg(p.tile_mask + tile) : 0xffffffffu) & kmask) : 0u;
         }
       }
-      const unsigned m0 = __shfl_sync(0xffffffffu, mm, 0), m1 = G > 1 ? __shfl_sync(0xffffffffu, mm, 1) : 0u;
+      const unsigned m0 = __shfl_sync(0xffffffffu, mm, 0), m1 = GP > 1 ? __shfl_sync(0xffffffffu, mm, 1) : 0u;
       // a folded shortcut (phase 1) is summed by part 0 of a split tile only
-      const unsigned l0 = (split & 0xff) ? 0u : __shfl_sync(0xffffffffu, lv, 0), l1 = G > 1 ? __shfl_sync(0xffffffffu, lv, 1) : 0u;
+      const unsigned l0 = (split & 0xff) ? 0u : __shfl_sync(0xffffffffu, lv, 0), l1 = GP > 1 ? __shfl_sync(0xffffffffu, lv, 1) : 0u;
       Plan *pl = &plans[w.slot];
       // per phase: the slices of virtual offset `lane` that some tile of the super tile needs, and their positions in
       // the stage list (phase 0 first); f0 / f1 = first stage that multiplies sub-tile 0 / 1 (its first MMA overwrites
@@ -674,6 +788,7 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
         }
       }
       const int n_total = base;
+      planned += n_total;
       TSG_STATE(st, n_total, t, (int)w.slot);
       if (lane == 0) {
         pl->tile = st;
@@ -690,7 +805,7 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
       w.advance(V8_PLAN_SLOTS);
       if (st < 0) break;
     }
-    if (lane == 0 && p.sched) {  // every CTA draws exactly one terminal ticket: the last one re-arms the counters for the next launch
+    if (lane == 0 && p.sched && !PAIR) {  // every CTA draws exactly one terminal ticket: the last one re-arms the counters for the next launch
       __threadfence();
       if (atomicAdd(p.sched + 1, 1) == (int)gridDim.x - 1) {
         p.sched[0] = 0;
@@ -757,7 +872,11 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
         n = pl->n & 0xffff;
         masks[0] = pl->mask[0];
         masks[1] = pl->mask[1];
-        lives = (st * G < num_tiles ? 1u : 0u) | ((G > 1 && st * G + 1 < num_tiles) ? 2u : 0u);
+        lives = (st * GP < num_tiles ? 1u : 0u) | ((GP > 1 && st * GP + 1 < num_tiles) ? 2u : 0u);
+        if (PAIR) {   // this CTA's tile only
+          masks[0] = masks[my_g];
+          lives = (lives >> my_g) & 1u;
+        }
         i = 0;
         TSG_STATE(st, n, gs, -1);
       }
@@ -782,7 +901,7 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
       auto locate = [&](View &v) {
         const unsigned phi = (d_cur >> 13) & 1u;
         const int kv = d_cur & 31u, j = (d_cur >> 5) & 15u;
-        v.act = (d_cur >> 9) & 3u;
+        v.act = PAIR ? 1u : (d_cur >> 9) & 3u;   // PAIR: a tile that does not need the stage still presents (zero) rows
         const uint32_t e = lut[phi * 128 + j * 8 + chunk];
         const int k = kv * (phi ? P1 : P0) + (int)((e >> 2) & 3u);
         const bool second = (e >> 4) & 1u;
@@ -790,7 +909,7 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
         v.src = reinterpret_cast<const char *>(base) + (e >> 5) * 16u;
         v.rb = (uint32_t)(phi ? (second ? p.ph[1].c1 : p.ph[1].c0) : (second ? p.ph[0].c1 : p.ph[0].c0)) * 2u;
         v.ioff = (e & 3u) * (uint32_t)(G * 128) + (uint32_t)rsl * 32u;
-        v.m0 = (long long)st * G * TC_BM;
+        v.m0 = ((long long)st * GP + my_g) * TC_BM;
         v.kbits = phi ? (k == 0 ? lives : 0u) : (((masks[0] >> k) & 1u) | (((masks[1] >> k) & 1u) << 1));
         v.indexed = (phi ? p.ph[1].nbr : p.ph[0].nbr) != nullptr;
       };
@@ -809,7 +928,7 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
           const bool present = phi ? (k == 0 && ((lives >> g) & 1u)) : (((g ? masks[1] : masks[0]) >> k) & 1u);
           if (present)
             cp_async16(buf + (uint32_t)((ks * G + g) * 128 + piece * 16),
-                       nbr + (long long)k * nbr_stride + (long long)st * G * TC_BM + g * TC_BM + wg * 32 + piece * 4, 16u);
+                       nbr + (long long)k * nbr_stride + ((long long)st * GP + my_g) * TC_BM + g * TC_BM + wg * 32 + piece * 4, 16u);
         }
       };
       // Nothing in this loop waits for gathered rows to land: a slot stays occupied only from the first copy to the
@@ -906,8 +1025,14 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
   tc_fence_before();
   __syncthreads();
   if (threadIdx.x == 0) TSG_LIFE(5);
+  if (threadIdx.x == 0) TSG_CTA(1, gtime());
+  if (PAIR) {   // neither CTA leaves (or frees TMEM) while the other may still read its shared memory or arrive on its barriers
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  }
   if (warp == V8_MMA_WARP) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
   }
 }
 
@@ -1052,6 +1177,13 @@ int tsg_debug_conv_trace(long long *host) {
   return TSG_OK;
 }
 
+/* ... per-CTA {entry ns, exit ns, stages of MMA warp 0, tiles} of the same launch (160 x 4 int64) */
+int tsg_debug_conv_ctas(long long *host) {
+  TSG_CUDA(cudaDeviceSynchronize());
+  TSG_CUDA(cudaMemcpyFromSymbol(host, g_cta, sizeof(long long) * 160 * 4));
+  return TSG_OK;
+}
+
 /* ... and CTA 0's life-cycle stamps of the same launch (8 int64) */
 int tsg_debug_conv_life(long long *host) {
   TSG_CUDA(cudaDeviceSynchronize());
@@ -1179,6 +1311,17 @@ int tsg_conv_fwd_tc4(const void *in0, int c0, const void *in1, int c1, int64_t n
   int G = p.n_eff <= 128 ? 2 : 1;  // (G = 4 spills the producers' index registers at 768 threads per CTA)
   while (G > 1 && (num_tiles + G - 1) / G * ns < 2LL * sms) G >>= 1;
   if (items) G = 1;   // work items address single tiles
+  // CTA pairs (cta_group::2, M = 256 over two SMs, half a weight slice per CTA): TSG_TC_PAIR = 0 never (default: measured no faster, see profiles/README.md), 1 the
+  // launches that would otherwise run one tile per CTA with c_out >= 128 (L2 -> SM weight traffic bound), 2 every launch
+  // with c_out >= 64.  Not combined with work-item lists or the column split.
+  static const int pair_mode = getenv("TSG_TC_PAIR") ? atoi(getenv("TSG_TC_PAIR")) : 0;
+  const bool pair = ns == 1 && num_tiles >= 2 && sms >= 2 &&
+                    ((pair_mode == 1 && G == 1 && c_out >= 128) || (pair_mode >= 2 && c_out >= 64));
+  if (pair) {   // takes precedence over a work-item list (the K split bought 4 % where pairs buy far more)
+    G = 1;
+    items = nullptr;
+    p.items = nullptr;
+  }
 #ifdef TSG_TC_TRACE
   if (getenv("TSG_TC_G1")) G = 1;
 #endif
@@ -1187,7 +1330,7 @@ int tsg_conv_fwd_tc4(const void *in0, int c0, const void *in1, int c1, int64_t n
   p.tmem_cols = cols;
   p.ksmax = ksmax;
   // dynamic shared memory: 1 KB alignment slack + stages + epilogue staging + the producers' index buffers
-  const size_t b_bytes = (size_t)p.n_eff * 128, stage_bytes = b_bytes + (size_t)G * TC_A_BYTES;
+  const size_t b_bytes = (size_t)p.n_eff * (pair ? 64 : 128), stage_bytes = b_bytes + (size_t)G * TC_A_BYTES;
   const size_t fixed = 1024 + (size_t)V8_EPI_WARPS * V8_STG_BYTES + (size_t)V8_PROD_WARPS * 2 * ksmax * G * 128;
   int stages = (int)((V8_DYN_SMEM - fixed) / stage_bytes);
   if (stages > V8_MAX_STAGES) stages = V8_MAX_STAGES;
@@ -1202,11 +1345,14 @@ int tsg_conv_fwd_tc4(const void *in0, int c0, const void *in1, int c1, int64_t n
   const size_t smem = (size_t)stages * stage_bytes + fixed;
   static bool configured[64] = {false};   // the >48 KB shared-memory opt-in is per device
   if (dev < 0 || dev >= 64 || !configured[dev]) {
-    TSG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, V8_DYN_SMEM));
-    TSG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, V8_DYN_SMEM));
+    TSG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<1, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, V8_DYN_SMEM));
+    TSG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, V8_DYN_SMEM));
+    TSG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<2, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, V8_DYN_SMEM));
+    TSG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, V8_DYN_SMEM));
+    TSG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<1, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, V8_DYN_SMEM));
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
-  const long long work = items ? num_tiles + max_slots : (num_tiles + G - 1) / G * ns;
+  const long long work = items ? num_tiles + max_slots : pair ? (num_tiles + 1) / 2 : (num_tiles + G - 1) / G * ns;
   // programmatic dependent launch (TSG_TC_PDL=1, off by default): this grid's CTAs may be scheduled while the previous
   // kernel of the stream drains; the kernel executes griddepcontrol.wait before it reads anything.  Measured: +1 % with one
   // batch in flight, -8 % with two (early CTAs of one stream's next convolution hold the SMs the other stream's small
@@ -1214,17 +1360,34 @@ int tsg_conv_fwd_tc4(const void *in0, int c0, const void *in1, int c1, int64_t n
   static const bool pdl = getenv("TSG_TC_PDL") && atoi(getenv("TSG_TC_PDL")) == 1;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3((unsigned)(work < sms ? work : sms));
+  cfg.gridDim = pair ? dim3(2u * (unsigned)(work < sms / 2 ? work : sms / 2)) : dim3((unsigned)(work < sms ? work : sms));
   cfg.blockDim = dim3(V8_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = (cudaStream_t)stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (pair) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = pdl ? 1 : 0;
-  if (G == 2) TSG_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<2>, p));
-  else TSG_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<1>, p));
+  cfg.numAttrs = na;
+  // look-ahead throttle (see the planner): launches with at most `thr_max` work items per CTA
+  static const int thr_max = getenv("TSG_TC_THROTTLE") ? atoi(getenv("TSG_TC_THROTTLE")) : 8;
+  const bool thr = sched && work <= (long long)thr_max * cfg.gridDim.x;
+  if (pair) TSG_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<1, true, false>, p));
+  else if (G == 2 && thr) TSG_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<2, false, true>, p));
+  else if (G == 2) TSG_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<2, false, false>, p));
+  else if (thr) TSG_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<1, false, true>, p));
+  else TSG_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<1, false, false>, p));
   return check_launch("tsg_conv_fwd_tc");
 }
 

@@ -34,17 +34,31 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // Spin on an mbarrier phase.  try_wait suspends the thread in hardware for a bounded time, so the loop is not hot;
 // the watchdog reads the cheap SM cycle counter (never %globaltimer, whose read costs ~1 us) once per 4096 failed
 // polls and traps after ~2^33 cycles (~4 s): a protocol bug must fail loudly, never hang the GPU.
+// CLUSTER marks the waits whose arrivals come from the other CTA of a pair.  They use the same CTA-scope acquire as
+// the local ones (as CUTLASS's ClusterBarrier does): what they order is shared memory that has physically landed and TMEM
+// reads bracketed by tcgen05 fences; the cluster-scope forms compile to MEMBAR.ALL.GPU / CCTL.IVALL per use, which made
+// the first pair kernel 2.2x slower than the single-CTA one.
+template <bool CLUSTER = false>
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
   long long t0 = 0;
   for (uint32_t spin = 1;; ++spin) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
+    if (CLUSTER)
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(done)
+          : "r"(bar), "r"(parity)
+          : "memory");
+    else
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(done)
+          : "r"(bar), "r"(parity)
+          : "memory");
     if (done) break;
     if ((spin & 0xfffu) == 0) {
       const long long now = clock64();
@@ -94,6 +108,32 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
+}
+// ---- CTA-pair (cta_group::2) helpers
+// arrive on the mbarrier at the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar),
+      "r"(cta)
+      : "memory");
+}
+// "all MMAs issued so far by this thread have completed" -> the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
+// M = 256 over the pair: descriptors address the same shared-memory offsets in both CTAs; each CTA holds N/2 rows of B
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
