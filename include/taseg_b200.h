@@ -264,6 +264,21 @@ int tsg_conv_wgrad(const float *in, int64_t n_in, int c_in, const float *grad_ou
  * kernel, so only the P = sum_k nbsizes[k] real pairs are multiplied (warp-level tensor-core MMAs). */
 int tsg_conv_wgrad_bf16(const void *in, int64_t n_in, int c_in, const void *grad_out, int64_t n_out, int c_out,
                         const int32_t *nbr, int k, float *grad_w, tsg_stream_t stream);
+/* Compact pair lists of a neighbour table for the weight gradient: pairs (capacity K * n_rows, int32 x 2) receives, offset
+ * by offset, the {in row = nbr[k, o], out row = o} of every hit in ascending o — the order of the reference's nbmaps
+ * (TS/nn/functional/conv.py:169-172) in 32-bit — and start (K + 1 int32, device) the first pair of every offset
+ * (start[K] = P).  Built once per kernel map, shared by every layer that uses the map.  Nothing returns to the host. */
+size_t tsg_kmap_pair_list_ws_bytes(int k, int64_t n_rows);
+int tsg_kmap_pair_list(const int32_t *nbr, int k, int64_t n_rows, int64_t nbr_stride, int32_t *pairs, int32_t *start, void *ws,
+                       size_t ws_bytes, tsg_stream_t stream);
+/* ... and on the 5th-generation tensor cores (tcgen05.mma, fp32 accumulators in TMEM): the gathered rows — 64 channels
+ * = 128 bytes per pair, eight pairs per swizzle atom — are MN-major operand tiles as they land in shared memory, so
+ * grad_w[k] = X_k^T gY_k needs no transposition; the pair list is the GEMM's K dimension (taseg_b200/csrc/conv_wgrad_tc.cu).
+ * Replaces the per-offset gather + torch::mm_out of TS/backend/convolution/convolution_cuda.cu:167-278 under autocast.
+ * c_in, c_out multiples of 8, c_out <= 256.  pairs / start: tsg_kmap_pair_list of the table whose rows are the forward's
+ * outputs; pair_cap = capacity of `pairs` (sizes the grid: the true count stays on the device). */
+int tsg_conv_wgrad_tc(const void *in, int64_t n_in, int c_in, const void *grad_out, int64_t n_out, int c_out,
+                      const int32_t *pairs, const int32_t *start, int64_t pair_cap, int k, float *grad_w, tsg_stream_t stream);
 
 /* tcgen05/TMEM path (bf16 operands, fp32 accumulate in tensor memory).
  * Weights are packed once per layer into the shared-memory image the MMA consumes (128B-swizzled K-major

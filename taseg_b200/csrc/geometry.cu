@@ -166,6 +166,51 @@ __global__ void __launch_bounds__(256) kmap_pairs_kernel(const int *__restrict__
   }
 }
 
+// ---- compact per-offset pair lists for the weight gradient (conv_wgrad_tc.cu): for offset k the rows o with
+// nbr[k, o] >= 0, ascending, as int2 {in row, out row}, all offsets back to back (k-major).  Three launches: per
+// (k, 1024-row block) counts, their exclusive scan, the ordered write.  start[k] = first pair of offset k, start[K] = total.
+__global__ void __launch_bounds__(256) pair_count_kernel(const int *__restrict__ nbr, int K, int64_t n_rows, int64_t stride,
+                                                         int *__restrict__ blockcnt, int64_t nblk) {
+  __shared__ int s_cnt[32];
+  if (threadIdx.x < 32) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const int64_t base = (int64_t)blockIdx.x * KM_ROWS;
+  for (int k = 0; k < K; ++k) {
+    int hits = 0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int64_t o = base + r * 256 + threadIdx.x;
+      const int in = o < n_rows ? __ldg(nbr + (int64_t)k * stride + o) : -1;
+      hits += __popc(__ballot_sync(0xffffffffu, in >= 0));
+    }
+    if ((threadIdx.x & 31) == 0 && hits) atomicAdd(&s_cnt[k], hits);
+  }
+  __syncthreads();
+  if (threadIdx.x < K) blockcnt[(int64_t)threadIdx.x * nblk + blockIdx.x] = s_cnt[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(256) pair_write_kernel(const int *__restrict__ nbr, int K, int64_t n_rows, int64_t stride,
+                                                         const int *__restrict__ blockoff, int64_t nblk, int2 *__restrict__ pairs,
+                                                         int *__restrict__ start, const int *__restrict__ last_cnt) {
+  const int64_t base = (int64_t)blockIdx.x * KM_ROWS;
+  for (int k = 0; k < K; ++k) {
+    int64_t off = blockoff[(int64_t)k * nblk + blockIdx.x];
+    if (blockIdx.x == 0 && threadIdx.x == 0) start[k] = (int)off;
+    for (int r = 0; r < 4; ++r) {  // rows r*256 .. r*256+255 in order
+      const int64_t o = base + r * 256 + threadIdx.x;
+      const int in = o < n_rows ? __ldg(nbr + (int64_t)k * stride + o) : -1;
+      int tot;
+      const int pos = block_exclusive_scan<256>(in >= 0 ? 1 : 0, &tot);
+      if (in >= 0) pairs[off + pos] = make_int2(in, (int)o);
+      off += tot;
+    }
+    // the last block of the last offset closes the list: its exclusive offset + its own count (saved before the scan)
+    if (k == K - 1 && blockIdx.x == nblk - 1 && threadIdx.x == 0) start[K] = blockoff[(int64_t)k * nblk + blockIdx.x] + *last_cnt;
+  }
+}
+
+__global__ void save_last_kernel(const int *__restrict__ blockcnt, int64_t n, int *__restrict__ last_cnt) { *last_cnt = blockcnt[n - 1]; }
+
 __global__ void fill_i32_kernel(int *p, int64_t n, int v) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
 }
@@ -326,6 +371,27 @@ int tsg_kmap_build_dev(const void *table, int64_t slots, const int32_t *out_coor
     return TSG_ERR_INVALID;
   }
   return kmap_build_impl(table, slots, out_coords, n_cap, n_dev, n_cap, offsets_host, k, nbr, nbsizes, blockcnt, stream);
+}
+
+size_t tsg_kmap_pair_list_ws_bytes(int k, int64_t n_rows) { return ((size_t)k * tsg_kmap_blocks(n_rows) + 1) * sizeof(int); }
+
+int tsg_kmap_pair_list(const int32_t *nbr, int k, int64_t n_rows, int64_t nbr_stride, int32_t *pairs, int32_t *start, void *ws,
+                       size_t ws_bytes, cudaStream_t stream) {
+  if (k <= 0 || k > 32 || n_rows <= 0 || nbr_stride < n_rows || (int64_t)k * n_rows >= (1ll << 31)) {
+    set_error("tsg_kmap_pair_list: need 0 < K <= 32, n_rows > 0, nbr_stride >= n_rows and K * n_rows < 2^31");
+    return TSG_ERR_INVALID;
+  }
+  if (ws_bytes < tsg_kmap_pair_list_ws_bytes(k, n_rows)) {
+    set_error("tsg_kmap_pair_list: workspace too small");
+    return TSG_ERR_INVALID;
+  }
+  const int64_t nblk = tsg_kmap_blocks(n_rows);
+  int *blockcnt = (int *)ws, *last = blockcnt + (int64_t)k * nblk;
+  pair_count_kernel<<<(unsigned)nblk, 256, 0, stream>>>(nbr, k, n_rows, nbr_stride, blockcnt, nblk);
+  save_last_kernel<<<1, 1, 0, stream>>>(blockcnt, (int64_t)k * nblk, last);
+  scan_inplace_kernel<<<1, 1024, 0, stream>>>(blockcnt, (int64_t)k * nblk);
+  pair_write_kernel<<<(unsigned)nblk, 256, 0, stream>>>(nbr, k, n_rows, nbr_stride, blockcnt, nblk, (int2 *)pairs, start, last);
+  return check_launch("tsg_kmap_pair_list");
 }
 
 int tsg_kmap_pairs(const int32_t *nbr, int k, int64_t n_out, int32_t *blockcnt, int64_t *nbmaps,

@@ -99,7 +99,9 @@ class ConvolutionFunction(Function):
             grad_input = ops.conv_dgrad(grad_output, weight, tab_out_of_in, input.shape[0]).to(input.dtype)
         else:
             grad_input = None
-        if input.dtype == torch.bfloat16 and c_in % 8 == 0 and c_out % 8 == 0:
+        if input.dtype == torch.bfloat16 and c_in % 8 == 0 and c_out % 8 == 0 and c_out <= 256 and ops.WGRAD_TC:
+            grad_weight = ops.conv_wgrad_tc(input, grad_output, tab_in_of_out, k).to(weight.dtype)      # tcgen05
+        elif input.dtype == torch.bfloat16 and c_in % 8 == 0 and c_out % 8 == 0:
             grad_weight = ops.conv_wgrad_bf16(input, grad_output, tab_in_of_out, k).to(weight.dtype)
         else:
             grad_weight = ops.conv_wgrad(input, grad_output, tab_in_of_out, k).to(weight.dtype)

@@ -545,6 +545,53 @@ def conv_wgrad_bf16(feats: torch.Tensor, grad_out: torch.Tensor, nbr: torch.Tens
     return gw
 
 
+WGRAD_TC = os.environ.get("TSG_WGRAD_TC", "1") != "0"   # A/B switch: tcgen05 weight gradient (0: the warp-level MMA kernel)
+
+
+class PairList:
+    """Compact per-offset {in row, out row} lists of a neighbour table (tsg_kmap_pair_list): the K dimension of the
+    weight-gradient GEMMs.  Built once per table and cached on it, so every layer that shares a kernel map shares it."""
+
+    def __init__(self, nbr: torch.Tensor):
+        assert nbr.dtype == torch.int32 and nbr.dim() == 2 and nbr.is_contiguous()
+        k, n = nbr.shape
+        dev = nbr.device
+        self.k, self.cap = k, k * n
+        self.pairs = torch.empty((max(self.cap, 1), 2), dtype=torch.int32, device=dev)
+        self.start = torch.zeros(k + 1, dtype=torch.int32, device=dev)
+        if n:
+            ws_bytes = int(L.lib().tsg_kmap_pair_list_ws_bytes(k, n))
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            call("tsg_kmap_pair_list", ptr(nbr), k, n, nbr.stride(0), ptr(self.pairs), ptr(self.start), ptr(ws), ws_bytes, stream())
+
+    @staticmethod
+    def of(nbr: torch.Tensor) -> "PairList":
+        key = (nbr.data_ptr(), nbr._version, tuple(nbr.shape))
+        cached = getattr(nbr, "_tsg_pairs", None)
+        if cached is None or cached[0] != key:
+            cached = (key, PairList(nbr))
+            try:
+                nbr._tsg_pairs = cached
+            except AttributeError:
+                pass
+        return cached[1]
+
+
+def conv_wgrad_tc(feats: torch.Tensor, grad_out: torch.Tensor, nbr: torch.Tensor, k: int,
+                  pairs: Optional[PairList] = None) -> torch.Tensor:
+    """Weight gradient on tcgen05 (tsg_conv_wgrad_tc): bf16 rows in, fp32 (K, c_in, c_out) out; c_out <= 256.
+    nbr (K, n_out): rows = outputs of the forward, values = input rows; its pair list is built once and cached."""
+    L.require_cuda(feats, grad_out, nbr)
+    feats = feats.to(torch.bfloat16).contiguous()
+    grad_out = grad_out.to(torch.bfloat16).contiguous()
+    c_in, c_out = feats.shape[1], grad_out.shape[1]
+    pl = pairs if pairs is not None else PairList.of(nbr)
+    gw = torch.empty((k, c_in, c_out), dtype=torch.float32, device=feats.device)
+    call("tsg_conv_wgrad_tc", ptr(feats), feats.shape[0], c_in, ptr(grad_out), grad_out.shape[0], c_out, ptr(pl.pairs),
+         ptr(pl.start), pl.cap, k, ptr(gw), stream())
+    return gw
+
+
 def pad16(c: int) -> int:
     return (c + 15) // 16 * 16
 

@@ -536,6 +536,8 @@ def test_conv_tensor_core_vs_oracle(ts):
     gx_ref, gw_ref = T.conv_backward(npy(x.float()), npy(gy.float()), npy(w.float()), nbmaps, nbsizes, False)
     gw = ops.conv_wgrad_bf16(x, gy, km.nbr, 27)
     assert rel_err(npy(gw), gw_ref) < 1e-3
+    gw_tc = ops.conv_wgrad_tc(x, gy, km.nbr, 27)          # tcgen05 weight gradient against the oracle's backward
+    assert rel_err(npy(gw_tc), gw_ref) < 1e-3
     # bf16 data gradient: tensor-core kernel over the transposed map with W[k]^T (output rounded to bf16)
     packed_t = ops.pack_weights(w.float().transpose(1, 2).contiguous(), 96)
     gx = ops.conv_forward_tc(gy, None, packed_t, 27, 64, km.nbr_t, km.tile_mask(True), n, out_dtype=torch.float32)
@@ -570,6 +572,41 @@ def test_conv_wgrad_bf16(ts, c_in, c_out, ks, n):
     torch.cuda.synchronize()
     assert got.shape == want.shape == (len(offs), c_in, c_out)
     assert rel_err(npy(got), npy(want)) < 1e-4
+    got_tc = ops.conv_wgrad_tc(x, gy, km.nbr, len(offs))     # the tcgen05 kernel: same products, fp32 accumulation in TMEM
+    torch.cuda.synchronize()
+    assert got_tc.shape == want.shape
+    assert rel_err(npy(got_tc), npy(want)) < 1e-4
+
+
+def test_conv_wgrad_tc_wide_and_empty(ts):
+    """tcgen05 weight gradient: more than 128 input channels (several TMEM-lane tiles), a transposed (stride-2) map, an
+    offset without any pair, fewer pairs than one 64-pair chunk, and run-to-run determinism with one split."""
+    from taseg_b200 import ops
+    rng = np.random.default_rng(5)
+    c = np.unique(rng.integers(0, 30, (12000, 3)).astype(np.int32), axis=0)
+    c = np.concatenate([c, np.zeros((len(c), 1), np.int32)], 1)
+    n = len(c)
+    tab = ops.Table.from_coords(cu(c))
+    km = ops.build_kmap(tab, n, cu(c), T.get_kernel_offsets(3, 1))
+    for c_in, c_out in [(384, 256), (256, 128), (200, 72)]:
+        x = torch.randn(n, c_in, device="cuda").bfloat16()
+        gy = torch.randn(n, c_out, device="cuda").bfloat16()
+        want = ops.conv_wgrad(x.float(), gy.float(), km.nbr, 27)
+        got = ops.conv_wgrad_tc(x, gy, km.nbr, 27)
+        torch.cuda.synchronize()
+        assert rel_err(npy(got), npy(want)) < 1e-4, (c_in, c_out)
+    # a map with empty offsets and very few pairs: 40 isolated voxels (only the centre offset has pairs)
+    iso = np.stack([np.arange(40) * 5, np.zeros(40), np.zeros(40), np.zeros(40)], 1).astype(np.int32)
+    km2 = ops.build_kmap(ops.Table.from_coords(cu(iso)), 40, cu(iso), T.get_kernel_offsets(3, 1))
+    x = torch.randn(40, 32, device="cuda").bfloat16()
+    gy = torch.randn(40, 64, device="cuda").bfloat16()
+    got = ops.conv_wgrad_tc(x, gy, km2.nbr, 27)
+    want = ops.conv_wgrad(x.float(), gy.float(), km2.nbr, 27)
+    torch.cuda.synchronize()
+    assert rel_err(npy(got), npy(want)) < 1e-4
+    assert float(got[:13].abs().max()) == 0.0 and float(got[14:].abs().max()) == 0.0
+    again = ops.conv_wgrad_tc(x, gy, km2.nbr, 27)
+    assert torch.equal(got, again)
 
 
 def test_backend_mirror(ts, golden):
