@@ -280,6 +280,24 @@ int tsg_kmap_pair_list(const int32_t *nbr, int k, int64_t n_rows, int64_t nbr_st
 int tsg_conv_wgrad_tc(const void *in, int64_t n_in, int c_in, const void *grad_out, int64_t n_out, int c_out,
                       const int32_t *pairs, const int32_t *start, int64_t pair_cap, int k, float *grad_w, tsg_stream_t stream);
 
+/* ---------------------------------------------------------------- BatchNorm over feature rows (a21)
+ * spnn.BatchNorm is nn.BatchNorm1d applied to SparseTensor.F (TS/torchsparse/nn/modules/norm.py:10-13; 63 of them in the
+ * benchmark network, one after every convolution).  x, y, dy, dx: (n, c) rows, fp32 or bf16, c a multiple of 8 <= 1024;
+ * statistics, affine parameters and their gradients fp32.  ws: tsg_bn_ws_bytes(n, c) bytes.  Deterministic (per-CTA
+ * partials combined in double precision in a fixed order; no floating-point atomics on global memory).
+ *   tsg_bn_stats:    batch mean / invstd = 1 / sqrt(biased var + eps); running statistics updated in place when given
+ *                    (momentum, unbiased variance — nn.BatchNorm1d's rule)
+ *   tsg_bn_apply:    y = (x - mean) invstd gamma + beta   (evaluation: mean / invstd derived from the running statistics)
+ *   tsg_bn_backward: sums = {dbeta, dgamma}; dx = gamma invstd (dy - dbeta / n - xhat dgamma / n)  (training) or
+ *                    gamma invstd dy (evaluation) */
+size_t tsg_bn_ws_bytes(int64_t n, int c);
+int tsg_bn_stats(const void *x, int dtype, int64_t n, int c, float eps, float momentum, float *running_mean, float *running_var,
+                 float *mean, float *invstd, void *ws, size_t ws_bytes, tsg_stream_t stream);
+int tsg_bn_apply(const void *x, int dtype, int64_t n, int c, const float *mean, const float *invstd, const float *gamma,
+                 const float *beta, void *y, tsg_stream_t stream);
+int tsg_bn_backward(const void *x, const void *dy, int dtype, int64_t n, int c, const float *mean, const float *invstd,
+                    const float *gamma, int training, float *sums, void *dx, void *ws, size_t ws_bytes, tsg_stream_t stream);
+
 /* tcgen05/TMEM path (bf16 operands, fp32 accumulate in tensor memory).
  * Weights are packed once per layer into the shared-memory image the MMA consumes (128B-swizzled K-major
  * [c_out][64] blocks per kernel offset and 64-channel slice; single-source layers with c0 of 16 or 32 put 64/c0

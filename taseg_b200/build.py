@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtaseg_b200.so")
-SOURCES = ["geometry.cu", "sort.cu", "points.cu", "pointvoxel.cu", "conv.cu", "conv_tc.cu", "conv_wgrad_tc.cu"]
+SOURCES = ["geometry.cu", "sort.cu", "points.cu", "pointvoxel.cu", "conv.cu", "conv_tc.cu", "conv_wgrad_tc.cu", "bn.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 

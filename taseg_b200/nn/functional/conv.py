@@ -38,7 +38,16 @@ def as_kernel_map(entry, k: int) -> ops.KernelMap:
 
 
 def _tc_ok(feats: torch.Tensor, c_in: int, c_out: int) -> bool:
-    return feats.dtype == torch.bfloat16 and c_in % 16 == 0 and c_out % 16 == 0 and c_out <= 256
+    """The tensor-core kernel takes it, possibly after zero-padding the input channels to a multiple of 16 (the 5-channel
+    stem) and / or in column blocks of <= 256 output channels (the data gradient of the 384-channel decoder concat)."""
+    return feats.dtype == torch.bfloat16 and c_out % 16 == 0
+
+
+def _col_blocks(c_out: int):
+    """Output-channel blocks of at most 256 (multiples of 16) the tensor-core kernel is launched over."""
+    nb = (c_out + 255) // 256
+    step = (c_out // 16 + nb - 1) // nb * 16
+    return [(a, min(c_out, a + step)) for a in range(0, c_out, step)]
 
 
 # Packed tensor-core images of a layer's weights, W[k] for the forward and W[k]^T for the data gradient, cached per
@@ -47,16 +56,42 @@ def _tc_ok(feats: torch.Tensor, c_in: int, c_out: int) -> bool:
 _PACKS = {}
 
 
-def packed_weights(param: torch.Tensor, transposed_w: bool) -> torch.Tensor:
-    key = (id(param), transposed_w)
+def _pack(w: torch.Tensor, cols):
+    """(K, c_in, c_out) -> packed image of W[:, :, cols[0]:cols[1]] with c_in zero-padded to a multiple of 16."""
+    k, c_in, c_out = w.shape
+    w = w[:, :, cols[0]:cols[1]]
+    if c_in % 16:
+        w = torch.nn.functional.pad(w, (0, 0, 0, 16 - c_in % 16))
+    return ops.pack_weights(w.contiguous(), w.shape[1])
+
+
+def packed_weights(param: Optional[torch.Tensor], weight: torch.Tensor, transposed_w: bool, cols) -> torch.Tensor:
+    """param: the fp32 parameter `weight` was cast from (the cache key), or None (no caching)."""
+    if param is None:
+        w = weight.detach().float()
+        return _pack(w.transpose(1, 2) if transposed_w else w, cols)
+    key = (id(param), transposed_w, cols)
     hit = _PACKS.get(key)
     if hit is not None and hit[0] == param._version and hit[1] == param.data_ptr():
         return hit[2]
     w = param.detach().float()
-    k, c_in, c_out = w.shape
-    packed = ops.pack_weights(w.transpose(1, 2).contiguous(), c_out) if transposed_w else ops.pack_weights(w, c_in)
+    packed = _pack(w.transpose(1, 2) if transposed_w else w, cols)
     _PACKS[key] = (param._version, param.data_ptr(), packed)
     return packed
+
+
+def _conv_tc(feats: torch.Tensor, param, weight: torch.Tensor, transposed_w: bool, kmap: ops.KernelMap, map_transposed: bool,
+             n_out: int) -> torch.Tensor:
+    """out = conv(feats, W or W^T) on the tensor cores over the (mask-sorted) map; bf16 in, bf16 out."""
+    k = weight.shape[0]
+    c_in, c_out = (weight.shape[2], weight.shape[1]) if transposed_w else (weight.shape[1], weight.shape[2])
+    if c_in % 16:
+        feats = torch.nn.functional.pad(feats, (0, 16 - c_in % 16))
+    feats = feats.contiguous()
+    nbr_s, mask_s, perm = kmap.sorted(map_transposed)      # mask-sorted tile rows: empty (tile, offset) pairs are skipped
+    outs = [ops.conv_forward_tc(feats, None, packed_weights(param, weight, transposed_w, cols), k, cols[1] - cols[0], nbr_s,
+                                mask_s, n_out, perm=perm) for cols in _col_blocks(c_out)]
+    return outs[0] if len(outs) == 1 else torch.cat(outs, dim=1)
 
 
 class ConvolutionFunction(Function):
@@ -72,9 +107,7 @@ class ConvolutionFunction(Function):
         n_out = kmap.n_in if transposed else kmap.n_out
         k, c_in, c_out = weight.shape
         if _tc_ok(input, c_in, c_out):
-            packed = packed_weights(param, False) if param is not None else ops.pack_weights(weight, c_in)
-            nbr_s, mask_s, perm = kmap.sorted(transposed)      # mask-sorted tile rows: empty (tile, offset) pairs are skipped
-            out = ops.conv_forward_tc(input, None, packed, k, c_out, nbr_s, mask_s, n_out, perm=perm)
+            out = _conv_tc(input, param, weight, False, kmap, transposed, n_out)
         else:
             out = ops.conv_forward(input, weight, nbr, n_out)
         ctx.for_backwards = (input, weight, kmap, transposed, param)
@@ -90,17 +123,15 @@ class ConvolutionFunction(Function):
         c_in, c_out = weight.shape[1], weight.shape[2]
         if ctx.needs_input_grad[0] and _tc_ok(input, c_out, c_in):
             # dgrad = the same tensor-core kernel over the transposed table with W[k]^T (bf16 operands, fp32 accumulate)
-            packed_t = (packed_weights(param, True) if param is not None
-                        else ops.pack_weights(weight.transpose(1, 2).contiguous(), c_out))
-            nbr_s, mask_s, perm = kmap.sorted(not transposed)
-            grad_input = ops.conv_forward_tc(grad_output.contiguous().to(torch.bfloat16), None, packed_t, k, c_in,
-                                             nbr_s, mask_s, input.shape[0], perm=perm)
+            grad_input = _conv_tc(grad_output.contiguous().to(torch.bfloat16), param, weight, True, kmap, not transposed,
+                                  input.shape[0])
         elif ctx.needs_input_grad[0]:
             grad_input = ops.conv_dgrad(grad_output, weight, tab_out_of_in, input.shape[0]).to(input.dtype)
         else:
             grad_input = None
-        if input.dtype == torch.bfloat16 and c_in % 8 == 0 and c_out % 8 == 0 and c_out <= 256 and ops.WGRAD_TC:
-            grad_weight = ops.conv_wgrad_tc(input, grad_output, tab_in_of_out, k).to(weight.dtype)      # tcgen05
+        if input.dtype == torch.bfloat16 and c_out % 8 == 0 and c_out <= 256 and ops.WGRAD_TC:
+            x = input if c_in % 8 == 0 else torch.nn.functional.pad(input, (0, 8 - c_in % 8))     # tcgen05; 5-channel stem padded
+            grad_weight = ops.conv_wgrad_tc(x, grad_output, tab_in_of_out, k)[:, :c_in].to(weight.dtype)
         elif input.dtype == torch.bfloat16 and c_in % 8 == 0 and c_out % 8 == 0:
             grad_weight = ops.conv_wgrad_bf16(input, grad_output, tab_in_of_out, k).to(weight.dtype)
         else:

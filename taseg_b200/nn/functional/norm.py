@@ -1,0 +1,53 @@
+"""BatchNorm over the (N, C) feature matrix on the C-ABI kernels (taseg_b200/csrc/bn.cu): the function spnn.BatchNorm and the
+segmentor's BatchNorm call on CUDA feature rows.  Semantics of nn.BatchNorm1d (TS/torchsparse/nn/modules/norm.py:10-13 applies
+it to SparseTensor.F): batch statistics + running-statistics update in training, running statistics in evaluation, fp32
+affine parameters, output in the input's dtype (so it composes with autocast like ATen's batch_norm does)."""
+from typing import Optional
+
+import torch
+from torch.autograd import Function
+
+from ... import ops
+
+__all__ = ['batch_norm']
+
+
+class BatchNormFunction(Function):
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, running_mean, running_var, training: bool, momentum: float, eps: float):
+        x = x.contiguous()
+        w = weight.float().contiguous() if weight is not None else None
+        b = bias.float().contiguous() if bias is not None else None
+        if training:
+            mean, invstd = ops.bn_stats(x, eps, momentum, running_mean, running_var)
+        else:
+            mean, invstd = running_mean.float(), torch.rsqrt(running_var.float() + eps)
+        y = ops.bn_apply(x, mean, invstd, w, b)
+        ctx.save_for_backward(x, mean, invstd, w)
+        ctx.training = training
+        ctx.has_affine = (weight is not None, bias is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, mean, invstd, w = ctx.saved_tensors
+        dx, dgamma, dbeta = ops.bn_backward(x, dy, mean, invstd, w, ctx.training, want_dx=ctx.needs_input_grad[0])
+        return (dx, dgamma if ctx.has_affine[0] else None, dbeta if ctx.has_affine[1] else None, None, None, None, None, None)
+
+
+def batch_norm(module: torch.nn.modules.batchnorm._BatchNorm, x: torch.Tensor) -> Optional[torch.Tensor]:
+    """nn.BatchNorm1d.forward(x) for CUDA feature rows the kernels take; None when the caller should use ATen."""
+    if not ops.bn_supported(x):
+        return None
+    training = module.training or (module.running_mean is None and module.running_var is None)
+    momentum = 0.0 if module.momentum is None else module.momentum
+    if module.training and module.track_running_stats and module.num_batches_tracked is not None:
+        module.num_batches_tracked.add_(1)
+        if module.momentum is None:      # cumulative moving average
+            momentum = 1.0 / float(module.num_batches_tracked)
+    rm = module.running_mean if (not training or module.track_running_stats) else None
+    rv = module.running_var if (not training or module.track_running_stats) else None
+    if rm is not None and (rm.dtype != torch.float32 or not rm.is_contiguous()):
+        return None
+    return BatchNormFunction.apply(x, module.weight, module.bias, rm, rv, training, momentum, module.eps)

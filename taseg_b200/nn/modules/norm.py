@@ -9,5 +9,10 @@ __all__ = ['BatchNorm']
 
 class BatchNorm(nn.BatchNorm1d):
 
+    def _rows(self, feats):
+        from ..functional.norm import batch_norm      # CUDA rows: streaming kernels of csrc/bn.cu; otherwise ATen
+        out = batch_norm(self, feats)
+        return out if out is not None else nn.BatchNorm1d.forward(self, feats)
+
     def forward(self, input: SparseTensor) -> SparseTensor:
-        return fapply(input, super().forward)
+        return fapply(input, self._rows)

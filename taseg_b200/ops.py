@@ -545,6 +545,53 @@ def conv_wgrad_bf16(feats: torch.Tensor, grad_out: torch.Tensor, nbr: torch.Tens
     return gw
 
 
+# ------------------------------------------------------------------------------- BatchNorm over feature rows
+FUSED_BN = os.environ.get("TSG_BN", "1") != "0"      # A/B switch: 0 = ATen's batch_norm
+
+
+def bn_supported(x: torch.Tensor) -> bool:
+    return (FUSED_BN and x.is_cuda and x.dim() == 2 and x.dtype in (torch.float32, torch.bfloat16) and x.shape[0] > 0
+            and x.shape[1] % 8 == 0 and x.shape[1] <= 1024)
+
+
+def _bn_ws(x: torch.Tensor) -> torch.Tensor:
+    return torch.empty(int(L.lib().tsg_bn_ws_bytes(x.shape[0], x.shape[1])), dtype=torch.uint8, device=x.device)
+
+
+def bn_stats(x: torch.Tensor, eps: float, momentum: float, running_mean: Optional[torch.Tensor],
+             running_var: Optional[torch.Tensor]):
+    """(mean, invstd) fp32 of the rows of x; running statistics (fp32, contiguous) updated in place."""
+    x = x.contiguous()
+    n, c = x.shape
+    mean = torch.empty(c, dtype=torch.float32, device=x.device)
+    invstd = torch.empty(c, dtype=torch.float32, device=x.device)
+    ws = _bn_ws(x)
+    call("tsg_bn_stats", ptr(x), L.DTYPES[x.dtype], n, c, float(eps), float(momentum), ptr(running_mean), ptr(running_var),
+         ptr(mean), ptr(invstd), ptr(ws), ws.numel(), stream())
+    return mean, invstd
+
+
+def bn_apply(x: torch.Tensor, mean: torch.Tensor, invstd: torch.Tensor, gamma: Optional[torch.Tensor],
+             beta: Optional[torch.Tensor]) -> torch.Tensor:
+    x = x.contiguous()
+    y = torch.empty_like(x)
+    call("tsg_bn_apply", ptr(x), L.DTYPES[x.dtype], x.shape[0], x.shape[1], ptr(mean), ptr(invstd), ptr(gamma), ptr(beta), ptr(y), stream())
+    return y
+
+
+def bn_backward(x: torch.Tensor, dy: torch.Tensor, mean: torch.Tensor, invstd: torch.Tensor, gamma: Optional[torch.Tensor],
+                training: bool, want_dx: bool = True):
+    """(dx | None, dgamma, dbeta)."""
+    x, dy = x.contiguous(), dy.contiguous().to(x.dtype)
+    n, c = x.shape
+    sums = torch.empty((2, c), dtype=torch.float32, device=x.device)
+    dx = torch.empty_like(x) if want_dx else None
+    ws = _bn_ws(x)
+    call("tsg_bn_backward", ptr(x), ptr(dy), L.DTYPES[x.dtype], n, c, ptr(mean), ptr(invstd), ptr(gamma), int(training), ptr(sums),
+         ptr(dx), ptr(ws), ws.numel(), stream())
+    return dx, sums[1], sums[0]
+
+
 WGRAD_TC = os.environ.get("TSG_WGRAD_TC", "1") != "0"   # A/B switch: tcgen05 weight gradient (0: the warp-level MMA kernel)
 
 

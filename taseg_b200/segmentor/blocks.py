@@ -16,9 +16,8 @@ class SyncBatchNorm(nn.SyncBatchNorm):
         return fapply(input, super().forward)
 
 
-class BatchNorm(nn.BatchNorm1d):
-    def forward(self, input: SparseTensor) -> SparseTensor:
-        return fapply(input, super().forward)
+class BatchNorm(spnn.BatchNorm):
+    """spnn.BatchNorm: nn.BatchNorm1d on the feature rows (CUDA rows run the kernels of csrc/bn.cu)."""
 
 
 def norm(channels: int, if_dist: bool) -> nn.Module:

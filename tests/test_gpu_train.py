@@ -89,3 +89,44 @@ def test_fp32_gradient_against_finite_differences():
         fd = (lp - lm) / (2 * eps)
         an = float(w.grad[k, i, j])
         assert abs(fd - an) <= 5e-2 * max(abs(fd), abs(an)) + 2e-4, ((k, i, j), fd, an)
+
+
+@pytest.mark.parametrize("c,dtype", [(32, torch.float32), (96, torch.bfloat16), (256, torch.bfloat16), (8, torch.float32)])
+def test_batch_norm_rows_vs_aten(c, dtype):
+    """spnn.BatchNorm on CUDA rows (csrc/bn.cu) against nn.BatchNorm1d (ATen) with the same parameters: training forward,
+    running statistics, input / weight / bias gradients, then evaluation mode; and run-to-run determinism."""
+    from taseg_b200 import nn as spnn
+    from taseg_b200 import ops
+    torch.manual_seed(c)
+    n = 70001
+    x = (torch.randn(n, c, device="cuda") * 1.7 + 0.3).to(dtype)
+    ours, ref = spnn.BatchNorm(c).cuda(), torch.nn.BatchNorm1d(c).cuda()
+    with torch.no_grad():
+        ours.weight.copy_(torch.rand(c) + 0.5)
+        ours.bias.copy_(torch.randn(c) * 0.2)
+    ref.load_state_dict(ours.state_dict())
+    gy = torch.randn(n, c, device="cuda").to(dtype)
+    outs = []
+    for m in (ours, ref):
+        xi = x.clone().requires_grad_(True)
+        y = m._rows(xi) if m is ours else m(xi)
+        y.backward(gy)
+        outs.append((y.detach().float(), xi.grad.float(), m.weight.grad.clone(), m.bias.grad.clone()))
+    assert ops.bn_supported(x)
+    tol = 1e-4 if dtype == torch.float32 else 2e-2
+    for a, b in zip(outs[0], outs[1]):
+        assert float((a - b).abs().max()) <= tol * max(1.0, float(b.abs().max())), (c, dtype)
+    assert torch.allclose(ours.running_mean, ref.running_mean, atol=1e-5) and torch.allclose(ours.running_var, ref.running_var, rtol=1e-4)
+    assert int(ours.num_batches_tracked) == 1
+    xi = x.clone().requires_grad_(True)
+    y2 = ours._rows(xi)
+    y2.backward(gy)
+    assert torch.equal(y2.detach().float(), outs[0][0]) and torch.equal(xi.grad.float(), outs[0][1]), "not deterministic"
+    ours.eval(), ref.eval()
+    ref.load_state_dict(ours.state_dict())
+    xe = x.clone().requires_grad_(True)
+    xr = x.clone().requires_grad_(True)
+    ye, yr = ours._rows(xe), ref(xr)
+    ye.backward(gy), yr.backward(gy)
+    assert float((ye.float() - yr.float()).abs().max()) <= tol * max(1.0, float(yr.float().abs().max()))
+    assert float((xe.grad.float() - xr.grad.float()).abs().max()) <= tol * max(1.0, float(xr.grad.float().abs().max()))
