@@ -673,7 +673,7 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
     // they finish (true heaviest-first list scheduling), short tiles still keep several plans in flight.
     // With many tiles per CTA the imbalance averages out and a stalled planner only costs (measured: +7 % on the
     // stride-1 layers), so the throttle is applied to launches with at most eight work items per CTA.
-    const int LOOKAHEAD = 3 * (int)nst + 4;   // progress is published by the MMA issuer, up to nst stages behind the producers
+    const int LOOKAHEAD = p.lookahead * (int)nst + 4;   // progress is published by the MMA issuer, up to nst stages behind the producers
     // A template switch, chosen by the host from the tile count: the two-tile kernel's hot loops are sensitive to every
     // KB of code (75 KB of SASS against the instruction cache) — the throttle, compiled in but never taken, cost the
     // stride-1 layers 6 %.
@@ -1382,6 +1382,8 @@ int tsg_conv_fwd_tc4(const void *in0, int c0, const void *in1, int c1, int64_t n
   cfg.numAttrs = na;
   // look-ahead throttle (see the planner): launches with at most `thr_max` work items per CTA
   static const int thr_max = getenv("TSG_TC_THROTTLE") ? atoi(getenv("TSG_TC_THROTTLE")) : 8;
+  static const int lookahead = getenv("TSG_TC_LOOKAHEAD") ? atoi(getenv("TSG_TC_LOOKAHEAD")) : 6;
+  p.lookahead = lookahead;
   const bool thr = sched && work <= (long long)thr_max * cfg.gridDim.x;
   if (pair) TSG_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<1, true, false>, p));
   else if (G == 2 && thr) TSG_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<2, false, true>, p));

@@ -195,6 +195,7 @@ struct TcParams {
   const int *n_items;    // device: number of work items
   float *split_scratch;  // slots x 128 x n_eff fp32 partial sums
   int *split_state;      // slots x 8 hand-off words, zero between launches
+  int lookahead;         // planner throttle: a ticket is drawn when fewer than lookahead * stages + 4 planned stages are left
 };
 
 struct Ring {  // slot + phase of a circular mbarrier pipeline

@@ -693,7 +693,8 @@ def _sched_ws(device) -> torch.Tensor:
 
 
 DYNAMIC_TILES = os.environ.get("TSG_DYNAMIC_TILES", "1") != "0"   # A/B switch: in-kernel dynamic tile scheduler
-SPLIT_K = os.environ.get("TSG_SPLIT_K", "1") != "0"               # A/B switch: K-split work items for launches with few tiles
+SPLIT_K = os.environ.get("TSG_SPLIT_K", "0") != "0"               # K-split work items for launches with few tiles (off: measured -4 % on the
+                                                                  # stride-16 launches alone, +1.5 % on the step with three batches in flight)
 SPLIT_MAX_TILES = int(os.environ.get("TSG_SPLIT_MAX_TILES", "222"))   # ... up to 1.5 tiles per SM of a B200
 SPLIT_CAP = int(os.environ.get("TSG_SPLIT_CAP", "14"))             # a tile with more active offsets becomes two work items
 

@@ -21,7 +21,7 @@ def main():
     out = frontend.aggregate_voxelize(torch.from_numpy(mfb.points).cuda(), mfb, 0.05, torch.from_numpy(mfb.cur_idx).cuda())
     geo = Geometry(out["coords"], field_bits=out["field_bits"])
     torch.manual_seed(0)
-    cases = [(0, 96, 96), (1, 32, 32), (0, 32, 32), (2, 64, 64), (4, 256, 256), (3, 128, 128)]
+    cases = [(0, 96, 96), (1, 32, 32), (0, 32, 32), (2, 64, 64), (4, 256, 256), (3, 128, 128), (3, 256, 256), (2, 128, 128), (1, 96, 96)]
     reps = int(os.environ.get("REPS", "1"))
     if os.environ.get("CASES"):
         cases = [cases[int(i)] for i in os.environ["CASES"].split(",")]
