@@ -30,15 +30,17 @@ inline int check_launch(const char *what) {
     }                                                                \
   } while (0)
 
-inline int num_sms() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
+inline int num_sms() {   // of the CURRENT device (cached per device: a process may drive several)
+  static int cache[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (!cache[dev]) {
+    int n = 0;
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+    cache[dev] = n > 0 ? n : 148;
   }
-  return n;
+  return cache[dev];
 }
 
 // grid for a grid-stride elementwise kernel: enough CTAs to fill the chip a few times, never more than needed

@@ -306,7 +306,7 @@ class Engine:
 def tta_vote(point_logits, save_score: bool = False):
     """Test-time-augmentation vote of the reference's evaluation loop (R/train.py:471-475, :497-503): the per-point
     logits of the `votes` augmented copies of one scan (one entry of `point_predict_logits` each) are SUMMED and the
-    arg-max is the prediction, returned as the uint32 column the `.label` dump holds (`taseg_b200.io.write_labels`), or
+    arg-max is the prediction, returned as int64 class ids (`taseg_b200.io.write_labels` casts them to the uint32 column of the `.label` dump), or
     the float32 summed scores with `save_score`.  Stays on the tensors' device: one D2H copy of N x 4 bytes per scan
     instead of votes x N x classes x 4."""
     total = point_logits[0].clone() if isinstance(point_logits, (list, tuple)) else point_logits.sum(dim=0)

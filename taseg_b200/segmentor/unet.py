@@ -166,7 +166,7 @@ class _SparseUNet(nn.Module):
                 rows = rows[batch_dict['point_mask'][pointer:pointer + n_ms].to(rows.device)]
                 pointer += n_ms
             rows = rows[:num_points[b]]
-            logits = ops.gather_rows(out.float(), rows) if out.dtype != torch.float32 or True else out[rows]
+            logits = ops.gather_rows(out.float(), rows)
             ret['point_predict'].append((logits.softmax(1) if want_prob else logits.argmax(1)).cpu().numpy())
             ret['point_predict_logits'].append(logits.cpu().numpy())
             ret['point_labels'].append(labels.F[lab_b == b][:num_points[b]].cpu().numpy())
