@@ -12,6 +12,8 @@
 //              [dx = gamma invstd (dy - s1 / N - xhat s2 / N)]
 #include <cuda_bf16.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace tsg {
@@ -76,22 +78,36 @@ __global__ void __launch_bounds__(BN_THREADS) bn_reduce_kernel(const T *__restri
         is[j] = invstd[cg * 8 + j];
       }
     }
-    for (int64_t r = r0 + rt; r < r1; r += rpp) {
-      float v[8];
-      load8<T>(x + r * c + cg * 8, v);
-      if (MODE == 0) {
+    // four rows per trip: the loads are independent, so a thread keeps 4 (8 with dy) 16-byte requests in flight — with one
+    // load per trip the pass ran at 1.8 TB/s, bound by latency x bytes in flight
+    constexpr int U = 4;
+    for (int64_t r = r0 + rt; r < r1; r += (int64_t)U * rpp) {
+      float v[U][8], g[U][8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          a[j] += v[j];
-          b[j] = fmaf(v[j], v[j], b[j]);
+      for (int u = 0; u < U; ++u) {
+        const int64_t ru = r + (int64_t)u * rpp;
+        if (ru < r1) {
+          load8<T>(x + ru * c + cg * 8, v[u]);
+          if (MODE == 1) load8<T>(dy + ru * c + cg * 8, g[u]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            v[u][j] = MODE == 1 ? mu[j] : 0.f;   // contributes nothing
+            g[u][j] = 0.f;
+          }
         }
-      } else {
-        float g[8];
-        load8<T>(dy + r * c + cg * 8, g);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          a[j] += g[j];
-          b[j] = fmaf(g[j], (v[j] - mu[j]) * is[j], b[j]);
+          if (MODE == 0) {
+            a[j] += v[u][j];
+            b[j] = fmaf(v[u][j], v[u][j], b[j]);
+          } else {
+            a[j] += g[u][j];
+            b[j] = fmaf(g[u][j], (v[u][j] - mu[j]) * is[j], b[j]);
+          }
         }
       }
     }
@@ -122,58 +138,82 @@ __global__ void __launch_bounds__(BN_THREADS) bn_reduce_kernel(const T *__restri
   }
 }
 
-// One warp per channel: lane l combines stripes l, l + 32, ... in order (Chan's update, double precision), then the 32
-// lane results are combined by a shuffle tree — a fixed order, so the statistics are deterministic.
-__device__ __forceinline__ void chan_merge(double &n, double &m, double &m2, double nb, double mb, double m2b) {
-  if (nb <= 0.0) return;
-  const double nt = n + nb, d = mb - m;
-  m += d * nb / nt;
-  m2 += m2b + d * d * n * nb / nt;
-  n = nt;
-}
-
-__global__ void __launch_bounds__(256) bn_finalize_kernel(const float *__restrict__ partial, int nb, int c, float eps, float momentum,
+constexpr int BN_FW = 32;   // warps of a finalize CTA
+// Lane = channel (32 consecutive channels per CTA: coalesced reads of the partial records), warp w combines stripes
+// w, w + 32, ... in order; the warp results are merged in warp order through shared memory.  Fixed order = deterministic.
+__global__ void __launch_bounds__(1024) bn_finalize_kernel(const float *__restrict__ partial, int nb, int c, float eps, float momentum,
                                                           float *__restrict__ running_mean, float *__restrict__ running_var,
                                                           float *__restrict__ mean, float *__restrict__ invstd) {
-  const int ch = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (ch >= c) return;
-  double n = 0.0, m = 0.0, m2 = 0.0;
-  for (int b = lane; b < nb; b += 32) {
+  // Two plain passes over the stripe records instead of a chain of Chan updates (a double-precision division per stripe
+  // and lane made the first version 90 us per call): mean = sum n_b m_b / N, then M2 = sum [M2_b + n_b (m_b - mean)^2].
+  __shared__ double sh[BN_FW][2][32];
+  __shared__ double s_mean[32], s_n;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, ch = blockIdx.x * 32 + lane;
+  const bool on = ch < c;
+  double n = 0.0, sm = 0.0;
+  #pragma unroll 4
+    for (int b = warp; b < nb; b += BN_FW) {
     const float *p = partial + (int64_t)b * (1 + 2 * c);
-    chan_merge(n, m, m2, (double)p[0], (double)p[1 + ch], (double)p[1 + c + ch]);
+    const double nb_ = (double)__ldg(p);
+    n += nb_;
+    if (on) sm += nb_ * (double)__ldg(p + 1 + ch);
   }
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {   // lane l absorbs lane l + d: stripes stay in ascending groups
-    const double on = __shfl_down_sync(0xffffffffu, n, d), om = __shfl_down_sync(0xffffffffu, m, d),
-                 om2 = __shfl_down_sync(0xffffffffu, m2, d);
-    if ((lane & (2 * d - 1)) == 0) chan_merge(n, m, m2, on, om, om2);
+  sh[warp][0][lane] = n;
+  sh[warp][1][lane] = sm;
+  __syncthreads();
+  if (warp == 0) {
+    for (int w = 1; w < BN_FW; ++w) {
+      n += sh[w][0][lane];
+      sm += sh[w][1][lane];
+    }
+    s_mean[lane] = n > 0.0 ? sm / n : 0.0;
+    if (lane == 0) s_n = n;
   }
-  if (lane == 0) {
-    const double var = n > 0.0 ? m2 / n : 0.0;
-    mean[ch] = (float)m;
+  __syncthreads();
+  const double mu = s_mean[lane], N = s_n;
+  double m2 = 0.0;
+  if (on) {
+    #pragma unroll 4
+    for (int b = warp; b < nb; b += BN_FW) {
+      const float *p = partial + (int64_t)b * (1 + 2 * c);
+      const double d = (double)__ldg(p + 1 + ch) - mu;
+      m2 += (double)__ldg(p + 1 + c + ch) + (double)__ldg(p) * d * d;
+    }
+  }
+  __syncthreads();
+  sh[warp][0][lane] = m2;
+  __syncthreads();
+  if (warp == 0 && on) {
+    for (int w = 1; w < BN_FW; ++w) m2 += sh[w][0][lane];
+    const double var = N > 0.0 ? m2 / N : 0.0;
+    mean[ch] = (float)mu;
     invstd[ch] = (float)(1.0 / sqrt(var + (double)eps));
-    if (running_mean) running_mean[ch] = (1.f - momentum) * running_mean[ch] + momentum * (float)m;
-    if (running_var) running_var[ch] = (1.f - momentum) * running_var[ch] + momentum * (float)(n > 1.0 ? m2 / (n - 1.0) : var);
+    if (running_mean) running_mean[ch] = (1.f - momentum) * running_mean[ch] + momentum * (float)mu;
+    if (running_var) running_var[ch] = (1.f - momentum) * running_var[ch] + momentum * (float)(N > 1.0 ? m2 / (N - 1.0) : var);
   }
 }
 
-// column sums of the gradient partials (one warp per channel, fixed order): sums[0][c] = sum dy (= dbeta),
-// sums[1][c] = sum dy xhat (= dgamma)
-__global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float *__restrict__ partial, int nb, int c, float *__restrict__ sums) {
-  const int ch = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (ch >= c) return;
+// column sums of the gradient partials, same geometry: sums[0][c] = sum dy (= dbeta), sums[1][c] = sum dy xhat (= dgamma)
+__global__ void __launch_bounds__(1024) bn_bwd_finalize_kernel(const float *__restrict__ partial, int nb, int c, float *__restrict__ sums) {
+  __shared__ double sh[BN_FW][2][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, ch = blockIdx.x * 32 + lane;
   double s1 = 0.0, s2 = 0.0;
-  for (int b = lane; b < nb; b += 32) {
-    const float *p = partial + (int64_t)b * (1 + 2 * c);
-    s1 += p[1 + ch];
-    s2 += p[1 + c + ch];
+  if (ch < c) {
+    #pragma unroll 4
+    for (int b = warp; b < nb; b += BN_FW) {
+      const float *p = partial + (int64_t)b * (1 + 2 * c);
+      s1 += (double)__ldg(p + 1 + ch);
+      s2 += (double)__ldg(p + 1 + c + ch);
+    }
   }
-#pragma unroll
-  for (int d = 16; d; d >>= 1) {
-    s1 += __shfl_down_sync(0xffffffffu, s1, d);
-    s2 += __shfl_down_sync(0xffffffffu, s2, d);
-  }
-  if (lane == 0) {
+  sh[warp][0][lane] = s1;
+  sh[warp][1][lane] = s2;
+  __syncthreads();
+  if (warp == 0 && ch < c) {
+    for (int w = 1; w < BN_FW; ++w) {
+      s1 += sh[w][0][lane];
+      s2 += sh[w][1][lane];
+    }
     sums[ch] = (float)s1;
     sums[c + ch] = (float)s2;
   }
@@ -186,42 +226,61 @@ __global__ void __launch_bounds__(BN_THREADS) bn_apply_kernel(const T *__restric
                                                               const float *__restrict__ mean, const float *__restrict__ invstd,
                                                               const float *__restrict__ gamma, const float *__restrict__ beta,
                                                               const float *__restrict__ sums, T *__restrict__ out) {
-  const int tpr = c / 8;
-  const int64_t total = n * tpr;
+  // A thread keeps ONE channel group for the whole pass (its 8 scales / shifts live in registers) and walks rows
+  // rt, rt + rows_in_flight, ...: consecutive threads still read consecutive 16-byte vectors of a row.
+  const int tpr = c / 8, rpp = BN_THREADS / tpr;
+  const int rt = threadIdx.x / tpr, cg = threadIdx.x - rt * tpr;
+  if (rt >= rpp) return;
   const float inv_n = 1.f / (float)n;
-  for (int64_t t = blockIdx.x * (int64_t)BN_THREADS + threadIdx.x; t < total; t += (int64_t)gridDim.x * BN_THREADS) {
-    const int cg = (int)(t % tpr);
-    float v[8], o[8];
-    if (MODE != 2) load8<T>(x + t * 8, v);
+  float sc[8], sh[8], k2[8];   // MODE 0: y = x sc + sh.  MODE 1: dx = g sc - sh - (x - mu) k2 with mu folded in.  MODE 2: dx = g sc
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int ch = cg * 8 + j;
+    const float is = invstd[ch], ga = gamma ? gamma[ch] : 1.f, mu = mean[ch];
     if (MODE == 0) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int ch = cg * 8 + j;
-        const float sc = invstd[ch] * (gamma ? gamma[ch] : 1.f);
-        o[j] = fmaf(v[j] - mean[ch], sc, beta ? beta[ch] : 0.f);
-      }
+      sc[j] = is * ga;
+      sh[j] = (beta ? beta[ch] : 0.f) - mu * is * ga;
+      k2[j] = 0.f;
+    } else if (MODE == 1) {
+      sc[j] = is * ga;
+      k2[j] = is * ga * is * sums[c + ch] * inv_n;            // coefficient of (x - mu)
+      sh[j] = is * ga * sums[ch] * inv_n - mu * k2[j];        // so that dx = g sc - sh - x k2
     } else {
-      float g[8];
-      load8<T>(dy + t * 8, g);
+      sc[j] = is * ga;
+      sh[j] = k2[j] = 0.f;
+    }
+  }
+  constexpr int U = 4;
+  const int64_t stride = (int64_t)gridDim.x * rpp;
+  for (int64_t r = (int64_t)blockIdx.x * rpp + rt; r < n; r += U * stride) {
+    float v[U][8], g[U][8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int ch = cg * 8 + j;
-        const float sc = invstd[ch] * (gamma ? gamma[ch] : 1.f);
-        if (MODE == 1) {
-          const float xh = (v[j] - mean[ch]) * invstd[ch];
-          o[j] = sc * (g[j] - sums[ch] * inv_n - xh * sums[c + ch] * inv_n);
-        } else {
-          o[j] = sc * g[j];
-        }
+    for (int u = 0; u < U; ++u) {
+      const int64_t ru = r + u * stride;
+      if (ru < n) {
+        if (MODE != 2) load8<T>(x + ru * c + cg * 8, v[u]);
+        if (MODE != 0) load8<T>(dy + ru * c + cg * 8, g[u]);
       }
     }
-    store8<T>(out + t * 8, o);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t ru = r + u * stride;
+      if (ru >= n) break;
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (MODE == 0) o[j] = fmaf(v[u][j], sc[j], sh[j]);
+        else if (MODE == 1) o[j] = fmaf(g[u][j], sc[j], -fmaf(v[u][j], k2[j], sh[j]));
+        else o[j] = g[u][j] * sc[j];
+      }
+      store8<T>(out + ru * c + cg * 8, o);
+    }
   }
 }
 
 static int bn_blocks(int64_t n, int c, int64_t *rows_per_cta) {
   const int rpp = BN_THREADS / (c / 8);
-  int64_t nb = 2LL * num_sms();
+  int64_t nb = 4LL * num_sms();
   int64_t rows = (n + nb - 1) / nb;
   rows = (rows + rpp - 1) / rpp * rpp;
   if (rows < 4 * rpp) rows = 4 * rpp;
@@ -262,7 +321,7 @@ int tsg_bn_stats(const void *x, int dtype, int64_t n, int c, float eps, float mo
   else
     bn_reduce_kernel<__nv_bfloat16, 0><<<nb, BN_THREADS, smem, stream>>>((const __nv_bfloat16 *)x, nullptr, n, c, rows, nullptr,
                                                                         nullptr, (float *)ws);
-  bn_finalize_kernel<<<(c + 7) / 8, 256, 0, stream>>>((const float *)ws, nb, c, eps, momentum, running_mean, running_var, mean,
+  bn_finalize_kernel<<<(c + 31) / 32, 1024, 0, stream>>>((const float *)ws, nb, c, eps, momentum, running_mean, running_var, mean,
                                                          invstd);
   return check_launch("tsg_bn_stats");
 }
@@ -274,7 +333,7 @@ int tsg_bn_apply(const void *x, int dtype, int64_t n, int c, const float *mean, 
     set_error("tsg_bn_apply: need n > 0, c a multiple of 8, fp32 or bf16 rows");
     return TSG_ERR_UNSUPPORTED;
   }
-  const int grid = grid_for(n * (c / 8), BN_THREADS);
+  const int grid = (int)std::min<int64_t>((n + (BN_THREADS / (c / 8)) - 1) / (BN_THREADS / (c / 8)), 16LL * num_sms());
   if (dtype == TSG_F32)
     bn_apply_kernel<float, 0><<<grid, BN_THREADS, 0, stream>>>((const float *)x, nullptr, n, c, mean, invstd, gamma, beta, nullptr,
                                                              (float *)y);
@@ -300,10 +359,10 @@ int tsg_bn_backward(const void *x, const void *dy, int dtype, int64_t n, int c, 
   int64_t rows;
   const int nb = bn_blocks(n, c, &rows);
   const size_t smem = 2 * (size_t)c * (BN_THREADS / (c / 8)) * sizeof(float);
-  const int grid = grid_for(n * (c / 8), BN_THREADS);
+  const int grid = (int)std::min<int64_t>((n + (BN_THREADS / (c / 8)) - 1) / (BN_THREADS / (c / 8)), 16LL * num_sms());
   if (dtype == TSG_F32) {
     bn_reduce_kernel<float, 1><<<nb, BN_THREADS, smem, stream>>>((const float *)x, (const float *)dy, n, c, rows, mean, invstd, (float *)ws);
-    bn_bwd_finalize_kernel<<<(c + 7) / 8, 256, 0, stream>>>((const float *)ws, nb, c, sums);
+    bn_bwd_finalize_kernel<<<(c + 31) / 32, 1024, 0, stream>>>((const float *)ws, nb, c, sums);
     if (dx && training)
       bn_apply_kernel<float, 1><<<grid, BN_THREADS, 0, stream>>>((const float *)x, (const float *)dy, n, c, mean, invstd, gamma, nullptr,
                                                                sums, (float *)dx);
@@ -313,7 +372,7 @@ int tsg_bn_backward(const void *x, const void *dy, int dtype, int64_t n, int c, 
   } else {
     bn_reduce_kernel<__nv_bfloat16, 1><<<nb, BN_THREADS, smem, stream>>>((const __nv_bfloat16 *)x, (const __nv_bfloat16 *)dy, n, c, rows,
                                                                         mean, invstd, (float *)ws);
-    bn_bwd_finalize_kernel<<<(c + 7) / 8, 256, 0, stream>>>((const float *)ws, nb, c, sums);
+    bn_bwd_finalize_kernel<<<(c + 31) / 32, 1024, 0, stream>>>((const float *)ws, nb, c, sums);
     if (dx && training)
       bn_apply_kernel<__nv_bfloat16, 1><<<grid, BN_THREADS, 0, stream>>>((const __nv_bfloat16 *)x, (const __nv_bfloat16 *)dy, n, c, mean,
                                                                        invstd, gamma, nullptr, sums, (__nv_bfloat16 *)dx);
