@@ -379,6 +379,14 @@ int tsg_coord_table_build_dev(const int32_t *coords, int64_t n_cap, const int32_
 int tsg_kmap_build_dev(const void *table, int64_t slots, const int32_t *out_coords, int64_t n_cap, const int32_t *n_dev,
                        const int32_t *offsets_host, int k, int32_t *nbr, int32_t *nbsizes, int32_t *blockcnt,
                        tsg_stream_t stream);
+/* ... the same, also emitting the K-bit "offset k has a neighbour" key of every row (row_keys, n_cap uint64; may be NULL) in the
+ * bit order tsg_kmap_sort_rows sorts by, so that tsg_kmap_sort_rows_dev2 does not re-read the K x n table to build it */
+int tsg_kmap_build_dev2(const void *table, int64_t slots, const int32_t *out_coords, int64_t n_cap, const int32_t *n_dev,
+                        const int32_t *offsets_host, int k, int32_t *nbr, int32_t *nbsizes, int32_t *blockcnt,
+                        uint64_t *row_keys, tsg_stream_t stream);
+int tsg_kmap_sort_rows_dev2(const int32_t *nbr, int k, int64_t n_cap, const int32_t *n_dev, int64_t in_stride, int32_t *perm,
+                            int32_t *nbr_sorted, int64_t out_stride, uint32_t *tile_mask, const uint64_t *row_keys, void *ws,
+                            size_t ws_bytes, tsg_stream_t stream);
 /* nbr (K, n_out_cap) -> nbr_t (K, n_in_cap), -1 where an input row has no output at that offset */
 int tsg_kmap_transpose_dev(const int32_t *nbr, int k, int64_t n_out_cap, const int32_t *n_out_dev, int64_t n_in_cap,
                            int32_t *nbr_t, tsg_stream_t stream);

@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(256) kmap_build_kernel(const Slot *__restrict_
                                                          const int *__restrict__ n_dev, int64_t nbr_stride,
                                                          Offsets offs, int K, int ksplit, int *__restrict__ nbr,
                                                          int *__restrict__ nbsizes, int *__restrict__ blockcnt,
-                                                         int64_t nblk) {
+                                                         int64_t nblk, unsigned long long *__restrict__ row_keys, KeyBits kb) {
   __shared__ int s_cnt[32];
   n_out = dev_count(n_dev, n_out);
   if (threadIdx.x < 32) s_cnt[threadIdx.x] = 0;
@@ -105,6 +105,8 @@ __global__ void __launch_bounds__(256) kmap_build_kernel(const Slot *__restrict_
     ok[r] = o < n_out;
     c[r] = ok[r] ? __ldg(out_coords + o) : make_int4(0, 0, 0, 0);
   }
+  unsigned long long key[4] = {0ull, 0ull, 0ull, 0ull};   // "offset k has a neighbour" bits of the thread's rows (the sort key of
+                                                          // tsg_kmap_sort_rows: emitted here, the rows are in registers anyway)
   for (int k = k0; k < k1; ++k) {
     const int dx = offs.v[3 * k], dy = offs.v[3 * k + 1], dz = offs.v[3 * k + 2];
     int hits = 0;
@@ -116,9 +118,19 @@ __global__ void __launch_bounds__(256) kmap_build_kernel(const Slot *__restrict_
         if (coord_in_range(x, y, z, c[r].w)) found = table_find_coord(tab, mask, pack_coord(x, y, z, c[r].w));
         __stcs(nbr + (int64_t)k * nbr_stride + base + r * 256 + threadIdx.x, found);
       }
+      key[r] |= (unsigned long long)(found >= 0) << kb.pos[k];
       hits += __popc(__ballot_sync(0xffffffffu, found >= 0));
     }
     if ((threadIdx.x & 31) == 0 && hits) atomicAdd(&s_cnt[k - k0], hits);
+  }
+  if (row_keys) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      if (!ok[r]) continue;
+      unsigned long long *dst = row_keys + base + r * 256 + threadIdx.x;
+      if (gridDim.y == 1) *dst = key[r];
+      else if (key[r]) atomicOr(dst, key[r]);       // offsets split over grid.y: the keys were zeroed by the host function
+    }
   }
   __syncthreads();
   if (threadIdx.x < k1 - k0) {
@@ -338,7 +350,7 @@ int64_t tsg_kmap_blocks(int64_t n_out) { return (n_out + KM_ROWS - 1) / KM_ROWS;
 
 static int kmap_build_impl(const void *table, int64_t slots, const int32_t *out_coords, int64_t n_out, const int *n_dev,
                            int64_t nbr_stride, const int32_t *offsets_host, int k, int32_t *nbr, int32_t *nbsizes,
-                           int32_t *blockcnt, cudaStream_t stream) {
+                           int32_t *blockcnt, cudaStream_t stream, unsigned long long *row_keys = nullptr) {
   if (k <= 0 || k > 32 || !pow2(slots)) {
     set_error("tsg_kmap_build: need 1 <= K <= 32 and power-of-two slots");
     return TSG_ERR_INVALID;
@@ -351,9 +363,10 @@ static int kmap_build_impl(const void *table, int64_t slots, const int32_t *out_
   // enough CTAs to cover the chip a few times: split the offsets when the map has few row blocks
   int ksplit = k;
   while (ksplit > 1 && nblk * ((k + ksplit - 1) / ksplit) < 4LL * num_sms()) ksplit = (ksplit + 2) / 3;
+  if (row_keys && ksplit < k) TSG_CUDA(cudaMemsetAsync(row_keys, 0, (size_t)n_out * sizeof(unsigned long long), stream));
   kmap_build_kernel<<<dim3((unsigned)nblk, (unsigned)((k + ksplit - 1) / ksplit)), 256, 0, stream>>>(
       (const Slot *)table, (unsigned long long)(slots - 1), (const int4 *)out_coords, n_out, n_dev, nbr_stride, offs, k, ksplit,
-      nbr, nbsizes, blockcnt, nblk);
+      nbr, nbsizes, blockcnt, nblk, row_keys, key_bits_for(k));
   return check_launch("tsg_kmap_build");
 }
 
@@ -371,6 +384,16 @@ int tsg_kmap_build_dev(const void *table, int64_t slots, const int32_t *out_coor
     return TSG_ERR_INVALID;
   }
   return kmap_build_impl(table, slots, out_coords, n_cap, n_dev, n_cap, offsets_host, k, nbr, nbsizes, blockcnt, stream);
+}
+
+int tsg_kmap_build_dev2(const void *table, int64_t slots, const int32_t *out_coords, int64_t n_cap, const int32_t *n_dev,
+                       const int32_t *offsets_host, int k, int32_t *nbr, int32_t *nbsizes, int32_t *blockcnt,
+                       uint64_t *row_keys, tsg_stream_t stream) {
+  if (!n_dev) {
+    set_error("tsg_kmap_build_dev2: need the device row counter");
+    return TSG_ERR_INVALID;
+  }
+  return kmap_build_impl(table, slots, out_coords, n_cap, n_dev, n_cap, offsets_host, k, nbr, nbsizes, blockcnt, stream, (unsigned long long *)row_keys);
 }
 
 size_t tsg_kmap_pair_list_ws_bytes(int k, int64_t n_rows) { return ((size_t)k * tsg_kmap_blocks(n_rows) + 1) * sizeof(int); }

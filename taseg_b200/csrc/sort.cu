@@ -218,18 +218,6 @@ int sort_pairs(const unsigned long long *keys_in, const unsigned *vals_in, int64
 // static order corners > outer-plane edges > outer face centres > middle-plane corners > middle-plane edges > centre
 // matches the measured frequencies on LiDAR scans (7 / 12 / 18 / 36 / 47 / 100 %) and cuts the active (tile, offset)
 // pairs from 0.40 (plain integer order of the mask) to 0.33; other kernel sizes keep the natural order.
-struct KeyBits {
-  unsigned char pos[32];
-};
-static KeyBits key_bits_for(int K) {
-  KeyBits kb;
-  for (int k = 0; k < 32; ++k) kb.pos[k] = (unsigned char)k;
-  if (K == 27) {
-    static const int order[27] = {0, 2, 6, 8, 18, 20, 24, 26, 1, 3, 5, 7, 19, 21, 23, 25, 4, 22, 9, 11, 15, 17, 10, 12, 14, 16, 13};
-    for (int r = 0; r < 27; ++r) kb.pos[order[r]] = (unsigned char)(26 - r);  // order[0] is the most significant bit
-  }
-  return kb;
-}
 __global__ void row_mask_keys_kernel(const int *__restrict__ nbr, int K, int64_t n_out, const int *__restrict__ n_dev,
                                      int64_t in_stride, KeyBits kb, unsigned long long *__restrict__ keys) {
   n_out = dev_count(n_dev, n_out);
@@ -239,12 +227,18 @@ __global__ void row_mask_keys_kernel(const int *__restrict__ nbr, int K, int64_t
     keys[o] = m;
   }
 }
-// nbr_sorted[k, r] = nbr[k, perm[r]] for r < n_out and -1 in the padding rows [n_out, out_stride)
-__global__ void permute_nbr_kernel(const int *__restrict__ nbr, const int *__restrict__ perm, int K, int64_t n_out,
-                                   const int *__restrict__ n_dev, int64_t in_stride, int64_t out_stride,
-                                   int *__restrict__ nbr_sorted) {
+// nbr_sorted[k, r] = nbr[k, perm[r]] for r < n_out and -1 in the padding rows [n_out, out_stride); the same CTA (256 tile
+// rows = two tiles) ORs the sorted keys of its rows into the two tile masks, key bits mapped back to offsets (one launch
+// instead of two: the 13 mask kernels of a step were ~10 us of launch latency each).
+__global__ void __launch_bounds__(256) permute_nbr_kernel(const int *__restrict__ nbr, const int *__restrict__ perm, int K, int64_t n_out,
+                                                          const int *__restrict__ n_dev, int64_t in_stride, int64_t out_stride,
+                                                          int *__restrict__ nbr_sorted, const unsigned long long *__restrict__ keys_sorted,
+                                                          KeyBits kb, unsigned *__restrict__ tile_mask, int64_t n_tiles) {
+  __shared__ unsigned long long s_or[8];
   n_out = dev_count(n_dev, n_out);
-  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < out_stride; r += (int64_t)gridDim.x * blockDim.x) {
+  const int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  unsigned long long m = r < n_out ? keys_sorted[r] : 0ull;
+  if (r < out_stride) {
     if (r < n_out) {
       const int o = __ldg(perm + r);
       for (int k = 0; k < K; ++k) nbr_sorted[(int64_t)k * out_stride + r] = __ldg(nbr + (int64_t)k * in_stride + o);
@@ -252,27 +246,20 @@ __global__ void permute_nbr_kernel(const int *__restrict__ nbr, const int *__res
       for (int k = 0; k < K; ++k) nbr_sorted[(int64_t)k * out_stride + r] = -1;
     }
   }
-}
-// tile_mask[t] = which offsets occur in tile rows [128 t, 128 t + 128): OR of the SORTED keys, key bits mapped back to offsets
-__global__ void __launch_bounds__(128) tile_mask_from_keys_kernel(const unsigned long long *__restrict__ keys_sorted,
-                                                                  int64_t n_out, const int *__restrict__ n_dev,
-                                                                  KeyBits kb, int K, unsigned *__restrict__ tile_mask) {
-  __shared__ unsigned long long s_or[4];
-  n_out = dev_count(n_dev, n_out);
-  const int64_t r = (int64_t)blockIdx.x * 128 + threadIdx.x;
-  unsigned long long m = r < n_out ? keys_sorted[r] : 0ull;
 #pragma unroll
   for (int o = 16; o; o >>= 1) m |= __shfl_xor_sync(0xffffffffu, m, o);
   if ((threadIdx.x & 31) == 0) s_or[threadIdx.x >> 5] = m;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    m = s_or[0] | s_or[1] | s_or[2] | s_or[3];
-    unsigned out = 0;
-    for (int k = 0; k < K; ++k) out |= (unsigned)((m >> kb.pos[k]) & 1ull) << k;
-    tile_mask[blockIdx.x] = out;
+  if (threadIdx.x < 2) {
+    const int64_t tile = (int64_t)blockIdx.x * 2 + threadIdx.x;
+    if (tile < n_tiles) {
+      const unsigned long long mm = s_or[4 * threadIdx.x] | s_or[4 * threadIdx.x + 1] | s_or[4 * threadIdx.x + 2] | s_or[4 * threadIdx.x + 3];
+      unsigned out = 0;
+      for (int k = 0; k < K; ++k) out |= (unsigned)((mm >> kb.pos[k]) & 1ull) << k;
+      tile_mask[tile] = out;
+    }
   }
 }
-
 // ---------------------------------------------------------------- unique voxels
 // fb = bit widths of (x, y, z, b) when the caller knows every coordinate lies in [0, 2^bits): keys are then packed
 // densely so the sort needs ceil(sum/8) passes instead of 8; fb.x == 0 selects the general 64-bit packing.
@@ -474,7 +461,7 @@ int64_t tsg_kmap_sort_stride(int64_t n_out) { return (n_out + 255) / 256 * 256; 
 
 static int kmap_sort_rows_impl(const int32_t *nbr, int k, int64_t n_out, const int *n_dev, int64_t in_stride, int32_t *perm,
                                int32_t *nbr_sorted, int64_t out_stride, uint32_t *tile_mask, void *ws, size_t ws_bytes,
-                               cudaStream_t stream) {
+                               cudaStream_t stream, const unsigned long long *row_keys = nullptr) {
   if (out_stride < n_out) {
     set_error("tsg_kmap_sort_rows: out_stride < n_out");
     return TSG_ERR_INVALID;
@@ -492,12 +479,14 @@ static int kmap_sort_rows_impl(const int32_t *nbr, int k, int64_t n_out, const i
   unsigned long long *keys = (unsigned long long *)base;
   unsigned long long *keys_sorted = (unsigned long long *)(base + align256((size_t)n_out * 8));
   char *sort_ws = base + 2 * align256((size_t)n_out * 8);
-  row_mask_keys_kernel<<<grid_for(n_out, 256), 256, 0, stream>>>(nbr, k, n_out, n_dev, in_stride, key_bits_for(k), keys);
+  if (row_keys) keys = const_cast<unsigned long long *>(row_keys);   // emitted by the kernel-map build (tsg_kmap_build_dev2)
+  else row_mask_keys_kernel<<<grid_for(n_out, 256), 256, 0, stream>>>(nbr, k, n_out, n_dev, in_stride, key_bits_for(k), keys);
   const int rc = sort_pairs(keys, nullptr, n_out, 0, k, keys_sorted, (unsigned *)perm, sort_ws,
                             ws_bytes - 2 * align256((size_t)n_out * 8), stream, n_dev);
   if (rc != TSG_OK) return rc;
-  permute_nbr_kernel<<<grid_for(out_stride, 256), 256, 0, stream>>>(nbr, perm, k, n_out, n_dev, in_stride, out_stride, nbr_sorted);
-  tile_mask_from_keys_kernel<<<(unsigned)((n_out + 127) / 128), 128, 0, stream>>>(keys_sorted, n_out, n_dev, key_bits_for(k), k, tile_mask);
+  const int64_t n_tiles = (n_out + 127) / 128, rows = out_stride > n_tiles * 128 ? out_stride : n_tiles * 128;
+  permute_nbr_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, stream>>>(nbr, perm, k, n_out, n_dev, in_stride, out_stride, nbr_sorted,
+                                                                       keys_sorted, key_bits_for(k), tile_mask, n_tiles);
   return check_launch("tsg_kmap_sort_rows");
 }
 
@@ -510,6 +499,13 @@ int tsg_kmap_sort_rows_dev(const int32_t *nbr, int k, int64_t n_cap, const int32
                            int32_t *nbr_sorted, int64_t out_stride, uint32_t *tile_mask, void *ws, size_t ws_bytes,
                            tsg_stream_t stream) {
   return kmap_sort_rows_impl(nbr, k, n_cap, n_dev, in_stride, perm, nbr_sorted, out_stride, tile_mask, ws, ws_bytes, stream);
+}
+
+int tsg_kmap_sort_rows_dev2(const int32_t *nbr, int k, int64_t n_cap, const int32_t *n_dev, int64_t in_stride, int32_t *perm,
+                            int32_t *nbr_sorted, int64_t out_stride, uint32_t *tile_mask, const uint64_t *row_keys, void *ws,
+                            size_t ws_bytes, tsg_stream_t stream) {
+  return kmap_sort_rows_impl(nbr, k, n_cap, n_dev, in_stride, perm, nbr_sorted, out_stride, tile_mask, ws, ws_bytes, stream,
+                             (const unsigned long long *)row_keys);
 }
 
 size_t tsg_unique_ws_bytes(int64_t n) { return unique_ws_layout(n > 0 ? n : 1, nullptr, nullptr); }

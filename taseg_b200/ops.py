@@ -212,8 +212,9 @@ def table_from_coords_dev(coords: torch.Tensor, n_dev: torch.Tensor, status: tor
     return t
 
 
-def build_kmap_dev(table: Table, out_coords: torch.Tensor, n_dev: torch.Tensor, offsets: np.ndarray) -> torch.Tensor:
-    """nbr (K, cap) int32 of the first *n_dev output rows (rows beyond are left untouched)."""
+def build_kmap_dev(table: Table, out_coords: torch.Tensor, n_dev: torch.Tensor, offsets: np.ndarray, want_keys: bool = False):
+    """nbr (K, cap) int32 of the first *n_dev output rows (rows beyond are left untouched); with want_keys also the rows'
+    neighbour-mask sort keys (cap,) int64 for kmap_sort_rows_dev(row_keys=...)."""
     cap = out_coords.shape[0]
     offs = np.ascontiguousarray(offsets, dtype=np.int32)
     k = offs.shape[0]
@@ -221,9 +222,10 @@ def build_kmap_dev(table: Table, out_coords: torch.Tensor, n_dev: torch.Tensor, 
     nbr = torch.empty((k, cap), dtype=torch.int32, device=dev)
     nbsizes = torch.empty((k,), dtype=torch.int32, device=dev)
     blockcnt = torch.empty((k * max(int(L.lib().tsg_kmap_blocks(cap)), 1),), dtype=torch.int32, device=dev)
-    call("tsg_kmap_build_dev", ptr(table.buf), table.slots, ptr(out_coords), cap, ptr(n_dev),
-         offs.ctypes.data_as(ctypes.c_void_p), k, ptr(nbr), ptr(nbsizes), ptr(blockcnt), stream())
-    return nbr
+    keys = torch.empty((cap,), dtype=torch.int64, device=dev) if want_keys else None
+    call("tsg_kmap_build_dev2", ptr(table.buf), table.slots, ptr(out_coords), cap, ptr(n_dev),
+         offs.ctypes.data_as(ctypes.c_void_p), k, ptr(nbr), ptr(nbsizes), ptr(blockcnt), ptr(keys), stream())
+    return (nbr, keys) if want_keys else nbr
 
 
 def kmap_transpose_dev(nbr: torch.Tensor, n_out_dev: torch.Tensor, n_in_cap: int) -> torch.Tensor:
@@ -233,8 +235,9 @@ def kmap_transpose_dev(nbr: torch.Tensor, n_out_dev: torch.Tensor, n_in_cap: int
     return out
 
 
-def kmap_sort_rows_dev(nbr: torch.Tensor, n_dev: torch.Tensor):
-    """(nbr_sorted (K, stride), tile_mask, perm) of a capacity-sized table, as KernelMap.sorted()."""
+def kmap_sort_rows_dev(nbr: torch.Tensor, n_dev: torch.Tensor, row_keys: Optional[torch.Tensor] = None):
+    """(nbr_sorted (K, stride), tile_mask, perm) of a capacity-sized table, as KernelMap.sorted().  row_keys: the keys
+    build_kmap_dev(want_keys=True) emitted for this table."""
     k, cap = nbr.shape
     dev = nbr.device
     perm = torch.empty((cap,), dtype=torch.int32, device=dev)
@@ -243,8 +246,8 @@ def kmap_sort_rows_dev(nbr: torch.Tensor, n_dev: torch.Tensor):
     mask = torch.empty(((cap + 127) // 128,), dtype=torch.int32, device=dev)
     ws_bytes = int(L.lib().tsg_kmap_sort_ws_bytes(cap))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    call("tsg_kmap_sort_rows_dev", ptr(nbr), k, cap, ptr(n_dev), cap, ptr(perm), ptr(nbr_s), stride, ptr(mask), ptr(ws), ws_bytes,
-         stream())
+    call("tsg_kmap_sort_rows_dev2", ptr(nbr), k, cap, ptr(n_dev), cap, ptr(perm), ptr(nbr_s), stride, ptr(mask), ptr(row_keys),
+         ptr(ws), ws_bytes, stream())
     return nbr_s, mask, perm
 
 

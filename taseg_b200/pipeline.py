@@ -52,13 +52,14 @@ class GeometryDev:
             lv.stride, lv.coords, lv.n, lv.n_dev = 2 ** l, coords[l], caps[l], counters[l]
             lv.km3 = lv.km2 = lv.m2 = lv.m2t = None
             lv.table = ops.table_from_coords_dev(coords[l], counters[l], status)
-            nbr3 = ops.build_kmap_dev(lv.table, coords[l], counters[l], kernel_offsets_np(3, lv.stride))
-            lv.m3 = ops.kmap_sort_rows_dev(nbr3, counters[l])
+            nbr3, keys3 = ops.build_kmap_dev(lv.table, coords[l], counters[l], kernel_offsets_np(3, lv.stride), want_keys=True)
+            lv.m3 = ops.kmap_sort_rows_dev(nbr3, counters[l], row_keys=keys3)
             if ops.SplitItems.wanted(caps[l], 27):      # few tiles per SM: K-split work items balance the launch
                 lv.m3 = lv.m3 + (ops.SplitItems(lv.m3[1], caps[l], 27, n_dev=counters[l]),)
             if l + 1 < n_levels:
-                nbr2 = ops.build_kmap_dev(lv.table, coords[l + 1], counters[l + 1], kernel_offsets_np(2, lv.stride))
-                lv.m2 = ops.kmap_sort_rows_dev(nbr2, counters[l + 1])
+                nbr2, keys2 = ops.build_kmap_dev(lv.table, coords[l + 1], counters[l + 1], kernel_offsets_np(2, lv.stride),
+                                                 want_keys=True)
+                lv.m2 = ops.kmap_sort_rows_dev(nbr2, counters[l + 1], row_keys=keys2)
                 nbr2t = ops.kmap_transpose_dev(nbr2, counters[l + 1], caps[l])
                 lv.m2t = ops.kmap_sort_rows_dev(nbr2t, counters[l])
             self.levels.append(lv)

@@ -468,8 +468,7 @@ def test_conv_tensor_core_k_split(ts):
     assert 64 * 128 < n <= ops.SPLIT_MAX_TILES * 128
     km = ops.build_kmap(ops.Table.from_coords(cu(c)), n, cu(c), T.get_kernel_offsets(3, 1))
     nbr_s, mask_s, perm = km.sorted()
-    sp = km.split_items()
-    assert sp is not None
+    sp = ops.SplitItems(mask_s, n, 27)        # (KernelMap.split_items() returns it only when TSG_SPLIT_K=1: off by default)
     n_items = int(sp.n_items.item())
     items = npy(sp.items[:n_items])
     tiles = (n + 127) // 128
