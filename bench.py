@@ -151,6 +151,9 @@ def cpu_arm(steps, warmup, seed=2000):
     t = statistics.median(times)
     sample = ("one 3-frame scan restricted to a %.1f deg azimuth sector (1/%d of the rays, %d voxels); "
               "scans/s = (1/%d scan)/t, t = median of %d runs" % (360 * SECTOR, round(1 / SECTOR), nvox, round(1 / SECTOR), len(times)))
+    if SECTOR < 1.0:    # the extrapolation was checked against a whole scan once (TSG_BENCH_CPU_SECTORS=1): committed record
+        sample += ("; recorded check on a whole scan (190075 voxels): 87.5 s = 0.01142 scans/s vs 0.01172 from the sector "
+                   "(profiles/r02/cpu_reference_full_scan.json)")
     return dict(value=SECTOR / t, unit=UNIT, cores=cores, kind=kind, sample=sample, seconds_per_sample=t)
 
 

@@ -541,6 +541,23 @@ def test_conv_tensor_core_vs_oracle(ts):
     packed_t = ops.pack_weights(w.float().transpose(1, 2).contiguous(), 96)
     gx = ops.conv_forward_tc(gy, None, packed_t, 27, 64, km.nbr_t, km.tile_mask(True), n, out_dtype=torch.float32)
     assert rel_err(npy(gx), gx_ref) < 1e-3
+    # ... and as the training path stores it (bf16 rows): per-layer bound of the bf16 data gradient, relative l2 <= 1e-2
+    gx16 = ops.conv_forward_tc(gy, None, packed_t, 27, 64, km.nbr_t, km.tile_mask(True), n, out_dtype=torch.bfloat16)
+    d = npy(gx16.float()).astype(np.float64) - gx_ref
+    assert np.linalg.norm(d) / np.linalg.norm(gx_ref) < 1e-2
+    # the autograd function end to end (padded 5-channel stem, 384-channel column blocks) against the oracle's backward
+    from taseg_b200.nn.functional.conv import ConvolutionFunction
+    for c_in, c_out in [(5, 32), (384, 256)]:
+        xi = torch.randn(n, c_in, device="cuda").bfloat16().requires_grad_(True)
+        wi = (torch.randn(27, c_in, c_out, device="cuda") * 0.05).bfloat16().requires_grad_(True)
+        go = torch.randn(n, c_out, device="cuda").bfloat16()
+        yo = ConvolutionFunction.apply(xi, wi, km, False, None)
+        yo.backward(go)
+        want_y = T.conv_forward(npy(xi.detach().float()), npy(wi.detach().float()), nbmaps, nbsizes, (n, n), False)
+        want_gx, want_gw = T.conv_backward(npy(xi.detach().float()), npy(go.float()), npy(wi.detach().float()), nbmaps, nbsizes, False)
+        for got_t, want_t in ((yo, want_y), (xi.grad, want_gx), (wi.grad, want_gw)):
+            dd = npy(got_t.detach().float()).astype(np.float64) - want_t
+            assert np.linalg.norm(dd) / np.linalg.norm(want_t) < 1e-2, (c_in, c_out)
 
 
 @pytest.mark.parametrize("c0,span", [(16, 160), (32, 160), (32, 60), (96, 160)])
