@@ -43,6 +43,33 @@ def _tc_ok(feats: torch.Tensor, c_in: int, c_out: int) -> bool:
     return feats.dtype == torch.bfloat16 and c_out % 16 == 0
 
 
+# fp32 tensors (train.py without --amp, fp32 evaluation through the module path) on the TENSOR cores: every operand is split
+# into two bf16 terms, x = xh + xl and w = wh + wl (16 mantissa bits together), and
+#   y = xh wh + xl wh + xh wl        (fp32 accumulation in TMEM; the dropped xl wl term is ~2^-16 relative)
+# is two launches of the bf16 kernel with fp32 output: (xh | xl) against (wh ; wh) — the kernel's two-tensor K split — and
+# xh against wl.  Error ~2e-5 relative, inside the fp32 parity bar (1e-3) and 10x faster than the CUDA-core FMA kernel at
+# benchmark sizes.  TSG_FP32_SPLIT=0 restores the exact fp32 kernels.
+import os as _os
+
+FP32_SPLIT = _os.environ.get("TSG_FP32_SPLIT", "1") != "0"
+
+
+def _split_bf16(t: torch.Tensor):
+    hi = t.to(torch.bfloat16)
+    lo = (t - hi.float()).to(torch.bfloat16)
+    return hi, lo
+
+
+def _fp32_split_ok(feats: torch.Tensor, c_out: int) -> bool:
+    """fp32 rows the split path takes: the two-tensor K split (xh | xl) must fit the kernel's slice plan (<= 16 slices per
+    group of offsets: every channel count of the TASeg networks does; e.g. 272 channels do not)."""
+    if not (FP32_SPLIT and feats.is_cuda and feats.dtype == torch.float32 and c_out % 16 == 0 and feats.shape[0] > 0):
+        return False
+    import math
+    cpo = 2 * ((feats.shape[1] + 15) // 16 * 16) // 8
+    return cpo // math.gcd(cpo, 8) <= 16
+
+
 def _col_blocks(c_out: int):
     """Output-channel blocks of at most 256 (multiples of 16) the tensor-core kernel is launched over."""
     nb = (c_out + 255) // 256
@@ -80,6 +107,57 @@ def packed_weights(param: Optional[torch.Tensor], weight: torch.Tensor, transpos
     return packed
 
 
+def _pack_split(w: torch.Tensor, cols):
+    """(K, c_in, c_out) fp32 -> packed images of (wh ; wh) for the (xh | xl) launch and of wl, columns cols, c_in padded to 16."""
+    k, c_in, c_out = w.shape
+    w = w[:, :, cols[0]:cols[1]]
+    if c_in % 16:
+        w = torch.nn.functional.pad(w, (0, 0, 0, 16 - c_in % 16))
+    wh, wl = _split_bf16(w)
+    c = w.shape[1]
+    return (ops.pack_weights(torch.cat([wh, wh], dim=1).float().contiguous(), c, c), ops.pack_weights(wl.float().contiguous(), c))
+
+
+def _conv_tc_fp32(feats: torch.Tensor, param, weight: torch.Tensor, transposed_w: bool, kmap: ops.KernelMap, map_transposed: bool,
+                  n_out: int) -> torch.Tensor:
+    """fp32 in, fp32 out through three bf16 products on the tensor cores (see FP32_SPLIT above)."""
+    k = weight.shape[0]
+    c_in, c_out = (weight.shape[2], weight.shape[1]) if transposed_w else (weight.shape[1], weight.shape[2])
+    if c_in % 16:
+        feats = torch.nn.functional.pad(feats, (0, 16 - c_in % 16))
+    xh, xl = _split_bf16(feats.contiguous())
+    nbr_s, mask_s, perm = kmap.sorted(map_transposed)
+    outs = []
+    for cols in _col_blocks(c_out):
+        key = (id(param), transposed_w, cols, "split") if param is not None else None
+        hit = _PACKS.get(key) if key is not None else None
+        if hit is not None and hit[0] == param._version and hit[1] == param.data_ptr():
+            p_hh, p_l = hit[2]
+        else:
+            w = (param if param is not None else weight).detach().float()
+            p_hh, p_l = _pack_split(w.transpose(1, 2) if transposed_w else w, cols)
+            if key is not None:
+                _PACKS[key] = (param._version, param.data_ptr(), (p_hh, p_l))
+        n_c = cols[1] - cols[0]
+        y = ops.conv_forward_tc(xh, xl, p_hh, k, n_c, nbr_s, mask_s, n_out, perm=perm, out_dtype=torch.float32)
+        y += ops.conv_forward_tc(xh, None, p_l, k, n_c, nbr_s, mask_s, n_out, perm=perm, out_dtype=torch.float32)
+        outs.append(y)
+    return outs[0] if len(outs) == 1 else torch.cat(outs, dim=1)
+
+
+def _wgrad_tc_fp32(x: torch.Tensor, gy: torch.Tensor, nbr: torch.Tensor, k: int) -> torch.Tensor:
+    """fp32 weight gradient as three bf16 pair-list GEMMs: xh gh + xl gh + xh gl."""
+    c_in = x.shape[1]
+    if c_in % 8:
+        x = torch.nn.functional.pad(x, (0, 8 - c_in % 8))
+    xh, xl = _split_bf16(x.contiguous())
+    gh, gl = _split_bf16(gy.contiguous())
+    gw = ops.conv_wgrad_tc(xh, gh, nbr, k)
+    gw += ops.conv_wgrad_tc(xl, gh, nbr, k)
+    gw += ops.conv_wgrad_tc(xh, gl, nbr, k)
+    return gw[:, :c_in]
+
+
 def _conv_tc(feats: torch.Tensor, param, weight: torch.Tensor, transposed_w: bool, kmap: ops.KernelMap, map_transposed: bool,
              n_out: int) -> torch.Tensor:
     """out = conv(feats, W or W^T) on the tensor cores over the (mask-sorted) map; bf16 in, bf16 out."""
@@ -108,6 +186,8 @@ class ConvolutionFunction(Function):
         k, c_in, c_out = weight.shape
         if _tc_ok(input, c_in, c_out):
             out = _conv_tc(input, param, weight, False, kmap, transposed, n_out)
+        elif _fp32_split_ok(input, c_out):
+            out = _conv_tc_fp32(input, param, weight, False, kmap, transposed, n_out)
         else:
             out = ops.conv_forward(input, weight, nbr, n_out)
         ctx.for_backwards = (input, weight, kmap, transposed, param)
@@ -125,6 +205,8 @@ class ConvolutionFunction(Function):
             # dgrad = the same tensor-core kernel over the transposed table with W[k]^T (bf16 operands, fp32 accumulate)
             grad_input = _conv_tc(grad_output.contiguous().to(torch.bfloat16), param, weight, True, kmap, not transposed,
                                   input.shape[0])
+        elif ctx.needs_input_grad[0] and _fp32_split_ok(grad_output, c_in):
+            grad_input = _conv_tc_fp32(grad_output, param, weight, True, kmap, not transposed, input.shape[0])
         elif ctx.needs_input_grad[0]:
             grad_input = ops.conv_dgrad(grad_output, weight, tab_out_of_in, input.shape[0]).to(input.dtype)
         else:
@@ -134,6 +216,9 @@ class ConvolutionFunction(Function):
             grad_weight = ops.conv_wgrad_tc(x, grad_output, tab_in_of_out, k)[:, :c_in].to(weight.dtype)
         elif input.dtype == torch.bfloat16 and c_in % 8 == 0 and c_out % 8 == 0:
             grad_weight = ops.conv_wgrad_bf16(input, grad_output, tab_in_of_out, k).to(weight.dtype)
+        elif (FP32_SPLIT and ops.WGRAD_TC and input.is_cuda and input.dtype == torch.float32 and grad_output.dtype == torch.float32
+              and c_out % 8 == 0 and c_out <= 256 and input.shape[0] > 0):
+            grad_weight = _wgrad_tc_fp32(input, grad_output, tab_in_of_out, k).to(weight.dtype)
         else:
             grad_weight = ops.conv_wgrad(input, grad_output, tab_in_of_out, k).to(weight.dtype)
         return grad_input, grad_weight, None, None, None

@@ -560,6 +560,37 @@ def test_conv_tensor_core_vs_oracle(ts):
             assert np.linalg.norm(dd) / np.linalg.norm(want_t) < 1e-2, (c_in, c_out)
 
 
+def test_conv_fp32_split_precision(ts, monkeypatch):
+    """fp32 tensors through the module path run on the tensor cores as three bf16 products (x = xh + xl, w = wh + wl;
+    nn/functional/conv.py FP32_SPLIT): forward, data gradient and weight gradient against the oracle (fp32 arithmetic) at
+    <= 1e-4 — a tenth of the fp32 parity bar — and the exact CUDA-core kernels stay available (TSG_FP32_SPLIT=0)."""
+    from taseg_b200 import ops
+    from taseg_b200.nn.functional import conv as C
+    rng = np.random.default_rng(17)
+    c = np.unique(rng.integers(0, 22, (5000, 3)).astype(np.int32), axis=0)
+    c = np.concatenate([c, np.zeros((len(c), 1), np.int32)], 1)
+    n = len(c)
+    km = ops.build_kmap(ops.Table.from_coords(cu(c)), n, cu(c), T.get_kernel_offsets(3, 1))
+    nbmaps, nbsizes = npy(km.nbmaps), npy(km.nbsizes)
+    assert C.FP32_SPLIT
+    for c_in, c_out in [(5, 32), (96, 96), (320, 272)]:
+        x = torch.randn(n, c_in, device="cuda").requires_grad_(True)
+        w = (torch.randn(27, c_in, c_out, device="cuda") * 0.05).requires_grad_(True)
+        gy = torch.randn(n, c_out, device="cuda")
+        y = C.ConvolutionFunction.apply(x, w, km, False, None)
+        y.backward(gy)
+        want_y = T.conv_forward(npy(x.detach()), npy(w.detach()), nbmaps, nbsizes, (n, n), False)
+        want_gx, want_gw = T.conv_backward(npy(x.detach()), npy(gy), npy(w.detach()), nbmaps, nbsizes, False)
+        assert y.dtype == torch.float32
+        assert rel_err(npy(y.detach()), want_y) < 1e-4, (c_in, c_out)
+        assert rel_err(npy(x.grad), want_gx) < 1e-4 and rel_err(npy(w.grad), want_gw) < 1e-4, (c_in, c_out)
+    monkeypatch.setattr(C, "FP32_SPLIT", False)
+    x = torch.randn(n, 32, device="cuda")
+    w = torch.randn(27, 32, 32, device="cuda") * 0.05
+    y = C.ConvolutionFunction.apply(x, w, km, False, None)
+    assert rel_err(npy(y), T.conv_forward(npy(x), npy(w), nbmaps, nbsizes, (n, n), False)) < 1e-5
+
+
 @pytest.mark.parametrize("c0,span", [(16, 160), (32, 160), (32, 60), (96, 160)])
 def test_conv_tensor_core_many_light_tiles(ts, c0, span):
     """Hundreds of super tiles per SM-wave with only one or two pipeline stages each (two sub-tiles per CTA, packed K
