@@ -31,7 +31,8 @@ BATCH = 4
 N_FRAMES = 3
 VOXEL = 0.05
 SECTOR = 1.0 / float(os.environ.get("TSG_BENCH_CPU_SECTORS", "16"))      # bounded sample for the CPU arms (1 = the whole scan, ~2 min)
-N_STREAMS = int(os.environ.get("TSG_BENCH_STREAMS", "3"))   # batches in flight (1 = strictly one batch at a time)
+N_STREAMS = int(os.environ.get("TSG_BENCH_STREAMS", "5"))   # batches in flight (1 = strictly one batch at a time; measured 3: 934-947,
+                                                            # 4: 944, 5: 964-976, 6: 949, 8: 894 scans/s — profiles/r02/ab_bench.txt)
 EAGER = os.environ.get("TSG_BENCH_EAGER", "0") == "1"        # A/B: round-1 eager path instead of the captured pipeline
 WORKLOAD = ("configs[1]: TASeg MinkUNetMs mk34 cr1.0 (IN_FEATURE_DIM 5, 20 classes), 3-frame temporal aggregation, "
             "SemanticKITTI shape (64x2048 rays/scan, 0.05 m voxels), batch 4 per GPU")
