@@ -42,7 +42,12 @@ struct WgradParams {
   int dbg;   // TSG_WG_DEBUG knock-outs for profiling (wrong results): 1 no gathers, 2 no MMAs, 4 no epilogue stores
 };
 
-__device__ long long g_wg_prof[8];   // TSG_WG_DEBUG & 64: cycle totals of CTA 0 (gather: wait empty, issue; MMA: wait full, issue; chunks; total)
+__device__ long long g_wg_prof[8];   // trace build, TSG_WG_DEBUG & 64: cycle totals of CTA 0 (gather: wait empty, issue; MMA: wait full, issue; chunks; total)
+#ifdef TSG_TC_TRACE
+#define WG_CLOCK() clock64()
+#else
+#define WG_CLOCK() 0ll
+#endif
 
 __global__ void __launch_bounds__(WT_THREADS) conv_wgrad_tc_kernel(const WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -108,9 +113,9 @@ __global__ void __launch_bounds__(WT_THREADS) conv_wgrad_tc_kernel(const WgradPa
       Ring r;
       long long t_wait = 0, t_issue = 0;
       for (int c = 0; c < n_chunks; ++c) {
-        const long long t0 = clock64();
+        const long long t0 = WG_CLOCK();
         mbar_wait(full0 + 8 * r.slot, r.phase);
-        const long long t1 = clock64();
+        const long long t1 = WG_CLOCK();
         t_wait += t1 - t0;
         fence_async_proxy();
         tc_fence_after();
@@ -125,7 +130,7 @@ __global__ void __launch_bounds__(WT_THREADS) conv_wgrad_tc_kernel(const WgradPa
         }
         umma_commit(empty0 + 8 * r.slot);
         r.advance(WT_STAGES);
-        t_issue += clock64() - t1;
+        t_issue += WG_CLOCK() - t1;
       }
       umma_commit(done);   // every MMA of this unit has completed
       if ((p.dbg & 64) && blockIdx.x == 0 && blockIdx.y == 0) {
@@ -169,14 +174,14 @@ __global__ void __launch_bounds__(WT_THREADS) conv_wgrad_tc_kernel(const WgradPa
     int pr_next = load_pair(0), pr_next2 = load_pair(1);
     Ring r;
     long long t_wait = 0, t_issue = 0;
-    const long long t_begin = clock64();
+    const long long t_begin = WG_CLOCK();
     for (int c = 0; c < n_chunks; ++c) {
       const int pr = pr_next;
       pr_next = pr_next2;
       pr_next2 = load_pair(c + 2);         // indices travel two chunks ahead of the gather that uses them
-      const long long t0 = clock64();
+      const long long t0 = WG_CLOCK();
       mbar_wait(empty0 + 8 * r.slot, r.phase ^ 1);
-      const long long t1 = clock64();
+      const long long t1 = WG_CLOCK();
       t_wait += t1 - t0;
       const uint32_t st0 = smem_base + r.slot * stage_bytes + (uint32_t)warp * 128u;
 #pragma unroll
@@ -195,12 +200,12 @@ __global__ void __launch_bounds__(WT_THREADS) conv_wgrad_tc_kernel(const WgradPa
       }
       cp_async_arrive(full0 + 8 * r.slot);   // fires once this thread's copies have landed
       r.advance(WT_STAGES);
-      t_issue += clock64() - t1;
+      t_issue += WG_CLOCK() - t1;
     }
     if ((p.dbg & 64) && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) {
       g_wg_prof[0] = t_wait;
       g_wg_prof[1] = t_issue;
-      g_wg_prof[5] = clock64() - t_begin;
+      g_wg_prof[5] = WG_CLOCK() - t_begin;
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
 
