@@ -287,16 +287,19 @@ int tsg_conv_wgrad_tc(const void *in, int64_t n_in, int c_in, const void *grad_o
  * partials combined in double precision in a fixed order; no floating-point atomics on global memory).
  *   tsg_bn_stats:    batch mean / invstd = 1 / sqrt(biased var + eps); running statistics updated in place when given
  *                    (momentum, unbiased variance — nn.BatchNorm1d's rule)
- *   tsg_bn_apply:    y = (x - mean) invstd gamma + beta   (evaluation: mean / invstd derived from the running statistics)
+ *   tsg_bn_apply:    y = (x - mean) invstd gamma + beta   (evaluation: mean / invstd derived from the running statistics);
+ *                    relu != 0 fuses the ReLU that follows every BatchNorm of a convolution block (blocks: conv, BN, ReLU —
+ *                    R/pcseg/model/segmentor/voxel/minkunet/minkunet.py:23-60) into the same pass, forward and backward
  *   tsg_bn_backward: sums = {dbeta, dgamma}; dx = gamma invstd (dy - dbeta / n - xhat dgamma / n)  (training) or
  *                    gamma invstd dy (evaluation) */
 size_t tsg_bn_ws_bytes(int64_t n, int c);
 int tsg_bn_stats(const void *x, int dtype, int64_t n, int c, float eps, float momentum, float *running_mean, float *running_var,
                  float *mean, float *invstd, void *ws, size_t ws_bytes, tsg_stream_t stream);
 int tsg_bn_apply(const void *x, int dtype, int64_t n, int c, const float *mean, const float *invstd, const float *gamma,
-                 const float *beta, void *y, tsg_stream_t stream);
+                 const float *beta, int relu, void *y, tsg_stream_t stream);
 int tsg_bn_backward(const void *x, const void *dy, int dtype, int64_t n, int c, const float *mean, const float *invstd,
-                    const float *gamma, int training, float *sums, void *dx, void *ws, size_t ws_bytes, tsg_stream_t stream);
+                    const float *gamma, const float *beta, int relu, int training, float *sums, void *dx, void *ws, size_t ws_bytes,
+                    tsg_stream_t stream);
 
 /* tcgen05/TMEM path (bf16 operands, fp32 accumulate in tensor memory).
  * Weights are packed once per layer into the shared-memory image the MMA consumes (128B-swizzled K-major

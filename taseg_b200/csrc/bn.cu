@@ -62,12 +62,13 @@ __device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16 *p, const fl
 template <typename T, int MODE>
 __global__ void __launch_bounds__(BN_THREADS) bn_reduce_kernel(const T *__restrict__ x, const T *__restrict__ dy, int64_t n, int c,
                                                                int64_t rows_per_cta, const float *__restrict__ mean,
-                                                               const float *__restrict__ invstd, float *__restrict__ partial) {
+                                                               const float *__restrict__ invstd, const float *__restrict__ gamma,
+                                                               const float *__restrict__ beta, int relu, float *__restrict__ partial) {
   extern __shared__ float s_acc[];   // [rpp][2][c]: every thread's sums, added up in a fixed order below
   const int tpr = c / 8, rpp = BN_THREADS / tpr;
   const int rt = threadIdx.x / tpr, cg = threadIdx.x - rt * tpr;
   const int64_t r0 = blockIdx.x * rows_per_cta, r1 = min(n, r0 + rows_per_cta);
-  float a[8], b[8], mu[8], is[8];
+  float a[8], b[8], mu[8], is[8], ga[8], be[8];   // ga / be: only for the ReLU mask of a fused BatchNorm + ReLU (MODE 1)
 #pragma unroll
   for (int j = 0; j < 8; ++j) a[j] = b[j] = 0.f;
   if (rt < rpp) {
@@ -76,6 +77,8 @@ __global__ void __launch_bounds__(BN_THREADS) bn_reduce_kernel(const T *__restri
       for (int j = 0; j < 8; ++j) {
         mu[j] = mean[cg * 8 + j];
         is[j] = invstd[cg * 8 + j];
+        ga[j] = (relu && gamma) ? gamma[cg * 8 + j] : 1.f;
+        be[j] = (relu && beta) ? beta[cg * 8 + j] : 0.f;
       }
     }
     // four rows per trip: the loads are independent, so a thread keeps 4 (8 with dy) 16-byte requests in flight — with one
@@ -105,8 +108,10 @@ __global__ void __launch_bounds__(BN_THREADS) bn_reduce_kernel(const T *__restri
             a[j] += v[u][j];
             b[j] = fmaf(v[u][j], v[u][j], b[j]);
           } else {
-            a[j] += g[u][j];
-            b[j] = fmaf(g[u][j], (v[u][j] - mu[j]) * is[j], b[j]);
+            const float xh = (v[u][j] - mu[j]) * is[j];
+            const float gj = (relu && fmaf(xh, ga[j], be[j]) <= 0.f) ? 0.f : g[u][j];   // dy through the fused ReLU
+            a[j] += gj;
+            b[j] = fmaf(gj, xh, b[j]);
           }
         }
       }
@@ -225,21 +230,23 @@ template <typename T, int MODE>
 __global__ void __launch_bounds__(BN_THREADS) bn_apply_kernel(const T *__restrict__ x, const T *__restrict__ dy, int64_t n, int c,
                                                               const float *__restrict__ mean, const float *__restrict__ invstd,
                                                               const float *__restrict__ gamma, const float *__restrict__ beta,
-                                                              const float *__restrict__ sums, T *__restrict__ out) {
+                                                              const float *__restrict__ sums, int relu, T *__restrict__ out) {
   // A thread keeps ONE channel group for the whole pass (its 8 scales / shifts live in registers) and walks rows
   // rt, rt + rows_in_flight, ...: consecutive threads still read consecutive 16-byte vectors of a row.
   const int tpr = c / 8, rpp = BN_THREADS / tpr;
   const int rt = threadIdx.x / tpr, cg = threadIdx.x - rt * tpr;
   if (rt >= rpp) return;
   const float inv_n = 1.f / (float)n;
-  float sc[8], sh[8], k2[8];   // MODE 0: y = x sc + sh.  MODE 1: dx = g sc - sh - (x - mu) k2 with mu folded in.  MODE 2: dx = g sc
+  float sc[8], sh[8], k2[8], sh0[8];   // MODE 0: y = x sc + sh.  MODE 1: dx = g sc - sh - (x - mu) k2 with mu folded in.  MODE 2: dx = g sc
+                                       // sh0: forward shift, for the mask of a fused ReLU in MODE 1 (z = x sc + sh0 > 0)
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int ch = cg * 8 + j;
     const float is = invstd[ch], ga = gamma ? gamma[ch] : 1.f, mu = mean[ch];
+    sh0[j] = (beta ? beta[ch] : 0.f) - mu * is * ga;
     if (MODE == 0) {
       sc[j] = is * ga;
-      sh[j] = (beta ? beta[ch] : 0.f) - mu * is * ga;
+      sh[j] = sh0[j];
       k2[j] = 0.f;
     } else if (MODE == 1) {
       sc[j] = is * ga;
@@ -269,9 +276,15 @@ __global__ void __launch_bounds__(BN_THREADS) bn_apply_kernel(const T *__restric
       float o[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        if (MODE == 0) o[j] = fmaf(v[u][j], sc[j], sh[j]);
-        else if (MODE == 1) o[j] = fmaf(g[u][j], sc[j], -fmaf(v[u][j], k2[j], sh[j]));
-        else o[j] = g[u][j] * sc[j];
+        if (MODE == 0) {
+          o[j] = fmaf(v[u][j], sc[j], sh[j]);
+          if (relu) o[j] = fmaxf(o[j], 0.f);
+        } else if (MODE == 1) {
+          const float gj = (relu && fmaf(v[u][j], sc[j], sh0[j]) <= 0.f) ? 0.f : g[u][j];
+          o[j] = fmaf(gj, sc[j], -fmaf(v[u][j], k2[j], sh[j]));
+        } else {
+          o[j] = g[u][j] * sc[j];
+        }
       }
       store8<T>(out + ru * c + cg * 8, o);
     }
@@ -317,18 +330,19 @@ int tsg_bn_stats(const void *x, int dtype, int64_t n, int c, float eps, float mo
   const int nb = bn_blocks(n, c, &rows);
   const size_t smem = 2 * (size_t)c * (BN_THREADS / (c / 8)) * sizeof(float);
   if (dtype == TSG_F32)
-    bn_reduce_kernel<float, 0><<<nb, BN_THREADS, smem, stream>>>((const float *)x, nullptr, n, c, rows, nullptr, nullptr, (float *)ws);
+    bn_reduce_kernel<float, 0><<<nb, BN_THREADS, smem, stream>>>((const float *)x, nullptr, n, c, rows, nullptr, nullptr, nullptr, nullptr, 0, (float *)ws);
   else
     bn_reduce_kernel<__nv_bfloat16, 0><<<nb, BN_THREADS, smem, stream>>>((const __nv_bfloat16 *)x, nullptr, n, c, rows, nullptr,
-                                                                        nullptr, (float *)ws);
+                                                                        nullptr, nullptr, nullptr, 0, (float *)ws);
   bn_finalize_kernel<<<(c + 31) / 32, 1024, 0, stream>>>((const float *)ws, nb, c, eps, momentum, running_mean, running_var, mean,
                                                          invstd);
   return check_launch("tsg_bn_stats");
 }
 
-/* y = (x - mean) * invstd * gamma + beta; gamma / beta may be NULL (affine=False) */
+/* y = (x - mean) * invstd * gamma + beta, then max(y, 0) when relu != 0 (the BatchNorm + ReLU pair of every convolution block
+ * in one pass); gamma / beta may be NULL (affine=False) */
 int tsg_bn_apply(const void *x, int dtype, int64_t n, int c, const float *mean, const float *invstd, const float *gamma,
-                 const float *beta, void *y, tsg_stream_t stream) {
+                 const float *beta, int relu, void *y, tsg_stream_t stream) {
   if (c <= 0 || c % 8 || n <= 0 || (dtype != TSG_F32 && dtype != TSG_BF16)) {
     set_error("tsg_bn_apply: need n > 0, c a multiple of 8, fp32 or bf16 rows");
     return TSG_ERR_UNSUPPORTED;
@@ -336,18 +350,24 @@ int tsg_bn_apply(const void *x, int dtype, int64_t n, int c, const float *mean, 
   const int grid = (int)std::min<int64_t>((n + (BN_THREADS / (c / 8)) - 1) / (BN_THREADS / (c / 8)), 16LL * num_sms());
   if (dtype == TSG_F32)
     bn_apply_kernel<float, 0><<<grid, BN_THREADS, 0, stream>>>((const float *)x, nullptr, n, c, mean, invstd, gamma, beta, nullptr,
-                                                             (float *)y);
+                                                             relu, (float *)y);
   else
     bn_apply_kernel<__nv_bfloat16, 0><<<grid, BN_THREADS, 0, stream>>>((const __nv_bfloat16 *)x, nullptr, n, c, mean, invstd, gamma,
-                                                                     beta, nullptr, (__nv_bfloat16 *)y);
+                                                                     beta, nullptr, relu, (__nv_bfloat16 *)y);
   return check_launch("tsg_bn_apply");
 }
 
 /* Backward.  training != 0: sums (2 x C fp32) receives {dbeta = sum dy, dgamma = sum dy * xhat} and
  * dx = gamma invstd (dy - sums[0] / n - xhat sums[1] / n);  training == 0 (running statistics were used): the same sums,
- * dx = gamma invstd dy.  dx may be NULL (only the parameter gradients are wanted). */
+ * dx = gamma invstd dy.  dx may be NULL (only the parameter gradients are wanted).  relu != 0 (training only): dy is the
+ * gradient of relu(bn(x)); it is masked by bn(x) > 0, recomputed from x, in both passes. */
 int tsg_bn_backward(const void *x, const void *dy, int dtype, int64_t n, int c, const float *mean, const float *invstd,
-                    const float *gamma, int training, float *sums, void *dx, void *ws, size_t ws_bytes, tsg_stream_t stream) {
+                    const float *gamma, const float *beta, int relu, int training, float *sums, void *dx, void *ws, size_t ws_bytes,
+                    tsg_stream_t stream) {
+  if (relu && !training) {
+    set_error("tsg_bn_backward: the fused ReLU is supported in training mode only");
+    return TSG_ERR_UNSUPPORTED;
+  }
   if (c <= 0 || c % 8 || c > BN_MAXC || n <= 0 || (dtype != TSG_F32 && dtype != TSG_BF16)) {
     set_error("tsg_bn_backward: need n > 0, c a multiple of 8 <= 1024, fp32 or bf16 rows");
     return TSG_ERR_UNSUPPORTED;
@@ -361,24 +381,24 @@ int tsg_bn_backward(const void *x, const void *dy, int dtype, int64_t n, int c, 
   const size_t smem = 2 * (size_t)c * (BN_THREADS / (c / 8)) * sizeof(float);
   const int grid = (int)std::min<int64_t>((n + (BN_THREADS / (c / 8)) - 1) / (BN_THREADS / (c / 8)), 16LL * num_sms());
   if (dtype == TSG_F32) {
-    bn_reduce_kernel<float, 1><<<nb, BN_THREADS, smem, stream>>>((const float *)x, (const float *)dy, n, c, rows, mean, invstd, (float *)ws);
+    bn_reduce_kernel<float, 1><<<nb, BN_THREADS, smem, stream>>>((const float *)x, (const float *)dy, n, c, rows, mean, invstd, gamma, beta, relu, (float *)ws);
     bn_bwd_finalize_kernel<<<(c + 31) / 32, 1024, 0, stream>>>((const float *)ws, nb, c, sums);
     if (dx && training)
-      bn_apply_kernel<float, 1><<<grid, BN_THREADS, 0, stream>>>((const float *)x, (const float *)dy, n, c, mean, invstd, gamma, nullptr,
-                                                               sums, (float *)dx);
+      bn_apply_kernel<float, 1><<<grid, BN_THREADS, 0, stream>>>((const float *)x, (const float *)dy, n, c, mean, invstd, gamma, beta,
+                                                               sums, relu, (float *)dx);
     else if (dx)
       bn_apply_kernel<float, 2><<<grid, BN_THREADS, 0, stream>>>((const float *)x, (const float *)dy, n, c, mean, invstd, gamma, nullptr,
-                                                               sums, (float *)dx);
+                                                               sums, 0, (float *)dx);
   } else {
     bn_reduce_kernel<__nv_bfloat16, 1><<<nb, BN_THREADS, smem, stream>>>((const __nv_bfloat16 *)x, (const __nv_bfloat16 *)dy, n, c, rows,
-                                                                        mean, invstd, (float *)ws);
+                                                                        mean, invstd, gamma, beta, relu, (float *)ws);
     bn_bwd_finalize_kernel<<<(c + 31) / 32, 1024, 0, stream>>>((const float *)ws, nb, c, sums);
     if (dx && training)
       bn_apply_kernel<__nv_bfloat16, 1><<<grid, BN_THREADS, 0, stream>>>((const __nv_bfloat16 *)x, (const __nv_bfloat16 *)dy, n, c, mean,
-                                                                       invstd, gamma, nullptr, sums, (__nv_bfloat16 *)dx);
+                                                                       invstd, gamma, beta, sums, relu, (__nv_bfloat16 *)dx);
     else if (dx)
       bn_apply_kernel<__nv_bfloat16, 2><<<grid, BN_THREADS, 0, stream>>>((const __nv_bfloat16 *)x, (const __nv_bfloat16 *)dy, n, c, mean,
-                                                                       invstd, gamma, nullptr, sums, (__nv_bfloat16 *)dx);
+                                                                       invstd, gamma, nullptr, sums, 0, (__nv_bfloat16 *)dx);
   }
   return check_launch("tsg_bn_backward");
 }

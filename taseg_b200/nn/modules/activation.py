@@ -8,8 +8,11 @@ __all__ = ['ReLU', 'LeakyReLU']
 
 
 class ReLU(nn.ReLU):
+    fused_upstream = False     # True: the BatchNorm in front of this module already applied the ReLU (norm.fuse_bn_relu)
 
     def forward(self, input: SparseTensor) -> SparseTensor:
+        if self.fused_upstream:
+            return input
         return fapply(input, super().forward)
 
 

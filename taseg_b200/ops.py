@@ -575,23 +575,24 @@ def bn_stats(x: torch.Tensor, eps: float, momentum: float, running_mean: Optiona
 
 
 def bn_apply(x: torch.Tensor, mean: torch.Tensor, invstd: torch.Tensor, gamma: Optional[torch.Tensor],
-             beta: Optional[torch.Tensor]) -> torch.Tensor:
+             beta: Optional[torch.Tensor], relu: bool = False) -> torch.Tensor:
     x = x.contiguous()
     y = torch.empty_like(x)
-    call("tsg_bn_apply", ptr(x), L.DTYPES[x.dtype], x.shape[0], x.shape[1], ptr(mean), ptr(invstd), ptr(gamma), ptr(beta), ptr(y), stream())
+    call("tsg_bn_apply", ptr(x), L.DTYPES[x.dtype], x.shape[0], x.shape[1], ptr(mean), ptr(invstd), ptr(gamma), ptr(beta), int(relu),
+         ptr(y), stream())
     return y
 
 
 def bn_backward(x: torch.Tensor, dy: torch.Tensor, mean: torch.Tensor, invstd: torch.Tensor, gamma: Optional[torch.Tensor],
-                training: bool, want_dx: bool = True):
-    """(dx | None, dgamma, dbeta)."""
+                training: bool, want_dx: bool = True, beta: Optional[torch.Tensor] = None, relu: bool = False):
+    """(dx | None, dgamma, dbeta); relu: dy is the gradient of relu(bn(x)) (training mode only)."""
     x, dy = x.contiguous(), dy.contiguous().to(x.dtype)
     n, c = x.shape
     sums = torch.empty((2, c), dtype=torch.float32, device=x.device)
     dx = torch.empty_like(x) if want_dx else None
     ws = _bn_ws(x)
-    call("tsg_bn_backward", ptr(x), ptr(dy), L.DTYPES[x.dtype], n, c, ptr(mean), ptr(invstd), ptr(gamma), int(training), ptr(sums),
-         ptr(dx), ptr(ws), ws.numel(), stream())
+    call("tsg_bn_backward", ptr(x), ptr(dy), L.DTYPES[x.dtype], n, c, ptr(mean), ptr(invstd), ptr(gamma), ptr(beta), int(relu),
+         int(training), ptr(sums), ptr(dx), ptr(ws), ws.numel(), stream())
     return dx, sums[1], sums[0]
 
 

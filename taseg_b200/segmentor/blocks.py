@@ -7,6 +7,7 @@
 from torch import nn
 
 from .. import nn as spnn
+from ..nn.modules.norm import fuse_bn_relu
 from ..nn.utils import fapply
 from ..tensor import SparseTensor
 
@@ -27,8 +28,8 @@ def norm(channels: int, if_dist: bool) -> nn.Module:
 class BasicConvolutionBlock(nn.Module):
     def __init__(self, inc, outc, ks=3, stride=1, dilation=1, if_dist=False):
         super().__init__()
-        self.net = nn.Sequential(spnn.Conv3d(inc, outc, kernel_size=ks, dilation=dilation, stride=stride),
-                                 norm(outc, if_dist), spnn.ReLU(True))
+        self.net = fuse_bn_relu(nn.Sequential(spnn.Conv3d(inc, outc, kernel_size=ks, dilation=dilation, stride=stride),
+                                              norm(outc, if_dist), spnn.ReLU(True)))
 
     def forward(self, x):
         return self.net(x)
@@ -37,8 +38,8 @@ class BasicConvolutionBlock(nn.Module):
 class BasicDeconvolutionBlock(nn.Module):
     def __init__(self, inc, outc, ks=3, stride=1, if_dist=False):
         super().__init__()
-        self.net = nn.Sequential(spnn.Conv3d(inc, outc, kernel_size=ks, stride=stride, transposed=True),
-                                 norm(outc, if_dist), spnn.ReLU(True))
+        self.net = fuse_bn_relu(nn.Sequential(spnn.Conv3d(inc, outc, kernel_size=ks, stride=stride, transposed=True),
+                                              norm(outc, if_dist), spnn.ReLU(True)))
 
     def forward(self, x):
         return self.net(x)
@@ -62,10 +63,10 @@ class ResidualBlock(_Residual):
 
     def __init__(self, inc, outc, ks=3, stride=1, dilation=1, if_dist=False):
         super().__init__()
-        self.net = nn.Sequential(spnn.Conv3d(inc, outc, kernel_size=ks, dilation=dilation, stride=stride),
-                                 norm(outc, if_dist), spnn.ReLU(True),
-                                 spnn.Conv3d(outc, outc, kernel_size=ks, dilation=dilation, stride=1),
-                                 norm(outc, if_dist))
+        self.net = fuse_bn_relu(nn.Sequential(spnn.Conv3d(inc, outc, kernel_size=ks, dilation=dilation, stride=stride),
+                                              norm(outc, if_dist), spnn.ReLU(True),
+                                              spnn.Conv3d(outc, outc, kernel_size=ks, dilation=dilation, stride=1),
+                                              norm(outc, if_dist)))
         self.downsample = self._shortcut(inc, outc, stride, if_dist)
         self.relu = spnn.ReLU(True)
 

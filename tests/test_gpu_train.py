@@ -130,3 +130,37 @@ def test_batch_norm_rows_vs_aten(c, dtype):
     ye.backward(gy), yr.backward(gy)
     assert float((ye.detach().float() - yr.detach().float()).abs().max()) <= tol * max(1.0, float(yr.detach().float().abs().max()))
     assert float((xe.grad.float() - xr.grad.float()).abs().max()) <= tol * max(1.0, float(xr.grad.float().abs().max()))
+
+
+@pytest.mark.parametrize("c,dtype", [(32, torch.float32), (96, torch.bfloat16)])
+def test_batch_norm_relu_fused(c, dtype):
+    """BatchNorm with the ReLU of its convolution block applied in the same pass (norm.fuse_bn_relu) against
+    relu(nn.BatchNorm1d(x)): outputs and all gradients in training mode, outputs in evaluation mode; the ReLU module behind a
+    fused BatchNorm is the identity; module / parameter names are unchanged."""
+    from taseg_b200 import nn as spnn
+    from taseg_b200.nn.modules.norm import fuse_bn_relu
+    torch.manual_seed(c + 1)
+    n = 50003
+    x = (torch.randn(n, c, device="cuda") * 1.3 + 0.2).to(dtype)
+    seq = fuse_bn_relu(torch.nn.Sequential(spnn.BatchNorm(c), spnn.ReLU(True))).cuda()
+    ours, ref = seq[0], torch.nn.BatchNorm1d(c).cuda()
+    assert ours.fuse_relu and seq[1].fused_upstream and list(seq.state_dict()) == ["0." + k for k in ref.state_dict()]
+    with torch.no_grad():
+        ours.weight.copy_(torch.rand(c) - 0.3)          # some negative scales: the mask must come from bn(x), not from x
+        ours.bias.copy_(torch.randn(c) * 0.3)
+    ref.load_state_dict(ours.state_dict())
+    gy = torch.randn(n, c, device="cuda").to(dtype)
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    ya = ours._rows(xa)
+    yb = torch.relu(ref(xb))
+    ya.backward(gy), yb.backward(gy)
+    tol = 1e-4 if dtype == torch.float32 else 2e-2
+    for a, b in ((ya, yb), (xa.grad, xb.grad), (ours.weight.grad, ref.weight.grad), (ours.bias.grad, ref.bias.grad)):
+        a, b = a.detach().float(), b.detach().float()
+        assert float((a - b).abs().max()) <= tol * max(1.0, float(b.abs().max())), (c, dtype)
+    assert float(ya.min()) >= 0.0
+    ours.eval(), ref.eval()
+    ref.load_state_dict(ours.state_dict())
+    with torch.no_grad():
+        ye, yr = ours._rows(x), torch.relu(ref(x))
+    assert float((ye.float() - yr.float()).abs().max()) <= tol * max(1.0, float(yr.float().abs().max()))
