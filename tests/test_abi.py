@@ -121,3 +121,27 @@ def test_kd_model_state_dict_matches_reference():
     ref = {k[3:]: tuple(g[k].shape) for k in g.files if k.startswith("sd/")}
     assert mine == ref
     assert sum(k.startswith("stem_gt.") for k in mine) == sum(k.startswith("stem.") for k in mine) > 0
+
+
+def test_training_path_host_logic_cpu():
+    """Host-side pieces of the round-2 training path that need no GPU: column blocks of the tensor-core data gradient, the
+    slice-plan guard of the split-precision fp32 path, BatchNorm + ReLU fusion marks (names unchanged, CPU rows fall back to
+    ATen + relu with identical results), K-split policy switches."""
+    import torch
+    from taseg_b200 import nn as spnn
+    from taseg_b200 import ops
+    from taseg_b200.nn.functional import conv as C
+    from taseg_b200.nn.modules.norm import fuse_bn_relu
+    assert C._col_blocks(96) == [(0, 96)] and C._col_blocks(256) == [(0, 256)]
+    assert C._col_blocks(384) == [(0, 192), (192, 384)] and C._col_blocks(272) == [(0, 144), (144, 272)]
+    assert all((b - a) % 16 == 0 and b - a <= 256 for a, b in C._col_blocks(1040))
+    seq = fuse_bn_relu(torch.nn.Sequential(spnn.BatchNorm(8), spnn.ReLU(True), spnn.BatchNorm(8)))
+    assert seq[0].fuse_relu and seq[1].fused_upstream and not seq[2].fuse_relu
+    assert list(seq.state_dict()) == list(torch.nn.Sequential(torch.nn.BatchNorm1d(8), torch.nn.ReLU(), torch.nn.BatchNorm1d(8)).state_dict())
+    x = torch.randn(64, 8)
+    ref = torch.nn.BatchNorm1d(8)
+    ref.load_state_dict(seq[0].state_dict())
+    got = seq[1](spnn.modules.norm.BatchNorm._rows(seq[0], x)) if False else seq[0]._rows(x)     # CPU rows: ATen + relu
+    assert torch.allclose(got, torch.relu(ref(x)), atol=1e-6)
+    assert not ops.SplitItems.wanted(15307, 27) or ops.SPLIT_K          # off by default
+    assert not ops.bn_supported(x)                                      # CPU tensors never reach the kernels
