@@ -27,15 +27,25 @@
 // Accumulators are double buffered in TMEM so the epilogue of super tile t overlaps the main loop of t+1.
 // v16: a launch may carry a second K PHASE — the 1x1x1 shortcut convolution of a residual block, gathered through the
 // centre offset's index line and accumulated into the same TMEM tile (no shortcut launch, no residual read: 66 -> 59
-// launches and -0.2 ms per benchmark step).  Two measured-and-rejected switches stay behind environment variables:
-// (tile, column half) work items for launches with fewer tiles than SMs (TSG_TC_NSPLIT=2) and programmatic dependent
-// launch (TSG_TC_PDL=1); see the host function for the numbers.
+// launches and -0.2 ms per benchmark step).
+// v17: conflict-free epilogue staging (64-byte pitch, XOR swizzle); the first ticket of a CTA is its block index; K-split work
+// items (tsg_conv_split_items / tsg_conv_fwd_tc4, off by default).
+// v18: the planner's LOOK-AHEAD THROTTLE.  The plan ring let every CTA draw four tickets in its first microsecond, so
+// launches with 2-3 tiles per SM were assigned statically and the CTAs holding the heaviest tiles got the most tiles
+// (per-CTA timelines: stride-8 layers finished between 21 and 50 us).  A ticket is now drawn only when fewer than
+// 6 x stages + 4 planned stages remain in front of the MMA issuers (template argument THR, chosen by the host for launches
+// with <= 8 work items per CTA): -22 % on the stride-8 layers, 3858 -> 3590 us of convolutions per benchmark step.
+// Also v18: the CTA-PAIR variant (template argument PAIR, tcgen05.mma.cta_group::2, see the kernel's comment) — built,
+// parity-tested, measured no faster on any layer class and therefore off by default (TSG_TC_PAIR).
+// Measured-and-rejected switches stay behind environment variables: (tile, column half) work items (TSG_TC_NSPLIT=2),
+// programmatic dependent launch (TSG_TC_PDL=1), K split (TSG_SPLIT_K=1), pairs (TSG_TC_PAIR=1/2); see the host function.
 // History and measurements (profiles/README.md): v1-v7 were bound, in turn, by producer instruction count, the single MMA
 // thread, per-stage bookkeeping done by all 16 producer warps (~2000 cycles of branchy scalar code per group stage) and a
 // thread-per-row epilogue; v9 moved the stage enumeration into the planner warp, v12 doubled and coalesced the epilogue,
-// v13 made the producer hand-off asynchronous, v14/v15 alternate two MMA issuers.  What bounds v15: shared-memory
-// bandwidth for c_out <= 128 (operand fetch of an MMA is (4096 + 32 N)/128 cycles), L2->SM ingest for the dense small
-// layers, tile quantisation at strides 8/16.
+// v13 made the producer hand-off asynchronous, v14/v15 alternate two MMA issuers.  What bounds v18 (ncu of every layer
+// class, profiles/r02/ncu_conv_v18_summary.md): the shared-memory data pipe on the 96-channel layers at strides 1-2
+// (LDGSTS + LDS/STS wavefronts 38-44 % of cycles + tensor-core operand reads 24-33 %), L2 -> SM weight traffic on 256 -> 256
+// at stride 8 (10.4 TB/s), the producers' latency chain and ~10 us of fixed cost per launch on the other one-tile launches.
 #include <cstdlib>
 #include <cstring>
 
