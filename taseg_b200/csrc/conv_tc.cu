@@ -282,8 +282,13 @@ __device__ __forceinline__ void epi_block(const TcParams &p, uint32_t taddr, boo
 //     arrives on empty[slot] / tfull[buf] of BOTH CTAs;
 //   * the peer's epilogue threads release the accumulator buffer on the LEADER's tempty (remote arrive).
 // THR: the planner's look-ahead throttle (heaviest-first list scheduling for launches with few tiles per CTA) is compiled in.
-template <int G, bool PAIR, bool THR>
+// SC: the launch carries the second K phase (a folded shortcut).  A template argument because the phase selects sit in the
+// planner's and the producers' hot loops and most launches have one phase: the one-phase kernels are smaller and faster.
+// F32: fp32 output rows (the classifier heads, the split-precision fp32 path); ITEMS: work-item list with K split (G = 1).
+// Template arguments for the same reason: each removes an epilogue variant (or the partial-sum exchange) from the others.
+template <int G, bool PAIR, bool THR, bool SC, bool F32, bool ITEMS>
 __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p) {
+  static_assert(!ITEMS || (G == 1 && !PAIR), "work items address single tiles of a single CTA");
   static_assert(!PAIR || G == 1, "a pair CTA holds one tile");
   constexpr int GP = PAIR ? 2 : G;   // tiles per plan (unit of scheduling)
   extern __shared__ uint8_t smem_raw[];
@@ -296,7 +301,7 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int NPH = p.n_phases;
+  constexpr int NPH = SC ? 2 : 1;
   const int P0 = p.ph[0].pk, Q0 = p.ph[0].kq, P1 = p.ph[1].pk, Q1 = p.ph[1].kq;  // offsets / slices per virtual offset
   const unsigned long long need0 = p.ph[0].slice_need, need1 = p.ph[1].slice_need;
   const int NS = p.ns, n_eff = p.n_eff;
@@ -408,7 +413,7 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
     const int quad = warp & 3, eset = warp >> 2;
     const uint32_t stg = stg0 + warp * V8_STG_BYTES;
     const int c_out = p.c_out;
-    const bool f32 = p.out_f32 != 0;
+    constexpr bool f32 = F32;
     const bool res_staged = p.residual != nullptr && !f32;
     const bool no_store = TSG_DBG(8) != 0;
     const char *resp = reinterpret_cast<const char *>(p.residual);
@@ -437,7 +442,7 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
       const long long r = (long long)my_tile * TC_BM + quad * 32 + lane;  // destination row: fetched before the long wait
       const int rows_g = r < n_rows ? (p.perm ? __ldg(p.perm + r) : (int)r) : -1;
       const bool live = my_tile < num_tiles && cfirst < n_eff;
-      const bool is_split = G == 1 && !PAIR && (split >> 8) > 1;       // one of the two work items of a K-split tile
+      const bool is_split = ITEMS && (split >> 8) > 1;                 // one of the two work items of a K-split tile
       if (res_staged && live && !is_split) prefetch_res(rows_g, cbase + cfirst, blk_cols(cfirst));  // lands while the main loop still runs
       mbar_wait_sleep(tfull0 + 8 * buf, ph);
       tc_fence_after();
@@ -644,7 +649,7 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
         const size_t hoff = (size_t)((pl->n >> 16) + my_g) * b_bytes;   // this work item's (PAIR: this CTA's) rows of every [c_out][64] block
         for (int i = 0; i < n; ++i) {
           const unsigned d = pl->stage[i];
-          const unsigned phi = (d >> 13) & 1u;
+          const unsigned phi = SC ? (d >> 13) & 1u : 0u;
           const uint8_t *src = (phi ? p.ph[1].packed_w : p.ph[0].packed_w) +
                                (size_t)((d & 31u) * (phi ? Q1 : Q0) + ((d >> 5) & 15u)) * b_full + hoff;
           TSG_STATE(pl->tile, n, i, n_w);
@@ -673,7 +678,7 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
     int static_next = blockIdx.x;
     bool first_ticket = true;
     // work-item list (K split, G == 1): the list replaces the tile enumeration; its length is a device value
-    const bool use_items = G == 1 && p.items != nullptr;
+    constexpr bool use_items = ITEMS;
     const int n_work = use_items ? __ldg(p.n_items) : num_super * NS;
     // Look-ahead throttle (v18).  The plan ring lets the planner run up to four tiles ahead — and at kernel start it
     // did: every CTA drew four tickets in its first microsecond, so a launch with 2-3 tiles per SM was assigned
@@ -909,7 +914,7 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
         bool indexed;       // neighbour indices come from an index line (false: identity map)
       };
       auto locate = [&](View &v) {
-        const unsigned phi = (d_cur >> 13) & 1u;
+        const unsigned phi = SC ? (d_cur >> 13) & 1u : 0u;
         const int kv = d_cur & 31u, j = (d_cur >> 5) & 15u;
         v.act = PAIR ? 1u : (d_cur >> 9) & 3u;   // PAIR: a tile that does not need the stage still presents (zero) rows
         const uint32_t e = lut[phi * 128 + j * 8 + chunk];
@@ -925,7 +930,7 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
       };
       // request the index lines of the delivered stage: per (offset of the slice, sub-tile) the warp's 32 rows = 128 B
       auto prefetch_idx = [&](uint32_t buf) {
-        const unsigned phi = (d_cur >> 13) & 1u;
+        const unsigned phi = SC ? (d_cur >> 13) & 1u : 0u;
         const int *nbr = phi ? p.ph[1].nbr : p.ph[0].nbr;
         if (!nbr) return;
         const long long nbr_stride = phi ? p.ph[1].nbr_stride : p.ph[0].nbr_stride;
@@ -1355,11 +1360,15 @@ int tsg_conv_fwd_tc4(const void *in0, int c0, const void *in1, int c1, int64_t n
   const size_t smem = (size_t)stages * stage_bytes + fixed;
   static bool configured[64] = {false};   // the >48 KB shared-memory opt-in is per device
   if (dev < 0 || dev >= 64 || !configured[dev]) {
-    TSG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<1, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, V8_DYN_SMEM));
-    TSG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, V8_DYN_SMEM));
-    TSG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<2, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, V8_DYN_SMEM));
-    TSG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, V8_DYN_SMEM));
-    TSG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<1, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, V8_DYN_SMEM));
+#define TSG_TC_SMEM(...) TSG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, V8_DYN_SMEM))
+#define TSG_TC_SMEM4(g, pair, thr, items)                                                                                   \
+  TSG_TC_SMEM(g, pair, thr, false, false, items); TSG_TC_SMEM(g, pair, thr, true, false, items);                            \
+  TSG_TC_SMEM(g, pair, thr, false, true, items); TSG_TC_SMEM(g, pair, thr, true, true, items)
+    TSG_TC_SMEM4(1, false, false, false); TSG_TC_SMEM4(1, false, true, false); TSG_TC_SMEM4(2, false, false, false);
+    TSG_TC_SMEM4(2, false, true, false); TSG_TC_SMEM4(1, true, false, false); TSG_TC_SMEM4(1, false, true, true);
+    TSG_TC_SMEM4(1, false, false, true);
+#undef TSG_TC_SMEM4
+#undef TSG_TC_SMEM
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
   const long long work = items ? num_tiles + max_slots : pair ? (num_tiles + 1) / 2 : (num_tiles + G - 1) / G * ns;
@@ -1395,11 +1404,24 @@ int tsg_conv_fwd_tc4(const void *in0, int c0, const void *in1, int c1, int64_t n
   static const int lookahead = getenv("TSG_TC_LOOKAHEAD") ? atoi(getenv("TSG_TC_LOOKAHEAD")) : 6;
   p.lookahead = lookahead;
   const bool thr = sched && work <= (long long)thr_max * cfg.gridDim.x;
-  if (pair) TSG_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<1, true, false>, p));
-  else if (G == 2 && thr) TSG_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<2, false, true>, p));
-  else if (G == 2) TSG_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<2, false, false>, p));
-  else if (thr) TSG_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<1, false, true>, p));
-  else TSG_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<1, false, false>, p));
+  const bool sc = p.n_phases > 1, f32 = p.out_f32 != 0;
+#define TSG_TC_GO(...) TSG_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<__VA_ARGS__>, p))
+#define TSG_TC_GO4(g, pair, thr, items)                                                  \
+  do {                                                                                   \
+    if (sc && f32) TSG_TC_GO(g, pair, thr, true, true, items);                           \
+    else if (sc) TSG_TC_GO(g, pair, thr, true, false, items);                            \
+    else if (f32) TSG_TC_GO(g, pair, thr, false, true, items);                           \
+    else TSG_TC_GO(g, pair, thr, false, false, items);                                   \
+  } while (0)
+  if (pair) TSG_TC_GO4(1, true, false, false);
+  else if (items && thr) TSG_TC_GO4(1, false, true, true);
+  else if (items) TSG_TC_GO4(1, false, false, true);
+  else if (G == 2 && thr) TSG_TC_GO4(2, false, true, false);
+  else if (G == 2) TSG_TC_GO4(2, false, false, false);
+  else if (thr) TSG_TC_GO4(1, false, true, false);
+  else TSG_TC_GO4(1, false, false, false);
+#undef TSG_TC_GO4
+#undef TSG_TC_GO
   return check_launch("tsg_conv_fwd_tc");
 }
 
