@@ -31,9 +31,27 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// Spin on an mbarrier phase.  try_wait suspends the thread in hardware for a bounded time, so the loop is not hot;
-// the watchdog reads the cheap SM cycle counter (never %globaltimer, whose read costs ~1 us) once per 4096 failed
-// polls and traps after ~2^33 cycles (~4 s): a protocol bug must fail loudly, never hang the GPU.
+// Spin on an mbarrier phase.  try_wait suspends the thread in hardware for a bounded time, so the loop is not hot.  A protocol
+// bug must fail loudly, never hang the GPU: the production build counts failed polls (2^26 of them are seconds) and traps;
+// the trace build reads the SM cycle counter and prints who hangs on what first.  (The watchdog used to be a clock64() /
+// 64-bit compare sequence inlined at each of the ~20 wait sites: 22 % of the kernel's SASS, and code size costs this kernel
+// measurable time — profiles/README.md.)
+#ifndef TSG_TC_TRACE
+template <bool CLUSTER = false>   // CLUSTER marks the waits whose arrivals come from the other CTA of a pair (same instruction:
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {   // see the note in the trace variant below)
+  uint32_t done = 0, spin = 0;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done && ++spin < (1u << 26));
+  if (!done) __trap();
+}
+#else
 // CLUSTER marks the waits whose arrivals come from the other CTA of a pair.  They use the same CTA-scope acquire as
 // the local ones (as CUTLASS's ClusterBarrier does): what they order is shared memory that has physically landed and TMEM
 // reads bracketed by tcgen05 fences; the cluster-scope forms compile to MEMBAR.ALL.GPU / CCTL.IVALL per use, which made
@@ -81,6 +99,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
   }
 }
+#endif
 // one non-blocking probe of an mbarrier phase
 __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
   uint32_t done;
@@ -215,6 +234,23 @@ __device__ __forceinline__ int next_bit(unsigned mask, int after) {  // first se
 
 // Long waits (an epilogue warp waiting for a whole mainloop): back off between polls so the idle warp does not
 // compete for issue slots with the producer / MMA warps that share its scheduler.
+#ifndef TSG_TC_TRACE
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0, spin = 0;
+  for (;;) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    __nanosleep(200);
+    if (++spin == (1u << 24)) __trap();   // > 3 s of back-off: a protocol bug
+  }
+}
+#else
 __device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
   long long t0 = 0;
@@ -243,5 +279,7 @@ __device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
     }
   }
 }
+
+#endif
 
 }  // namespace tsg
