@@ -382,19 +382,22 @@ def main():
     copy_stream = torch.cuda.Stream()       # host -> device
     down_stream = torch.cuda.Stream()       # device -> host
     nbuf = max(2, N_STREAMS) if EAGER else N_STREAMS      # graph mode: one input buffer per captured pipeline
-    dev_pts = [p.points for p in pipes] if not EAGER else [torch.empty_like(pts) for _ in range(nbuf)]
-    while len(dev_pts) < nbuf:
-        dev_pts.append(dev_pts[0])
+    # uploads land in staging buffers of their own and are moved into the pipeline's static input buffer by a device copy at
+    # the head of the step (10 us for 23 MB), so the upload of step i+1 never waits for the pipeline that will consume it
+    dev_pts = [pts.clone() for _ in range(nbuf)]
     dev_out = [torch.empty((n_cur, 20), dtype=torch.float32, device="cuda") for _ in range(nbuf)]
     h2d_done = [torch.cuda.Event() for _ in range(nbuf)]
+    in_taken = [torch.cuda.Event() for _ in range(nbuf)]
     out_ready = [torch.cuda.Event() for _ in range(nbuf)]
     d2h_done = [torch.cuda.Event() for _ in range(nbuf)]
     e2e_state = {"i": 0, "primed": False}
+    E2E_SKIP = os.environ.get("TSG_BENCH_E2E_SKIP", "")      # diagnosis only ("h2d", "d2h", "stage", "out"): such a run prints no e2e claim
 
     def enqueue_h2d(slot):
         with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(out_ready[slot])      # the step that last read this buffer has finished with it
-            dev_pts[slot].copy_(host_pts, non_blocking=True)
+            copy_stream.wait_event(in_taken[slot])       # the step that last read this staging buffer has taken its copy
+            if "h2d" not in E2E_SKIP:
+                dev_pts[slot].copy_(host_pts, non_blocking=True)
             h2d_done[slot].record(copy_stream)
 
     def step_e2e():
@@ -406,16 +409,25 @@ def main():
         enqueue_h2d((i + 1) % nbuf)                       # next step's input travels while this step computes
         main = streams[slot % N_STREAMS]
         main.wait_event(h2d_done[slot])
-        main.wait_event(d2h_done[slot])                   # dev_out[slot] was drained nbuf steps ago
         with torch.cuda.stream(main):
             if EAGER:
-                dev_out[slot].copy_(forward_eager(dev_pts[slot]))
+                logits = forward_eager(dev_pts[slot])
+                in_taken[slot].record(main)
+                main.wait_event(d2h_done[slot])
+                dev_out[slot].copy_(logits)
             else:
-                dev_out[slot].copy_(pipes[slot % N_STREAMS]())
+                if "stage" not in E2E_SKIP:
+                    pipes[slot % N_STREAMS].points.copy_(dev_pts[slot])
+                in_taken[slot].record(main)
+                logits = pipes[slot % N_STREAMS]()
+                main.wait_event(d2h_done[slot])           # dev_out[slot] was drained nbuf steps ago; waiting HERE, not in front
+                if "out" not in E2E_SKIP:                 # of the graph, keeps this pipeline busy while that download finishes
+                    dev_out[slot].copy_(logits)
         out_ready[slot].record(main)
         with torch.cuda.stream(down_stream):
             down_stream.wait_event(out_ready[slot])
-            host_out.copy_(dev_out[slot], non_blocking=True)
+            if "d2h" not in E2E_SKIP:
+                host_out.copy_(dev_out[slot], non_blocking=True)
             if not EAGER:
                 host_status[slot % N_STREAMS:slot % N_STREAMS + 1].copy_(pipes[slot % N_STREAMS].status, non_blocking=True)
             d2h_done[slot].record(down_stream)
@@ -515,6 +527,8 @@ def main():
                         "d2h_bytes_per_step": host_out.numel() * 4, "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
                 "points_per_step": int(mfb.total), "current_points_per_step": n_cur}
+        if E2E_SKIP:
+            line["e2e"] = {"diagnostic_only": E2E_SKIP, "ms_per_step": ms_e2e / args.steps}
         if others is not None:
             line["other_configs"] = others
         if world == 1 and not args.no_cpu_baseline:
