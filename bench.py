@@ -292,7 +292,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     config = {"workload": WORKLOAD, "batch_per_gpu": BATCH, "frames": N_FRAMES, "voxel_size": VOXEL,
               "l2": "no flush: every step streams >1 GB of activations and kernel maps through the 126 MB L2",
-              "streams": N_STREAMS}
+              "streams": N_STREAMS, "shards": "every rank processes the same four scans (fixed work per GPU)"
+              if os.environ.get("TSG_BENCH_SAME_SHARD", "1") == "1" else "different scans per rank"}
 
     if args.impl == "reference":
         if rank != 0:
@@ -330,7 +331,13 @@ def main():
     _lib.lib()
     model = make_model()
     engine = Engine(model)
-    samples = make_samples(2000 + rank * BATCH, BATCH)          # seed = 1000*config_id + sample_idx
+    # seed = 1000*config_id + sample_idx.  Weak scaling = the same work on every GPU: all ranks process the four scans of
+    # configs[1] (rank 0's), each through its own front end, kernel maps, network and host copies.  TSG_BENCH_SAME_SHARD=0
+    # gives every rank scans of its own: the time is then set by the rank that drew the heaviest scans (4 GPUs: ranks at
+    # 4.01 / 4.02 / 4.36 / 3.91 ms per step, 3666 instead of 3925 scans/s; profiles/r02/scale_shards.txt) — data imbalance,
+    # not a property of the system.  ms_per_step_by_rank is printed either way.
+    SAME_SHARD = os.environ.get("TSG_BENCH_SAME_SHARD", "1") == "1"
+    samples = make_samples(2000 + (0 if SAME_SHARD else rank) * BATCH, BATCH)
     mfb = frontend.MultiFrameBatch([s[0] for s in samples], [s[1] for s in samples])
     host_pts = torch.from_numpy(mfb.points).pin_memory()
     pts = host_pts.cuda()
@@ -443,13 +450,17 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    host_ms, rank_ms = {}, {}
+
     def timed(fn, k):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         w0 = time.time()
         e0.record()
+        h0 = time.perf_counter()
         for _ in range(k):
             fn()
+        host_ms[fn.__name__] = (time.perf_counter() - h0) * 1e3 / k      # host time to enqueue one step (this rank)
         if fn is step_e2e:
             e2e_drain()       # the last logits must have reached the host inside the timed region
         else:
@@ -458,14 +469,22 @@ def main():
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
         if world > 1:
+            every = [torch.zeros_like(ms) for _ in range(world)]
+            dist.all_gather(every, ms)
+            rank_ms[fn.__name__] = [round(float(t.item()) / k, 4) for t in every]
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()), w0, time.time()
 
     for _ in range(max(3, args.warmup)):
         step()
-    sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else
-                           int(os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local_rank]))
-    sampler.start()
+    # rank 0 samples the clocks of every GPU of the job with ONE nvidia-smi process (eight pollers on one host take the
+    # driver's locks eight times as often); the line's clocks are the median over all of them, the reasons their union
+    vis = [v for v in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if v]
+    gpu_ids = [vis[i] if i < len(vis) else str(i) for i in range(world)] if world > 1 else \
+              [vis[local_rank] if local_rank < len(vis) else str(torch.cuda.current_device())]
+    sampler = ClockSampler(",".join(gpu_ids))
+    if rank == 0:
+        sampler.start()
     time.sleep(0.3)
     launches0 = _lib.launch_count
     ms, w0, w1 = timed(step, args.steps)
@@ -527,6 +546,9 @@ def main():
                         "d2h_bytes_per_step": host_out.numel() * 4, "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
                 "points_per_step": int(mfb.total), "current_points_per_step": n_cur}
+        line["host_enqueue_ms_per_step"] = {"value": round(host_ms.get("step", 0.0), 4), "e2e": round(host_ms.get("step_e2e", 0.0), 4)}
+        if rank_ms:
+            line["ms_per_step_by_rank"] = {"value": rank_ms.get("step"), "e2e": rank_ms.get("step_e2e")}
         if E2E_SKIP:
             line["e2e"] = {"diagnostic_only": E2E_SKIP, "ms_per_step": ms_e2e / args.steps}
         if others is not None:
