@@ -360,19 +360,21 @@ int tsg_conv_fwd_tc3(const void *in0, int c0, const void *in1, int c1, int64_t n
  * The reference has no counterpart: its 27 x (gather, cuBLAS GEMM, scatter) of TS/backend/convolution/convolution_cuda.cu:53-165
  * is balanced by cuBLAS; an output-stationary kernel must balance (tile, offset) work itself.  tsg_conv_split_items turns the
  * tile masks of a (mask-sorted) kernel map into a list of work items {tile, offset mask, part | parts << 8, slot} (4 int32
- * each, heaviest first; capacity ceil(n_out_cap / 128) + max_slots items): a tile with more than `cap` active offsets is
- * summed by TWO items over disjoint halves of its offsets.  tsg_conv_fwd_tc4 with `items` runs them on different SMs; the
- * item that finishes first parks its fp32 accumulators in split_scratch (max_slots x 128 x c_out floats), the other adds
- * them before bias / residual / ReLU (a + b commutes: results do not depend on the arrival order).  split_state:
- * max_slots x 8 int32, zero before the first launch (the kernel re-arms it).  items == NULL: tsg_conv_fwd_tc3. */
-int tsg_conv_split_items(const uint32_t *tile_mask, int64_t n_out_cap, const int32_t *n_out_dev, int k, int cap, int max_slots,
-                         int32_t *items, int32_t *n_items, tsg_stream_t stream);
+ * each, heaviest first; capacity ceil(n_out_cap / 128) + max_slots (max_parts - 1) items): a tile with more than `cap` active
+ * offsets is summed by ceil(active / cap) <= max_parts items over disjoint runs of its offsets.  tsg_conv_fwd_tc4 with `items`
+ * runs them on different SMs; every item but the last to arrive parks its fp32 accumulators in its slab of split_scratch
+ * (max_slots x max_parts x 128 x c_out floats), the last one sums the parts in part order before bias / residual / ReLU, so
+ * the result does not depend on the arrival order.  split_state: max_slots x 16 int32, zero before the first launch (the
+ * kernel re-arms it).  items == NULL: tsg_conv_fwd_tc3. */
+int tsg_conv_split_items(const uint32_t *tile_mask, int64_t n_out_cap, const int32_t *n_out_dev, int k, int cap, int max_parts,
+                         int max_slots, int32_t *items, int32_t *n_items, tsg_stream_t stream);
 int tsg_conv_fwd_tc4(const void *in0, int c0, const void *in1, int c1, int64_t n_in, const void *packed_w, int k,
                      int c_out, const int32_t *nbr, int64_t nbr_stride, const uint32_t *tile_mask, const int32_t *perm,
                      int64_t n_out_cap, const int32_t *n_out_dev, const void *sc_in0, int sc_c0, const void *sc_in1,
                      int sc_c1, const void *sc_packed_w, const int32_t *sc_idx, void *out, int out_dtype,
                      const float *bias, const void *residual, int relu, int num_sms, int32_t *sched, const int32_t *items,
-                     const int32_t *n_items, int max_slots, float *split_scratch, int32_t *split_state, tsg_stream_t stream);
+                     const int32_t *n_items, int max_slots, int max_parts, float *split_scratch, int32_t *split_state,
+                     tsg_stream_t stream);
 int tsg_unique_coords_dev(const int32_t *in_coords, int64_t n_cap, const int32_t *n_dev, int trunc_stride,
                           const int32_t *field_bits_host, int32_t *out_coords, int64_t out_cap, int32_t *first_idx,
                           int32_t *inverse, int32_t *m_dev, int32_t *status, void *ws, size_t ws_bytes, tsg_stream_t stream);

@@ -161,27 +161,34 @@ __device__ __forceinline__ void spin_until(const int *flag, int want) {
   }
 }
 
-// K split: the first of a tile's two work items to finish parks its fp32 accumulators in global memory ...
+// K split: every work item of a tile but the last to arrive parks its fp32 accumulators in its own slab of global memory.
+// Slab layout: [16-byte column chunk][tile row] float4, so the 32 lanes of a warp (32 consecutive tile rows) write and read
+// 512 contiguous bytes per instruction (a row-major slab made the exchange 13 us of a 53 us launch: every lane its own sector).
 template <int NCOLS>
-__device__ __forceinline__ void epi_store_partial(uint32_t taddr, float *part_row) {
+__device__ __forceinline__ void epi_store_partial(uint32_t taddr, float4 *slab_row) {   // slab_row: this lane's row, first chunk
 #pragma unroll
   for (int cc = 0; cc < NCOLS; cc += 16) {
     uint32_t v[16];
     tmem_ld16(taddr + cc, v);
 #pragma unroll
     for (int j = 0; j < 4; ++j)
-      __stcg(reinterpret_cast<float4 *>(part_row + cc + 4 * j),
+      __stcg(slab_row + (cc / 4 + j) * TC_BM,
              make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
                          __uint_as_float(v[4 * j + 3])));
   }
 }
 
-// ... and the second adds them to its own (part_row != nullptr) before bias / residual / ReLU.  a + b is commutative, so
-// the result does not depend on which item finished first.
+// ... and the last one sums all parts IN PART ORDER (its own from TMEM, the others from their slabs) before bias / residual /
+// ReLU: the result does not depend on which item arrived last.
+struct SplitParts {
+  const float4 *slab_row;   // part 0's slab: this lane's row, first chunk of the column block in hand; nullptr = not split
+  int nparts, mine;
+  size_t part_stride;       // float4s between the slabs of consecutive parts
+};
 template <int NCOLS, bool F32>
 __device__ __forceinline__ void epi_block(const TcParams &p, uint32_t taddr, bool have_acc, const float *bias_c, uint32_t stg,
                                           int lane, int rows_g, int c0, bool res_staged, bool no_store,
-                                          const float *part_row = nullptr) {
+                                          const SplitParts sp = SplitParts{nullptr, 1, 0, 0}) {
   const uint32_t my_row = stg + lane * V8_STG_PITCH;
   const int my_x = (lane >> 1) & 3;                       // chunk c of this thread's row sits at my_row + ((c ^ my_x) << 4)
   auto my_chunk = [&](int c) -> uint32_t { return my_row + (uint32_t)((c ^ my_x) << 4); };
@@ -195,15 +202,25 @@ __device__ __forceinline__ void epi_block(const TcParams &p, uint32_t taddr, boo
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] = 0u;
     }
-    if (part_row) {
+    if (sp.slab_row) {
+      float a[16];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float4 o = __ldcg(reinterpret_cast<const float4 *>(part_row + cc + 4 * j));
-        v[4 * j] = __float_as_uint(__uint_as_float(v[4 * j]) + o.x);
-        v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + o.y);
-        v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + o.z);
-        v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + o.w);
+      for (int j = 0; j < 16; ++j) a[j] = 0.f;
+      for (int q = 0; q < sp.nparts; ++q) {
+        if (q == sp.mine) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) a[j] += __uint_as_float(v[j]);
+        } else {
+          const float4 *src = sp.slab_row + (size_t)q * sp.part_stride + (cc / 4) * TC_BM;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 o = __ldcg(src + j * TC_BM);
+            a[4 * j] += o.x; a[4 * j + 1] += o.y; a[4 * j + 2] += o.z; a[4 * j + 3] += o.w;
+          }
+        }
       }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(a[j]);
     }
     float f[16];
 #pragma unroll
@@ -450,34 +467,41 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
       if (live) {
         const bool have_acc = mask_g != 0u || NPH > 1;   // a folded shortcut multiplies every live tile
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (buf * G + g) * (uint32_t)n_eff;
-        // K split: this warp and the warp with the same number in the tile's other work item own the same rows and
-        // columns.  Whichever arrives first (state 0 -> 1) stores its accumulators and raises the state again when they
-        // are visible; the other waits for that (state 3), adds them to its own and runs the real epilogue.
-        int role = -1;
-        float *part = nullptr;
+        // K split: this warp and the warps with the same number in the tile's other work items own the same rows and
+        // columns.  Every arrival but the last (counter state[0]) stores its accumulators in its own slab and reports them
+        // visible (state[1]); the last one waits for nparts - 1 such reports, sums the parts in part order and runs the real
+        // epilogue.  Nobody but the last arrival ever waits, and it waits only for warps that are already in their epilogue.
+        int role = -1;                       // -1 whole tile, 0 contributor, 1 finisher
+        SplitParts sp{nullptr, 1, 0, 0};
+        float4 *slab = nullptr;
         int *state = nullptr;
         if (is_split) {
-          state = p.split_state + (size_t)pslot * V8_EPI_WARPS + warp;
-          part = p.split_scratch + ((size_t)pslot * TC_BM + quad * 32 + lane) * n_eff;
+          const int nparts = split >> 8;
+          state = p.split_state + ((size_t)pslot * V8_EPI_WARPS + warp) * 2;
+          sp.part_stride = (size_t)(n_eff / 4) * TC_BM;
+          slab = reinterpret_cast<float4 *>(p.split_scratch) + (size_t)pslot * p.split_parts * sp.part_stride + quad * 32 + lane;
+          sp.nparts = nparts;
+          sp.mine = split & 0xff;
           int a = 0;
           if (lane == 0) a = atomicAdd(state, 1);
           a = __shfl_sync(0xffffffffu, a, 0);
-          role = a == 0 ? 0 : 1;
+          role = a == nparts - 1 ? 1 : 0;
           if (role == 1) {
-            if (a == 1 && lane == 0) spin_until(state, 3);
+            if (lane == 0) spin_until(state + 1, nparts - 1);
             __syncwarp();
             __threadfence();
             if (res_staged) prefetch_res(rows_g, cbase + cfirst, blk_cols(cfirst));
           }
         }
         if (role == 0) {
+          float4 *mine = slab + (size_t)sp.mine * sp.part_stride;
           for (int lc = cfirst; lc < n_eff; lc += cstep) {
-            if (blk_cols(lc) == 32 && !f32) epi_store_partial<32>(taddr + lc, part + lc);
-            else epi_store_partial<16>(taddr + lc, part + lc);
+            if (blk_cols(lc) == 32 && !f32) epi_store_partial<32>(taddr + lc, mine + (lc / 4) * TC_BM);
+            else epi_store_partial<16>(taddr + lc, mine + (lc / 4) * TC_BM);
           }
           __threadfence();
           __syncwarp();
-          if (lane == 0) atomicAdd(state, 1);
+          if (lane == 0) atomicAdd(state + 1, 1);
         } else {
           for (int lc = cfirst; lc < n_eff; lc += cstep) {     // lc: column inside the work item, c0: output channel
             const int ncols = blk_cols(lc), c0 = cbase + lc;
@@ -486,14 +510,18 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
               asm volatile("cp.async.wait_all;" ::: "memory");
               __syncwarp();
             }
-            const float *pr_ = role == 1 ? part + lc : nullptr;
-            if (f32) epi_block<16, true>(p, taddr + lc, have_acc, bias_s + c0, stg, lane, rows_g, c0, res_staged, no_store, pr_);
-            else if (ncols == 32) epi_block<32, false>(p, taddr + lc, have_acc, bias_s + c0, stg, lane, rows_g, c0, res_staged, no_store, pr_);
-            else epi_block<16, false>(p, taddr + lc, have_acc, bias_s + c0, stg, lane, rows_g, c0, res_staged, no_store, pr_);
+            SplitParts spc = sp;
+            if (role == 1) spc.slab_row = slab + (lc / 4) * TC_BM;
+            if (f32) epi_block<16, true>(p, taddr + lc, have_acc, bias_s + c0, stg, lane, rows_g, c0, res_staged, no_store, spc);
+            else if (ncols == 32) epi_block<32, false>(p, taddr + lc, have_acc, bias_s + c0, stg, lane, rows_g, c0, res_staged, no_store, spc);
+            else epi_block<16, false>(p, taddr + lc, have_acc, bias_s + c0, stg, lane, rows_g, c0, res_staged, no_store, spc);
           }
-          if (role == 1) {   // both parts are in: re-arm the pair's state for the next launch
+          if (role == 1) {   // all parts are in: re-arm the tile's counters for the next launch
             __syncwarp();
-            if (lane == 0) *state = 0;
+            if (lane == 0) {
+              state[0] = 0;
+              state[1] = 0;
+            }
           }
         }
       }
@@ -1100,20 +1128,22 @@ __global__ void pack_weights_kernel(const float *__restrict__ w, int K, int c_in
 }
 
 // Work-item list of a K-split launch.  One block; tiles are listed heaviest first (descending tile index of a mask-sorted
-// map).  A tile with more than `cap` active offsets becomes two items that sum the lower / upper half of its offsets —
-// the serial stage chain of the heaviest tile is what a launch with fewer tiles than SMs waits for (stride-16 level of the
-// benchmark: 120 tiles, 9.2 active offsets per SM on average but 27 on the critical path).  At most max_slots tiles are split.
+// map).  A tile with more than `cap` active offsets becomes ceil(active / cap) work items (at most max_parts) over disjoint,
+// equally sized runs of its active offsets: the serial stage chain of the heaviest tile is what a launch with fewer tiles than
+// SMs waits for (stride-16 level of the benchmark: 120 tiles, 9.2 active offsets per SM on average but 27 on the critical path).
+// At most max_slots tiles are split.
 __global__ void __launch_bounds__(1024, 1) conv_split_items_kernel(const unsigned *__restrict__ tile_mask, long long n_out,
-                                                                 const int *__restrict__ n_out_dev, int K, int cap, int max_slots,
-                                                                 int4 *__restrict__ items, int *__restrict__ n_items) {
+                                                                 const int *__restrict__ n_out_dev, int K, int cap, int max_parts,
+                                                                 int max_slots, int4 *__restrict__ items, int *__restrict__ n_items) {
   __shared__ int scan_a[1024], scan_b[1024];
   const long long n_rows = dev_count(n_out_dev, n_out);
   const int num_tiles = (int)((n_rows + TC_BM - 1) / TC_BM);
   const unsigned kmask = K >= 32 ? 0xffffffffu : ((1u << K) - 1u);
   const int per = (num_tiles + 1023) / 1024;
   const int i0 = threadIdx.x * per, i1 = min(num_tiles, i0 + per);   // positions in heavy-first order: tile = num_tiles - 1 - i
+  auto parts_of = [&](int x) -> int { return x > cap ? min(max_parts, (x + cap - 1) / cap) : 1; };
   int nsplit = 0;
-  for (int i = i0; i < i1; ++i) nsplit += __popc(tile_mask[num_tiles - 1 - i] & kmask) > cap ? 1 : 0;
+  for (int i = i0; i < i1; ++i) nsplit += parts_of(__popc(tile_mask[num_tiles - 1 - i] & kmask)) > 1 ? 1 : 0;
   // exclusive block scans (Hillis-Steele over 1024 partial sums): split tiles before this thread, then items
   auto block_scan = [&](int *buf, int v) -> int {
     buf[threadIdx.x] = v;
@@ -1131,28 +1161,30 @@ __global__ void __launch_bounds__(1024, 1) conv_split_items_kernel(const unsigne
   {
     int sb = sbase;
     for (int i = i0; i < i1; ++i) {
-      const bool sp = __popc(tile_mask[num_tiles - 1 - i] & kmask) > cap && sb < max_slots;
-      if (__popc(tile_mask[num_tiles - 1 - i] & kmask) > cap) ++sb;
-      nitems += sp ? 2 : 1;
+      const int np = parts_of(__popc(tile_mask[num_tiles - 1 - i] & kmask));
+      nitems += (np > 1 && sb < max_slots) ? np : 1;
+      if (np > 1) ++sb;
     }
   }
   int ibase = block_scan(scan_b, nitems);
   for (int i = i0; i < i1; ++i) {
     const int tile = num_tiles - 1 - i;
     const unsigned m = tile_mask[tile] & kmask;
-    const int x = __popc(m);
-    if (x > cap && sbase < max_slots) {
-      unsigned lo = 0, rest = m;
-      for (int b = 0; b < (x + 1) / 2; ++b) {   // lower half of the active offsets
-        lo |= rest & (0u - rest);
-        rest &= rest - 1;
+    const int x = __popc(m), np = parts_of(x);
+    if (np > 1 && sbase < max_slots) {
+      unsigned rest = m;
+      for (int q = 0; q < np; ++q) {            // part q: active offsets [q x / np, (q + 1) x / np) in ascending order
+        unsigned mine = 0;
+        for (int b = q * x / np; b < (q + 1) * x / np; ++b) {
+          mine |= rest & (0u - rest);
+          rest &= rest - 1;
+        }
+        items[ibase++] = make_int4(tile, (int)mine, q | (np << 8), sbase);
       }
-      items[ibase++] = make_int4(tile, (int)lo, 0 | (2 << 8), sbase);
-      items[ibase++] = make_int4(tile, (int)rest, 1 | (2 << 8), sbase);
     } else {
       items[ibase++] = make_int4(tile, (int)m, 0 | (1 << 8), 0);
     }
-    if (x > cap) ++sbase;
+    if (np > 1) ++sbase;
   }
   if (threadIdx.x == 1023) *n_items = scan_b[1023];
 }
@@ -1229,14 +1261,15 @@ static int fill_phase(TcPhase &h, const void *in0, int c0, const void *in1, int 
   return TSG_OK;
 }
 
-int tsg_conv_split_items(const uint32_t *tile_mask, int64_t n_out, const int32_t *n_out_dev, int k, int cap, int max_slots,
-                         int32_t *items, int32_t *n_items, tsg_stream_t stream) {
-  if (!tile_mask || !items || !n_items || k <= 0 || k > 32 || cap < 1 || max_slots < 0 || n_out <= 0 ||
-      (n_out + TC_BM - 1) / TC_BM > 4096) {
-    set_error("tsg_conv_split_items: need tile_mask, items, n_items, 0 < K <= 32, cap >= 1 and at most 4096 tiles");
+int tsg_conv_split_items(const uint32_t *tile_mask, int64_t n_out, const int32_t *n_out_dev, int k, int cap, int max_parts,
+                         int max_slots, int32_t *items, int32_t *n_items, tsg_stream_t stream) {
+  if (!tile_mask || !items || !n_items || k <= 0 || k > 32 || cap < 1 || max_parts < 2 || max_parts > 32 || max_slots < 0 ||
+      n_out <= 0 || (n_out + TC_BM - 1) / TC_BM > 4096) {
+    set_error("tsg_conv_split_items: need tile_mask, items, n_items, 0 < K <= 32, cap >= 1, 2 <= max_parts <= 32 and at most 4096 tiles");
     return TSG_ERR_INVALID;
   }
-  conv_split_items_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(tile_mask, n_out, n_out_dev, k, cap, max_slots, (int4 *)items, n_items);
+  conv_split_items_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(tile_mask, n_out, n_out_dev, k, cap, max_parts, max_slots,
+                                                                (int4 *)items, n_items);
   return check_launch("tsg_conv_split_items");
 }
 
@@ -1245,7 +1278,8 @@ int tsg_conv_fwd_tc4(const void *in0, int c0, const void *in1, int c1, int64_t n
                      int64_t n_out, const int32_t *n_out_dev, const void *sc_in0, int sc_c0, const void *sc_in1, int sc_c1,
                      const void *sc_packed_w, const int32_t *sc_idx, void *out, int out_dtype, const float *bias,
                      const void *residual, int relu, int num_sms_hint, int32_t *sched, const int32_t *items,
-                     const int32_t *n_items, int max_slots, float *split_scratch, int32_t *split_state, tsg_stream_t stream) {
+                     const int32_t *n_items, int max_slots, int max_parts, float *split_scratch, int32_t *split_state,
+                     tsg_stream_t stream) {
   if (c0 % 16 || c1 % 16 || c_out % 16 || c_out > 256 || c_out <= 0 || c0 <= 0 || k <= 0 || k > 32 ||
       (out_dtype != TSG_BF16 && out_dtype != TSG_F32)) {
     set_error("tsg_conv_fwd_tc: need c0,c1,c_out multiples of 16, c_out<=256, K<=32, out bf16/f32");
@@ -1293,14 +1327,15 @@ int tsg_conv_fwd_tc4(const void *in0, int c0, const void *in1, int c1, int64_t n
   p.relu = relu;
   p.sched = sched;
   if (items) {
-    if (!n_items || !sched || (max_slots > 0 && (!split_scratch || !split_state))) {
-      set_error("tsg_conv_fwd_tc: a work-item list needs n_items, the scheduler counters and (max_slots > 0) scratch + state");
+    if (!n_items || !sched || (max_slots > 0 && (!split_scratch || !split_state || max_parts < 2))) {
+      set_error("tsg_conv_fwd_tc: a work-item list needs n_items, the scheduler counters and (max_slots > 0) scratch + state + max_parts >= 2");
       return TSG_ERR_INVALID;
     }
     p.items = (const int4 *)items;
     p.n_items = n_items;
     p.split_scratch = split_scratch;
     p.split_state = split_state;
+    p.split_parts = max_parts;
   }
 #ifdef TSG_TC_TRACE  // profiling knock-outs (trace build only, wrong results): 1 no gathers, 2 no weight copies,
   const char *dbg_env = getenv("TSG_TC_DEBUG");  // 4 no MMAs, 8 no epilogue stores, 128 trace; re-read on every launch
@@ -1371,7 +1406,7 @@ int tsg_conv_fwd_tc4(const void *in0, int c0, const void *in1, int c1, int64_t n
 #undef TSG_TC_SMEM
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
-  const long long work = items ? num_tiles + max_slots : pair ? (num_tiles + 1) / 2 : (num_tiles + G - 1) / G * ns;
+  const long long work = items ? num_tiles + (long long)max_slots * (max_parts - 1) : pair ? (num_tiles + 1) / 2 : (num_tiles + G - 1) / G * ns;
   // programmatic dependent launch (TSG_TC_PDL=1, off by default): this grid's CTAs may be scheduled while the previous
   // kernel of the stream drains; the kernel executes griddepcontrol.wait before it reads anything.  Measured: +1 % with one
   // batch in flight, -8 % with two (early CTAs of one stream's next convolution hold the SMs the other stream's small
@@ -1432,7 +1467,7 @@ int tsg_conv_fwd_tc3(const void *in0, int c0, const void *in1, int c1, int64_t n
                      const void *residual, int relu, int num_sms_hint, int32_t *sched, tsg_stream_t stream) {
   return tsg_conv_fwd_tc4(in0, c0, in1, c1, n_in, packed_w, k, c_out, nbr, nbr_stride, tile_mask, perm, n_out, n_out_dev, sc_in0,
                           sc_c0, sc_in1, sc_c1, sc_packed_w, sc_idx, out, out_dtype, bias, residual, relu, num_sms_hint, sched,
-                          nullptr, nullptr, 0, nullptr, nullptr, stream);
+                          nullptr, nullptr, 0, 0, nullptr, nullptr, stream);
 }
 
 int tsg_conv_fwd_tc2(const void *in0, int c0, const void *in1, int c1, int64_t n_in, const void *packed_w, int k,

@@ -212,8 +212,9 @@ struct TcParams {
   // enumeration; tiles with many active offsets are summed by two items (on two SMs) and combined in the epilogue
   const int4 *items;
   const int *n_items;    // device: number of work items
-  float *split_scratch;  // slots x 128 x n_eff fp32 partial sums
-  int *split_state;      // slots x 8 hand-off words, zero between launches
+  float *split_scratch;  // slots x split_parts slabs of (n_eff / 4) x 128 float4 partial sums
+  int *split_state;      // slots x 8 epilogue warps x {arrivals, parked parts}, zero between launches
+  int split_parts;       // slabs per slot (most parts a tile is split into)
   int lookahead;         // planner throttle: a ticket is drawn when fewer than lookahead * stages + 4 planned stages are left
 };
 

@@ -697,25 +697,26 @@ def _sched_ws(device) -> torch.Tensor:
 
 
 DYNAMIC_TILES = os.environ.get("TSG_DYNAMIC_TILES", "1") != "0"   # A/B switch: in-kernel dynamic tile scheduler
-SPLIT_K = os.environ.get("TSG_SPLIT_K", "0") != "0"               # K-split work items for launches with few tiles (off: measured -4 % on the
-                                                                  # stride-16 launches alone, +1.5 % on the step with three batches in flight)
+SPLIT_K = os.environ.get("TSG_SPLIT_K", "0") != "0"               # K-split work items for launches with few tiles
 SPLIT_MAX_TILES = int(os.environ.get("TSG_SPLIT_MAX_TILES", "222"))   # ... up to 1.5 tiles per SM of a B200
-SPLIT_CAP = int(os.environ.get("TSG_SPLIT_CAP", "14"))             # a tile with more active offsets becomes two work items
+SPLIT_CAP = int(os.environ.get("TSG_SPLIT_CAP", "14"))             # a tile with more active offsets is summed by ceil(active / cap) items
+SPLIT_PARTS = int(os.environ.get("TSG_SPLIT_PARTS", "2"))          # ... at most this many (measured: profiles/r02/ksplit_nway.txt)
 
 
 class SplitItems:
     """Work-item list of a K-split tensor-core launch (tsg_conv_split_items) for one (mask-sorted) kernel map."""
 
     def __init__(self, tile_mask: torch.Tensor, n_out: int, k: int, n_dev: Optional[torch.Tensor] = None,
-                 cap: int = 0, max_slots: int = 0):
+                 cap: int = 0, max_slots: int = 0, max_parts: int = 0):
         tiles = (int(n_out) + 127) // 128
         self.max_slots = int(max_slots) if max_slots else min(tiles, 128)
+        self.max_parts = max(2, int(max_parts) if max_parts else SPLIT_PARTS)
         dev = tile_mask.device
-        self.items = torch.empty((tiles + self.max_slots, 4), dtype=torch.int32, device=dev)
+        self.items = torch.empty((tiles + self.max_slots * (self.max_parts - 1), 4), dtype=torch.int32, device=dev)
         self.n_items = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.state = torch.zeros(self.max_slots * 8, dtype=torch.int32, device=dev)
-        call("tsg_conv_split_items", ptr(tile_mask), int(n_out), ptr(n_dev), int(k), int(cap or SPLIT_CAP), self.max_slots,
-             ptr(self.items), ptr(self.n_items), stream())
+        self.state = torch.zeros(self.max_slots * 16, dtype=torch.int32, device=dev)
+        call("tsg_conv_split_items", ptr(tile_mask), int(n_out), ptr(n_dev), int(k), int(cap or SPLIT_CAP), self.max_parts,
+             self.max_slots, ptr(self.items), ptr(self.n_items), stream())
 
     @staticmethod
     def wanted(n_out: int, k: int) -> bool:
@@ -777,11 +778,11 @@ def conv_forward_tc(in0: torch.Tensor, in1: Optional[torch.Tensor], packed_w: to
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
     if split is not None and DYNAMIC_TILES:
-        scratch = torch.empty((split.max_slots * 128 * c_out,), dtype=torch.float32, device=in0.device)
+        scratch = torch.empty((split.max_slots * split.max_parts * 128 * c_out,), dtype=torch.float32, device=in0.device)
         call("tsg_conv_fwd_tc4", ptr(in0), c0, ptr(in1), c1, in0.shape[0], ptr(packed_w), k, c_out, ptr(nbr), nbr_stride,
              ptr(tile_mask), ptr(perm), int(n_out), ptr(n_dev), ptr(s0), sc0, ptr(s1), sc1, ptr(sw), ptr(sidx), ptr(out),
              L.DTYPES[out_dtype], ptr(bias), ptr(residual), int(relu), int(num_sms), ptr(_sched_ws(in0.device)),
-             ptr(split.items), ptr(split.n_items), split.max_slots, ptr(scratch), ptr(split.state), stream())
+             ptr(split.items), ptr(split.n_items), split.max_slots, split.max_parts, ptr(scratch), ptr(split.state), stream())
     else:
         call("tsg_conv_fwd_tc3", ptr(in0), c0, ptr(in1), c1, in0.shape[0], ptr(packed_w), k, c_out, ptr(nbr), nbr_stride,
              ptr(tile_mask), ptr(perm), int(n_out), ptr(n_dev), ptr(s0), sc0, ptr(s1), sc1, ptr(sw), ptr(sidx), ptr(out), L.DTYPES[out_dtype],

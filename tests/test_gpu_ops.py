@@ -457,8 +457,8 @@ def test_conv_tensor_core_column_split(ts, monkeypatch):
 
 def test_conv_tensor_core_k_split(ts):
     """K-split work items (tsg_conv_split_items + tsg_conv_fwd_tc4): launches with about as many tiles as SMs sum heavy
-    tiles with two work items on two SMs.  The list must cover every (tile, offset) exactly once; the result must match the
-    oracle, must not depend on which item finishes first (run-to-run torch.equal) and must stay within fp32 summation-order
+    tiles with up to four work items on as many SMs.  The list must cover every (tile, offset) exactly once; the result must match the
+    oracle, must not depend on which item finishes last (run-to-run torch.equal) and must stay within fp32 summation-order
     round-off of the unsplit launch; folded shortcut, residual, ReLU and fp32 output ride along."""
     from taseg_b200 import ops
     rng = np.random.default_rng(11)
@@ -468,7 +468,7 @@ def test_conv_tensor_core_k_split(ts):
     assert 64 * 128 < n <= ops.SPLIT_MAX_TILES * 128
     km = ops.build_kmap(ops.Table.from_coords(cu(c)), n, cu(c), T.get_kernel_offsets(3, 1))
     nbr_s, mask_s, perm = km.sorted()
-    sp = ops.SplitItems(mask_s, n, 27)        # (KernelMap.split_items() returns it only when TSG_SPLIT_K=1: off by default)
+    sp = ops.SplitItems(mask_s, n, 27, cap=7, max_parts=4)   # (KernelMap.split_items() returns one only when TSG_SPLIT_K=1: off by default)
     n_items = int(sp.n_items.item())
     items = npy(sp.items[:n_items])
     tiles = (n + 127) // 128
@@ -477,11 +477,11 @@ def test_conv_tensor_core_k_split(ts):
         assert 0 <= tile < tiles and (cover[tile] & (int(m) & 0x7ffffff)) == 0
         cover[tile] |= int(m) & 0x7ffffff
         parts = part >> 8
-        assert parts in (1, 2) and (part & 0xff) < parts and 0 <= slot < sp.max_slots
-        if parts == 1:
-            assert bin(int(m) & 0x7ffffff).count("1") <= ops.SPLIT_CAP or slot == 0
+        assert 1 <= parts <= sp.max_parts and (part & 0xff) < parts and 0 <= slot < sp.max_slots
+        assert bin(int(m) & 0x7ffffff).count("1") <= 7 or (parts == 1 and slot == 0)
     assert np.array_equal(cover, npy(mask_s).astype(np.int64) & 0x7ffffff), "work items do not cover the tile masks"
     assert n_items > tiles, "no tile was split: the case does not exercise the partial-sum path"
+    assert int((items[:, 2] >> 8).max()) >= 3, "no tile was split more than two ways"
     nbmaps, nbsizes = npy(km.nbmaps), npy(km.nbsizes)
     for c_in, c_out, od in [(256, 256, torch.bfloat16), (64, 128, torch.float32), (96, 96, torch.bfloat16)]:
         x = torch.randn(n, c_in, device="cuda").bfloat16()
