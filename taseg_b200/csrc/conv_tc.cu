@@ -541,10 +541,12 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
     // executes tcgen05.fence::after_thread_sync — accumulation order, and the result, are those of a single issuer.
     const int mw = warp - V8_MMA_WARP;
     if (PAIR && rank != 0) {
-      // peer CTA of a pair: no MMA issue.  Warp 8 relays "my half of stage s is full" to the leader, warp 9 only keeps
-      // the plan ring moving.
+      // peer CTA of a pair: no MMA issue.  Its two warps relay "my half of stage s is full" to the leader, alternating
+      // stages like the leader's two issuers do: one thread needs ~800 cycles per stage for wait + proxy fence + remote
+      // arrival (stage-level trace, profiles/r02/stage_trace_l4_256.txt: the pair kernel ran at exactly that rate with a
+      // single relay thread, whatever the stage size).
       if (lane == 0) {
-        Ring r;
+        uint32_t slot0 = 0, phase0 = 0, gpar = 0;
         for (;;) {
           const volatile Plan *pl = plan_wait();
           if (pl->tile < 0) {
@@ -552,13 +554,27 @@ __global__ void __launch_bounds__(V8_THREADS, 1) conv_tc_kernel(const TcParams p
             break;
           }
           const int n = pl->n & 0xffff;
-          if (mw == 0) {
-            for (int i = 0; i < n; ++i) {
-              mbar_wait(full0 + 8 * r.slot, r.phase);   // this CTA's rows (cp.async) and weight half (bulk copy) have landed
-              fence_async_proxy();                      // ... ordered before the tensor cores' (async proxy) reads
-              mbar_arrive_remote(pfull0 + 8 * r.slot, 0);
-              r.advance(nst);
+          const int i0 = (int)((mw ^ gpar) & 1u);
+          uint32_t slot = slot0 + i0, phase = phase0;
+          if (slot >= nst) {
+            slot -= nst;
+            phase ^= 1;
+          }
+          for (int i = i0; i < n; i += 2) {
+            mbar_wait(full0 + 8 * slot, phase);       // this CTA's rows (cp.async) and weight half (bulk copy) have landed
+            fence_async_proxy();                      // ... ordered before the tensor cores' (async proxy) reads
+            mbar_arrive_remote(pfull0 + 8 * slot, 0);
+            slot += 2;
+            if (slot >= nst) {
+              slot -= nst;
+              phase ^= 1;
             }
+          }
+          gpar ^= (uint32_t)n & 1u;
+          slot0 += (uint32_t)n;
+          while (slot0 >= nst) {
+            slot0 -= nst;
+            phase0 ^= 1;
           }
           plan_release_lane();
         }
