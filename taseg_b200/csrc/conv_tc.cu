@@ -43,7 +43,7 @@
 // thread, per-stage bookkeeping done by all 16 producer warps (~2000 cycles of branchy scalar code per group stage) and a
 // thread-per-row epilogue; v9 moved the stage enumeration into the planner warp, v12 doubled and coalesced the epilogue,
 // v13 made the producer hand-off asynchronous, v14/v15 alternate two MMA issuers.  What bounds v18 (ncu of every layer
-// class, profiles/r02/ncu_conv_v18_summary.md): the shared-memory data pipe on the 96-channel layers at strides 1-2
+// class, profiles/r02/ncu_conv_final_summary.md): the shared-memory data pipe on the 96-channel layers at strides 1-2
 // (LDGSTS + LDS/STS wavefronts 38-44 % of cycles + tensor-core operand reads 24-33 %), L2 -> SM weight traffic on 256 -> 256
 // at stride 8 (10.4 TB/s), the producers' latency chain and ~10 us of fixed cost per launch on the other one-tile launches.
 #include <cstdlib>

@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """SASS opcode histogram of the hot kernels (cuobjdump -sass on the built objects): which Blackwell instructions each one uses.
-    python tools/sass_hist.py > profiles/r02/sass_opcodes_v18.md"""
+    python tools/sass_hist.py > profiles/r02/sass_opcodes_final.md"""
 import collections
 import os
 import re
