@@ -13,6 +13,7 @@ device -> host copy of the logits every step.  `--impl reference` times the refe
 """
 import argparse
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -260,9 +261,14 @@ def other_configs(rank, world, steps=6, warmup=2):
         reducer = parallel.GradientReducer(model.parameters(), bucket_mb=25.0)
         comm = []
 
-        def step_train():
+        last_loss = [None]
+
+        def step_train():      # the loss of step i is read (device -> host) after step i + 1 has been enqueued: logged every step, never a stall
             batch = {"lidar_ms": ts.SparseTensor(feats.clone(), coords), "targets_ms": ts.SparseTensor(labels, coords)}
-            return parallel.train_step(model, batch, opt, reducer, amp_dtype=torch.bfloat16, comm_events=comm)
+            loss = parallel.train_step(model, batch, opt, reducer, amp_dtype=torch.bfloat16, comm_events=comm, sync=False)
+            if last_loss[0] is not None and not math.isfinite(float(last_loss[0])):
+                raise RuntimeError("training loss is not finite")
+            last_loss[0] = loss
 
         ms = timed(step_train, n_streams=1)
         exposed = [a.elapsed_time(b) for a, b in comm[-steps:]] if comm else [0.0]

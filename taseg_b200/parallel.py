@@ -12,6 +12,8 @@ from typing import Iterable, List, Optional, Sequence
 import torch
 import torch.distributed as dist
 
+from .utils.lazy import LazyScalar
+
 
 def shard_indices(n_items: int, rank: int, world: int, pad: bool = True) -> List[int]:
     """Items of rank `rank`: torch DistributedSampler semantics without shuffling (the reference's eval sampler,
@@ -112,10 +114,12 @@ class GradientReducer:
 
 def train_step(model: torch.nn.Module, batch_dict: dict, optimizer: torch.optim.Optimizer,
                reducer: Optional[GradientReducer] = None, amp_dtype: Optional[torch.dtype] = torch.bfloat16,
-               clip_grad_norm: Optional[float] = 10.0, comm_events: Optional[list] = None) -> float:
+               clip_grad_norm: Optional[float] = 10.0, comm_events: Optional[list] = None, sync: bool = True):
     """One training step of the reference loop (R/train.py:399-417) with bf16 autocast instead of fp16 + GradScaler:
     forward -> loss -> backward (gradient buckets all-reduced while backward runs) -> clip -> optimizer step.
-    comm_events: optional list that receives one (start, end) CUDA event pair per step around `reducer.finish()`."""
+    comm_events: optional list that receives one (start, end) CUDA event pair per step around `reducer.finish()`.
+    sync=True returns the loss as a float (the host waits for the step); sync=False returns a LazyScalar, so a loop that
+    logs the loss of step i after it has enqueued step i + 1 never leaves the GPU without queued work."""
     model.train()
     optimizer.zero_grad(set_to_none=True)
     dev_type = next(model.parameters()).device.type
@@ -134,4 +138,4 @@ def train_step(model: torch.nn.Module, batch_dict: dict, optimizer: torch.optim.
     if clip_grad_norm:
         torch.nn.utils.clip_grad_norm_(model.parameters(), clip_grad_norm)
     optimizer.step()
-    return float(loss.detach())
+    return float(loss.detach()) if sync else LazyScalar(loss)

@@ -15,6 +15,7 @@ from torch import nn
 from .. import ops
 from ..operators import cat
 from ..tensor import PointTensor
+from ..utils.lazy import LazyScalar
 from .blocks import BLOCKS, BasicConvolutionBlock, BasicDeconvolutionBlock, norm
 from .utils import initial_voxelize, point_to_voxel, voxel_to_point
 from .. import nn as spnn
@@ -145,7 +146,8 @@ class _SparseUNet(nn.Module):
             target = batch_dict[key].F.long().cuda(non_blocking=True)
             crit = self.criterion or (lambda o, t: nn.functional.cross_entropy(o, t, ignore_index=self.model_cfgs.IGNORE_LABEL))
             loss = crit(out, target)
-            return {'loss': loss}, {'loss': loss.item()}, {'loss': loss.item()}
+            lazy = LazyScalar(loss)      # read like a float; the host waits for it only when the logger looks (utils/lazy.py)
+            return {'loss': loss}, {'loss': lazy}, {'loss': lazy}
         return self.eval_outputs(batch_dict, x, out, return_logit or return_tta)
 
     def eval_outputs(self, batch_dict, x, out, want_prob):

@@ -49,7 +49,7 @@ def main():
 
     def step():
         batch = {"lidar_ms": ts.SparseTensor(feats.clone(), coords), "targets_ms": ts.SparseTensor(labels, coords)}
-        return parallel.train_step(model, batch, opt, reducer, amp_dtype=torch.bfloat16)
+        return parallel.train_step(model, batch, opt, reducer, amp_dtype=torch.bfloat16, sync=os.environ.get("TRAIN_SYNC", "0") == "1")
 
     for _ in range(args.warmup):
         loss = step()
@@ -59,6 +59,22 @@ def main():
         loss = step()
         torch.cuda.synchronize()
         torch.cuda.cudart().cudaProfilerStop()
+    if os.environ.get("HOST_PROFILE"):     # where the host spends its time enqueuing a step (cProfile, host time only)
+        import cProfile
+        import pstats
+        import time
+        pr = cProfile.Profile()
+        t0 = time.perf_counter()
+        pr.enable()
+        for _ in range(5):
+            loss = step()
+        pr.disable()
+        t1 = time.perf_counter()
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        print("host enqueue %.2f ms per step, drain %.2f ms after the last enqueue" % ((t1 - t0) * 200, (t2 - t1) * 1e3))
+        pstats.Stats(pr).sort_stats("tottime").print_stats(int(os.environ["HOST_PROFILE"]))
+        pstats.Stats(pr).sort_stats("cumulative").print_stats(int(os.environ["HOST_PROFILE"]))
     if world > 1:
         dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -79,7 +95,7 @@ def main():
     if rank == 0:
         print(json.dumps({"metric": "train step (MinkUNetMs mk34 cr1.0, 3-frame KITTI shape, bf16 autocast)", "n_gpus": world,
                           "batch_per_gpu": args.batch, "sync_bn": bool(args.sync_bn and world > 1), "ms_per_step": ms, "scans_per_s": args.batch * world / (ms * 1e-3),
-                          "loss": loss, "voxels_per_gpu": int(coords.shape[0]),
+                          "loss": float(loss), "voxels_per_gpu": int(coords.shape[0]),
                           "allreduce_bytes_per_step": reducer.bytes_per_step(), "buckets": len(reducer.buckets),
                           "param_checksum_spread_over_ranks": spread, "bn_running_stat_spread_over_ranks": bn_spread,
                           "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}))
