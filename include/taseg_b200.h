@@ -295,6 +295,9 @@ int tsg_conv_wgrad_tc(const void *in, int64_t n_in, int c_in, const void *grad_o
 size_t tsg_bn_ws_bytes(int64_t n, int c);
 int tsg_bn_stats(const void *x, int dtype, int64_t n, int c, float eps, float momentum, float *running_mean, float *running_var,
                  float *mean, float *invstd, void *ws, size_t ws_bytes, tsg_stream_t stream);
+/* tsg_bn_stats + nn.BatchNorm1d's `num_batches_tracked += 1` (int64 device scalar, may be NULL) in the same launch */
+int tsg_bn_stats2(const void *x, int dtype, int64_t n, int c, float eps, float momentum, float *running_mean, float *running_var,
+                  int64_t *num_batches_tracked, float *mean, float *invstd, void *ws, size_t ws_bytes, tsg_stream_t stream);
 int tsg_bn_apply(const void *x, int dtype, int64_t n, int c, const float *mean, const float *invstd, const float *gamma,
                  const float *beta, int relu, void *y, tsg_stream_t stream);
 int tsg_bn_backward(const void *x, const void *dy, int dtype, int64_t n, int c, const float *mean, const float *invstd,
@@ -322,6 +325,11 @@ int tsg_bn_backward(const void *x, const void *dy, int dtype, int64_t n, int c, 
 size_t tsg_conv_pack_bytes(int k, int c0, int c1, int c_out);
 int tsg_conv_pack_weights(const float *weight, int k, int c_in, int c_out, int c0, int c1,
                           const float *out_scale, void *packed, tsg_stream_t stream);
+/* ... from a strided (K, c_in, c_out) view (element strides): W[k]^T for the data gradient and column blocks of wide layers are
+ * packed straight from the parameter, without a transposed / sliced copy (TS/backend/convolution/convolution_cuda.cu:229-246
+ * multiplies by the transposed kernel through cuBLAS flags) */
+int tsg_conv_pack_weights2(const float *weight, int k, int c_in, int c_out, int64_t stride_k, int64_t stride_cin,
+                           int64_t stride_cout, int c0, int c1, const float *out_scale, void *packed, tsg_stream_t stream);
 int tsg_kmap_tile_mask(const int32_t *nbr, int k, int64_t n_out, uint32_t *tile_mask, tsg_stream_t stream);
 int tsg_conv_fwd_tc(const void *in0, int c0, const void *in1, int c1, int64_t n_in, const void *packed_w, int k,
                     int c_out, const int32_t *nbr, int64_t nbr_stride, const uint32_t *tile_mask, const int32_t *perm, int64_t n_out,

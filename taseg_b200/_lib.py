@@ -107,7 +107,7 @@ KERNELS_PER_CALL = {"tsg_table_build": 2, "tsg_coord_table_build": 2, "tsg_kmap_
                     "tsg_sort_pairs": 4, "tsg_unique_coords": 7, "tsg_unique_hash": 11, "tsg_aggregate_quantize": 4,
                     "tsg_compact_rows": 3, "tsg_kmap_sort_rows": 5, "tsg_aggregate_quantize_nus": 4, "tsg_aggregate_quantize_dev": 4,
                     "tsg_unique_coords_dev": 7, "tsg_coord_table_build_dev": 2, "tsg_kmap_sort_rows_dev": 4, "tsg_kmap_sort_rows_dev2": 3,
-                    "tsg_kmap_transpose_dev": 2, "tsg_voxelize_plan": 5, "tsg_kmap_pair_list": 4, "tsg_bn_stats": 2, "tsg_bn_backward": 3}
+                    "tsg_kmap_transpose_dev": 2, "tsg_voxelize_plan": 5, "tsg_kmap_pair_list": 4, "tsg_bn_stats": 2, "tsg_bn_stats2": 2, "tsg_bn_backward": 3}
 launch_count = 0
 
 

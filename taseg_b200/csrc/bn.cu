@@ -148,7 +148,9 @@ constexpr int BN_FW = 32;   // warps of a finalize CTA
 // w, w + 32, ... in order; the warp results are merged in warp order through shared memory.  Fixed order = deterministic.
 __global__ void __launch_bounds__(1024) bn_finalize_kernel(const float *__restrict__ partial, int nb, int c, float eps, float momentum,
                                                           float *__restrict__ running_mean, float *__restrict__ running_var,
-                                                          float *__restrict__ mean, float *__restrict__ invstd) {
+                                                          float *__restrict__ mean, float *__restrict__ invstd,
+                                                          long long *__restrict__ batches_tracked) {
+  if (batches_tracked && blockIdx.x == 0 && threadIdx.x == 0) *batches_tracked += 1;   // nn.BatchNorm1d's num_batches_tracked
   // Two plain passes over the stripe records instead of a chain of Chan updates (a double-precision division per stripe
   // and lane made the first version 90 us per call): mean = sum n_b m_b / N, then M2 = sum [M2_b + n_b (m_b - mean)^2].
   __shared__ double sh[BN_FW][2][32];
@@ -318,6 +320,12 @@ size_t tsg_bn_ws_bytes(int64_t n, int c) {
  * running_mean / running_var (may be NULL) are updated as nn.BatchNorm1d does (momentum, unbiased variance). */
 int tsg_bn_stats(const void *x, int dtype, int64_t n, int c, float eps, float momentum, float *running_mean, float *running_var,
                  float *mean, float *invstd, void *ws, size_t ws_bytes, tsg_stream_t stream) {
+  return tsg_bn_stats2(x, dtype, n, c, eps, momentum, running_mean, running_var, nullptr, mean, invstd, ws, ws_bytes, stream);
+}
+
+/* ... and num_batches_tracked (int64 device scalar, may be NULL) incremented in the same launch */
+int tsg_bn_stats2(const void *x, int dtype, int64_t n, int c, float eps, float momentum, float *running_mean, float *running_var,
+                  int64_t *num_batches_tracked, float *mean, float *invstd, void *ws, size_t ws_bytes, tsg_stream_t stream) {
   if (c <= 0 || c % 8 || c > BN_MAXC || n <= 0 || (dtype != TSG_F32 && dtype != TSG_BF16)) {
     set_error("tsg_bn_stats: need n > 0, c a multiple of 8 <= 1024, fp32 or bf16 rows");
     return TSG_ERR_UNSUPPORTED;
@@ -335,7 +343,7 @@ int tsg_bn_stats(const void *x, int dtype, int64_t n, int c, float eps, float mo
     bn_reduce_kernel<__nv_bfloat16, 0><<<nb, BN_THREADS, smem, stream>>>((const __nv_bfloat16 *)x, nullptr, n, c, rows, nullptr,
                                                                         nullptr, nullptr, nullptr, 0, (float *)ws);
   bn_finalize_kernel<<<(c + 31) / 32, 1024, 0, stream>>>((const float *)ws, nb, c, eps, momentum, running_mean, running_var, mean,
-                                                         invstd);
+                                                         invstd, (long long *)num_batches_tracked);
   return check_launch("tsg_bn_stats");
 }
 

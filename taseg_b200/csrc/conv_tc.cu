@@ -1123,8 +1123,9 @@ static SlicePlan slice_plan(int c0, int c1) {
 // W (K, c_in, c_out) fp32 -> per (virtual offset kv, slice j) a [c_out][64] bf16 block, K-major, 128B-swizzled: the byte
 // image the MMA reads, so a linear bulk copy stages it.  Column 8 c + e of block (kv, j) is channel 8 cc + e of offset
 // kv P + ksub with 8 j + c = ksub cpo + cc.  Optional per-output-channel scale (folded BatchNorm).
-__global__ void pack_weights_kernel(const float *__restrict__ w, int K, int c_in, int c_out, int P, int Q, int cpo,
-                                    const float *__restrict__ out_scale, __nv_bfloat16 *__restrict__ packed) {
+__global__ void pack_weights_kernel(const float *__restrict__ w, int K, int c_in, int c_out, long long sk, long long sci,
+                                    long long sco, int P, int Q, int cpo, const float *__restrict__ out_scale,
+                                    __nv_bfloat16 *__restrict__ packed) {   // sk / sci / sco: element strides of W (a transposed or sliced view packs without a copy)
   const int KV = (K + P - 1) / P;
   const long long total = (long long)KV * Q * c_out * TC_KB;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
@@ -1135,7 +1136,7 @@ __global__ void pack_weights_kernel(const float *__restrict__ w, int K, int c_in
     const int f = 8 * j + (col >> 3), ksub = f / cpo, cc = f - ksub * cpo;
     const int k = kv * P + ksub, ch = cc * 8 + (col & 7);
     float v = 0.f;
-    if (k < K && ch < c_in) v = w[((long long)k * c_in + ch) * c_out + n];
+    if (k < K && ch < c_in) v = w[k * sk + ch * sci + n * sco];
     if (out_scale) v *= out_scale[n];
     const long long blk = ((long long)kv * Q + j) * c_out * TC_KB;
     const int sw = (((col >> 3) ^ (n & 7)) << 3) | (col & 7);
@@ -1218,6 +1219,11 @@ size_t tsg_conv_pack_bytes(int k, int c0, int c1, int c_out) {
 
 int tsg_conv_pack_weights(const float *weight, int k, int c_in, int c_out, int c0, int c1, const float *out_scale,
                           void *packed, tsg_stream_t stream) {
+  return tsg_conv_pack_weights2(weight, k, c_in, c_out, (int64_t)c_in * c_out, c_out, 1, c0, c1, out_scale, packed, stream);
+}
+
+int tsg_conv_pack_weights2(const float *weight, int k, int c_in, int c_out, int64_t stride_k, int64_t stride_cin,
+                           int64_t stride_cout, int c0, int c1, const float *out_scale, void *packed, tsg_stream_t stream) {
   if (c0 % 16 || c1 % 16 || c_out % 16 || c_out > 256 || c_out <= 0 || c0 <= 0 || c0 + c1 < c_in) {
     set_error("tsg_conv_pack_weights: need c0,c1,c_out multiples of 16, c_out<=256, c0+c1>=c_in");
     return TSG_ERR_UNSUPPORTED;
@@ -1228,8 +1234,8 @@ int tsg_conv_pack_weights(const float *weight, int k, int c_in, int c_out, int c
     return TSG_ERR_UNSUPPORTED;
   }
   const long long total = (long long)((k + sp.P - 1) / sp.P) * sp.Q * c_out * TC_KB;
-  pack_weights_kernel<<<grid_for(total, 256), 256, 0, stream>>>(weight, k, c_in, c_out, sp.P, sp.Q, sp.cpo, out_scale,
-                                                                (__nv_bfloat16 *)packed);
+  pack_weights_kernel<<<grid_for(total, 256), 256, 0, stream>>>(weight, k, c_in, c_out, stride_k, stride_cin, stride_cout, sp.P, sp.Q,
+                                                                sp.cpo, out_scale, (__nv_bfloat16 *)packed);
   return check_launch("tsg_conv_pack_weights");
 }
 

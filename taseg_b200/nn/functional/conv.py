@@ -86,10 +86,7 @@ _PACKS = {}
 def _pack(w: torch.Tensor, cols):
     """(K, c_in, c_out) -> packed image of W[:, :, cols[0]:cols[1]] with c_in zero-padded to a multiple of 16."""
     k, c_in, c_out = w.shape
-    w = w[:, :, cols[0]:cols[1]]
-    if c_in % 16:
-        w = torch.nn.functional.pad(w, (0, 0, 0, 16 - c_in % 16))
-    return ops.pack_weights(w.contiguous(), w.shape[1])
+    return ops.pack_weights(w[:, :, cols[0]:cols[1]], (c_in + 15) // 16 * 16)      # a strided view: packed without a copy, rows past c_in are zero
 
 
 def packed_weights(param: Optional[torch.Tensor], weight: torch.Tensor, transposed_w: bool, cols) -> torch.Tensor:
@@ -232,7 +229,12 @@ def conv3d(input: SparseTensor, weight: torch.Tensor, kernel_size: Union[int, Li
     param = weight if (weight.dim() == 3 and weight.is_leaf) else None
     if torch.is_autocast_enabled():        # reference: custom_fwd(cast_inputs=torch.half) (conv.py:19)
         dt = torch.get_autocast_dtype('cuda')
-        feats, weight = feats.to(dt), weight.to(dt)
+        feats = feats.to(dt)
+        # A leaf fp32 parameter is NOT cast: the tensor-core paths read its packed bf16 images (cached per parameter
+        # version) and the weight gradient comes out of the kernels in fp32, so the cast, the fp32 -> bf16 rounding of the
+        # gradient and autograd's cast back (three launches per convolution and step) buy nothing.
+        if param is None:
+            weight = weight.to(dt)
 
     if kernel_size == (1, 1, 1) and stride == (1, 1, 1) and dilation == (1, 1, 1):
         out_stride, out_coords = input.stride, input.coords

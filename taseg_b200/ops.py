@@ -562,15 +562,17 @@ def _bn_ws(x: torch.Tensor) -> torch.Tensor:
 
 
 def bn_stats(x: torch.Tensor, eps: float, momentum: float, running_mean: Optional[torch.Tensor],
-             running_var: Optional[torch.Tensor]):
-    """(mean, invstd) fp32 of the rows of x; running statistics (fp32, contiguous) updated in place."""
+             running_var: Optional[torch.Tensor], batches_tracked: Optional[torch.Tensor] = None):
+    """(mean, invstd) fp32 of the rows of x; running statistics (fp32, contiguous) updated in place, `batches_tracked` (int64
+    scalar on the device) incremented in the same launch."""
+    assert batches_tracked is None or (batches_tracked.dtype == torch.int64 and batches_tracked.is_cuda)
     x = x.contiguous()
     n, c = x.shape
     mean = torch.empty(c, dtype=torch.float32, device=x.device)
     invstd = torch.empty(c, dtype=torch.float32, device=x.device)
     ws = _bn_ws(x)
-    call("tsg_bn_stats", ptr(x), L.DTYPES[x.dtype], n, c, float(eps), float(momentum), ptr(running_mean), ptr(running_var),
-         ptr(mean), ptr(invstd), ptr(ws), ws.numel(), stream())
+    call("tsg_bn_stats2", ptr(x), L.DTYPES[x.dtype], n, c, float(eps), float(momentum), ptr(running_mean), ptr(running_var),
+         ptr(batches_tracked), ptr(mean), ptr(invstd), ptr(ws), ws.numel(), stream())
     return mean, invstd
 
 
@@ -662,10 +664,10 @@ def pack_weights(weight: torch.Tensor, c0: int, c1: int = 0, out_scale: Optional
         if out_scale is not None:
             out_scale = torch.nn.functional.pad(out_scale, (0, c_out_pad - c_out))
         c_out = c_out_pad
-    w = w.contiguous()
     nbytes = int(L.lib().tsg_conv_pack_bytes(k, c0, c1, c_out))
     packed = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
-    call("tsg_conv_pack_weights", ptr(w), k, c_in, c_out, c0, c1, ptr(out_scale), ptr(packed), stream())
+    sk, sci, sco = w.stride()          # transposed / column-sliced views are packed in place (element strides)
+    call("tsg_conv_pack_weights2", ptr(w), k, c_in, c_out, sk, sci, sco, c0, c1, ptr(out_scale), ptr(packed), stream())
     return packed
 
 
