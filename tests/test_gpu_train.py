@@ -164,3 +164,19 @@ def test_batch_norm_relu_fused(c, dtype):
     with torch.no_grad():
         ye, yr = ours._rows(x), torch.relu(ref(x))
     assert float((ye.float() - yr.float()).abs().max()) <= tol * max(1.0, float(yr.float().abs().max()))
+
+
+def test_batch_norm_statistics_are_stable():
+    """Mean / variance of rows whose mean is 10^3 standard deviations away from zero (fp32 rows, fp64 reference): the one-pass
+    combination of the per-CTA records is pivoted, so nothing cancels there (a plain E[x^2] - E[x]^2 in fp32 would be off by
+    ~10 % of the variance here)."""
+    from taseg_b200 import ops
+    torch.manual_seed(3)
+    n, c = 200003, 64
+    x = (torch.randn(n, c, device="cuda", dtype=torch.float64) * 0.01 + 10.0).float()
+    mean, invstd = ops.bn_stats(x, 0.0, 0.1, None, None)
+    xd = x.double()
+    mu, var = xd.mean(0), xd.var(0, unbiased=False)
+    err_mean = float(((mean.double() - mu).abs() / 0.01).max())             # in units of the standard deviation
+    err_std = float((invstd.double() * var.sqrt() - 1).abs().max())
+    assert err_mean < 5e-3 and err_std < 5e-3, (err_mean, err_std)
