@@ -84,3 +84,15 @@ def test_gradient_allreduce_matches_single_process_gloo():
         assert torch.allclose(grads2, want, atol=1e-6)
         assert t == 11.0                                    # max over ranks
     assert torch.equal(out[0][0], out[1][0]), "ranks disagree after the all-reduce"
+
+
+def test_lazy_scalar_reads_like_a_float():
+    """utils/lazy.py: what the model's display dictionaries and train_step(sync=False) return instead of loss.item()."""
+    import numpy as np
+    import torch
+    from taseg_b200.utils.lazy import LazyScalar
+    x = LazyScalar(torch.tensor(1.5, requires_grad=True) * 1.0)
+    assert '{:.2f}'.format(x) == '1.50' and repr(x) == '1.5' and float(x) == 1.5 and x.item() == 1.5
+    assert x + 1 == 2.5 and 2 * x == 3.0 and 3 / x == 2.0 and x - 0.5 == 1.0 and x < 2 and x >= 1.5 and max(x, 1.0) is x
+    assert np.isfinite(x) and np.isfinite([x, x]).all() and round(x) == 2 and int(x) == 1 and bool(x)
+    assert x._t is None, "the device tensor is released after the first read"
