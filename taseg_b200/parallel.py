@@ -7,7 +7,7 @@ R/train.py:247-251).  Inference has no data-path collective at all.
 from __future__ import annotations
 
 import math
-from typing import Iterable, List, Optional, Sequence
+from typing import Iterable, List, Optional
 
 import torch
 import torch.distributed as dist
